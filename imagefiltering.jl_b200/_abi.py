@@ -1,0 +1,236 @@
+"""ctypes view of include/b2f.h.
+
+`Library(path)` wraps one shared object exporting the b2f C ABI.  The product package only ever
+instantiates it on `libb2f.so` (see `_lib.py`); the test-suite instantiates a second one on
+`oracle/libb2f_oracle.so`, which exports the same symbols.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+MAXDIM = 4
+MAXSTAGES = 16
+
+# dtypes
+U8, N0F8, I16, I32, I64, F32, F64, U16, U32 = range(9)
+HOST, DEVICE = 0, 1
+REPLICATE, CIRCULAR, SYMMETRIC, REFLECT, FILL, INNER, NOPAD = range(7)
+STAGE_1D, STAGE_DENSE = 0, 1
+TAPS_F64, TAPS_F32, TAPS_INT = 0, 1, 2
+OK, EDIM, EARG, EINEXACT, ECUDA, ENOTSUP, ENOMEM = 0, -1, -2, -3, -4, -5, -6
+
+DTYPE_SIZE = {U8: 1, N0F8: 1, I16: 2, I32: 4, I64: 8, F32: 4, F64: 8, U16: 2, U32: 4}
+NP_TO_DTYPE = {
+    np.dtype(np.uint8): U8, np.dtype(np.int16): I16, np.dtype(np.int32): I32,
+    np.dtype(np.int64): I64, np.dtype(np.float32): F32, np.dtype(np.float64): F64,
+    np.dtype(np.uint16): U16, np.dtype(np.uint32): U32,
+}
+DTYPE_TO_NP = {v: k for k, v in NP_TO_DTYPE.items()}
+DTYPE_TO_NP[N0F8] = np.dtype(np.uint8)
+
+# every symbol include/b2f.h declares (tests check the built library exports all of them)
+SYMBOLS = [
+    "b2f_version", "b2f_last_error", "b2f_is_device_library", "b2f_set_device", "b2f_device_count",
+    "b2f_malloc", "b2f_free", "b2f_host_alloc", "b2f_host_free", "b2f_memcpy_h2d", "b2f_memcpy_d2h",
+    "b2f_sync", "b2f_imfilter", "b2f_imgradients", "b2f_mapwindow_extrema", "b2f_imfilter_slab",
+    "b2f_launch_count", "b2f_reset_launch_count", "b2f_last_path",
+]
+
+
+class b2f_array(C.Structure):
+    _fields_ = [
+        ("ptr", C.c_void_p), ("dtype", C.c_int32), ("ndim", C.c_int32),
+        ("dims", C.c_int64 * MAXDIM), ("origin", C.c_int64 * MAXDIM),
+        ("mem", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
+class b2f_stage(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int32), ("axis", C.c_int32), ("ndim", C.c_int32), ("tap_dtype", C.c_int32),
+        ("len", C.c_int64 * MAXDIM), ("lo", C.c_int64 * MAXDIM), ("taps", C.POINTER(C.c_double)),
+    ]
+
+
+class b2f_border(C.Structure):
+    _fields_ = [
+        ("style", C.c_int32), ("npad", C.c_int32), ("fill", C.c_double),
+        ("lo", C.c_int64 * MAXDIM), ("hi", C.c_int64 * MAXDIM),
+    ]
+
+
+class DimensionMismatch(ValueError):
+    """Julia `DimensionMismatch` (reference src/imfilter.jl:604-615)."""
+
+
+class ArgumentError(ValueError):
+    """Julia `ArgumentError` (reference src/border.jl:147-155)."""
+
+
+class InexactError(ArithmeticError):
+    """Julia `InexactError` (reference src/imfilter.jl:233-254)."""
+
+
+class CudaError(RuntimeError):
+    pass
+
+
+class NotSupportedError(NotImplementedError):
+    """A valid reference call that this library does not accelerate (there is no CPU fallback)."""
+
+
+_EXC = {EDIM: DimensionMismatch, EARG: ArgumentError, EINEXACT: InexactError, ECUDA: CudaError,
+        ENOTSUP: NotSupportedError, ENOMEM: MemoryError}
+
+
+def make_array(ptr: int, dtype: int, dims, origin=None, mem=HOST) -> b2f_array:
+    a = b2f_array()
+    a.ptr = ptr
+    a.dtype = dtype
+    a.ndim = len(dims)
+    if len(dims) > MAXDIM:
+        raise NotSupportedError(f"arrays with more than {MAXDIM} dimensions are not supported")
+    for d in range(MAXDIM):
+        a.dims[d] = dims[d] if d < len(dims) else 1
+        a.origin[d] = (origin[d] if origin is not None else 1) if d < len(dims) else 0
+    a.mem = mem
+    return a
+
+
+def numpy_array_desc(x: np.ndarray, origin=None, dtype=None) -> b2f_array:
+    """Describe a Fortran-contiguous numpy array (axis 0 fastest == Julia dim 1)."""
+    if x.ndim > 1 and not x.flags.f_contiguous:
+        raise ValueError("array must be Fortran-contiguous (Julia memory order)")
+    if x.ndim == 1 and not x.flags.c_contiguous:
+        raise ValueError("vector must be contiguous")
+    dt = NP_TO_DTYPE[x.dtype] if dtype is None else dtype
+    return make_array(x.ctypes.data, dt, x.shape, origin, HOST)
+
+
+class StageList:
+    """Keeps the tap buffers alive next to the ctypes stage array."""
+
+    def __init__(self, stages):
+        # stages: list of dicts {kind, axis, ndim, tap_dtype, len(list), lo(list), taps(np f64, F-order)}
+        n = len(stages)
+        self.n = n
+        self.arr = (b2f_stage * max(n, 1))()
+        self._keep = []
+        for i, s in enumerate(stages):
+            st = self.arr[i]
+            st.kind = s["kind"]
+            st.axis = s.get("axis", 0)
+            st.ndim = s.get("ndim", 0)
+            st.tap_dtype = s.get("tap_dtype", TAPS_F64)
+            taps = np.ascontiguousarray(np.asarray(s["taps"], dtype=np.float64).ravel(order="F"))
+            self._keep.append(taps)
+            for d in range(MAXDIM):
+                st.len[d] = s["len"][d] if d < len(s["len"]) else 1
+                st.lo[d] = s["lo"][d] if d < len(s["lo"]) else 0
+            st.taps = taps.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def make_border(style: int, fill: float = 0.0, lo=None, hi=None) -> b2f_border:
+    b = b2f_border()
+    b.style = style
+    b.fill = float(fill)
+    if lo is not None:
+        b.npad = len(lo)
+        for d in range(len(lo)):
+            b.lo[d] = lo[d]
+            b.hi[d] = hi[d]
+    else:
+        b.npad = 0
+    return b
+
+
+class Library:
+    def __init__(self, path: str):
+        if not os.path.exists(path):
+            raise ImportError(f"b2f shared library not found: {path}")
+        self.path = path
+        self.dll = C.CDLL(path)
+        d = self.dll
+        d.b2f_version.restype = C.c_char_p
+        d.b2f_last_error.restype = C.c_char_p
+        d.b2f_last_path.restype = C.c_char_p
+        d.b2f_launch_count.restype = C.c_int64
+        d.b2f_reset_launch_count.restype = None
+        d.b2f_malloc.argtypes = [C.POINTER(C.c_void_p), C.c_uint64]
+        d.b2f_free.argtypes = [C.c_void_p]
+        d.b2f_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_uint64]
+        d.b2f_host_free.argtypes = [C.c_void_p]
+        d.b2f_memcpy_h2d.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+        d.b2f_memcpy_d2h.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+        d.b2f_set_device.argtypes = [C.c_int]
+        d.b2f_device_count.argtypes = [C.POINTER(C.c_int)]
+        d.b2f_imfilter.argtypes = [
+            C.POINTER(b2f_array), C.POINTER(b2f_array), C.POINTER(b2f_stage), C.c_int32,
+            C.POINTER(b2f_border), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_void_p]
+        d.b2f_imgradients.argtypes = [
+            C.POINTER(b2f_array), C.POINTER(b2f_array), C.c_int32, C.POINTER(b2f_stage), C.c_int32,
+            C.POINTER(b2f_border), C.c_void_p]
+        d.b2f_mapwindow_extrema.argtypes = [
+            C.POINTER(b2f_array), C.POINTER(b2f_array), C.POINTER(b2f_array), C.c_int32,
+            C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(b2f_border), C.c_void_p]
+        d.b2f_imfilter_slab.argtypes = [
+            C.POINTER(b2f_array), C.POINTER(b2f_array), C.POINTER(b2f_stage), C.c_int32,
+            C.POINTER(b2f_border), C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_void_p]
+
+    # -- helpers ---------------------------------------------------------------------------
+    def check(self, rc: int):
+        if rc == OK:
+            return
+        msg = (self.dll.b2f_last_error() or b"").decode()
+        raise _EXC.get(rc, RuntimeError)(msg or f"b2f status {rc}")
+
+    def version(self) -> str:
+        return self.dll.b2f_version().decode()
+
+    def is_device_library(self) -> bool:
+        return bool(self.dll.b2f_is_device_library())
+
+    def last_path(self) -> str:
+        return self.dll.b2f_last_path().decode()
+
+    def launch_count(self) -> int:
+        return int(self.dll.b2f_launch_count())
+
+    def reset_launch_count(self):
+        self.dll.b2f_reset_launch_count()
+
+    # -- raw calls on descriptors -------------------------------------------------------------
+    def imfilter(self, img: b2f_array, out: b2f_array, stages: StageList, border: b2f_border,
+                 roi=None, stream: int = 0):
+        if roi is not None:
+            lo = (C.c_int64 * MAXDIM)(*list(roi[0]) + [0] * (MAXDIM - len(roi[0])))
+            hi = (C.c_int64 * MAXDIM)(*list(roi[1]) + [0] * (MAXDIM - len(roi[1])))
+        else:
+            lo = hi = None
+        self.check(self.dll.b2f_imfilter(C.byref(img), C.byref(out), stages.arr, stages.n,
+                                         C.byref(border), lo, hi, C.c_void_p(stream)))
+
+    def imgradients(self, img: b2f_array, outs, stages: StageList, nstages_each: int,
+                    border: b2f_border, stream: int = 0):
+        arr = (b2f_array * len(outs))(*outs)
+        self.check(self.dll.b2f_imgradients(C.byref(img), arr, len(outs), stages.arr, nstages_each,
+                                            C.byref(border), C.c_void_p(stream)))
+
+    def mapwindow_extrema(self, img: b2f_array, out_min, out_max, interleaved: bool, win_lo, win_hi,
+                          border: b2f_border, stream: int = 0):
+        lo = (C.c_int64 * MAXDIM)(*list(win_lo) + [0] * (MAXDIM - len(win_lo)))
+        hi = (C.c_int64 * MAXDIM)(*list(win_hi) + [0] * (MAXDIM - len(win_hi)))
+        self.check(self.dll.b2f_mapwindow_extrema(
+            C.byref(img), C.byref(out_min) if out_min is not None else None,
+            C.byref(out_max) if out_max is not None else None, 1 if interleaved else 0, lo, hi,
+            C.byref(border), C.c_void_p(stream)))
+
+    def imfilter_slab(self, img: b2f_array, out: b2f_array, stages: StageList, border: b2f_border,
+                      global_last_dim: int, slab_first: int, halo_lo: int, halo_hi: int,
+                      stream: int = 0):
+        self.check(self.dll.b2f_imfilter_slab(C.byref(img), C.byref(out), stages.arr, stages.n,
+                                              C.byref(border), global_last_dim, slab_first, halo_lo,
+                                              halo_hi, C.c_void_p(stream)))

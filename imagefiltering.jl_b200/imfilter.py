@@ -1,0 +1,381 @@
+"""imfilter / imfilter! / imgradients — host-side mirror of the reference's dispatch ladder
+(src/imfilter.jl:2-49 `imfilter`, :204-254 `imfilter!`, src/specialty.jl:39-53 `imgradients`).
+
+Everything here is metadata work (steps 1-5 of the reference: output eltype, kernel
+canonicalisation, default border, allocation, resource check).  All arithmetic happens behind the
+C ABI of libb2f.so (include/b2f.h); there is no numpy/CPU computation of filter results here.
+
+Julia's `imfilter!` is spelled `imfilter_` (a trailing `!` is not a Python identifier).
+Array convention: numpy axis k == Julia dimension k+1; data is handed to the library in Julia
+(column-major) memory order, so C-ordered inputs are copied to Fortran order first.
+"""
+from __future__ import annotations
+
+import warnings
+
+import numpy as np
+
+from . import _abi
+from ._abi import ArgumentError, DimensionMismatch, NotSupportedError
+from .border import AbstractBorder, Fill, Inner, NoPad, Pad, borderinstance
+from .device import DeviceArray
+from .kernel import Laplacian
+from .kernelfactors import ReshapedOneD
+from .n0f8 import N0f8Array
+from .offsetarrays import OffsetArray, centered
+from .resources import AbstractResource, Alg, CUDALibs, FIR, FIRTiled
+
+STAGE_LAPLACIAN = 2
+
+
+# ---- step 1: output element type (src/imfilter.jl:1131-1154) -----------------------------------
+def _img_eltype(img):
+    if isinstance(img, N0f8Array):
+        return "n0f8"
+    if isinstance(img, DeviceArray):
+        return "n0f8" if img.dtype == _abi.N0F8 else _abi.DTYPE_TO_NP[img.dtype]
+    if isinstance(img, OffsetArray):
+        return _img_eltype(img.parent)
+    return np.asarray(img).dtype
+
+
+def _mul_type(S, K):
+    """typeof(zero(S)*zero(K) + zero(S)*zero(K)) for the element types this package handles."""
+    K = np.dtype(K)
+    if isinstance(S, str):  # N0f8
+        if K.kind == "f":
+            return K
+        return np.dtype(np.float32)  # floattype(N0f8); integer taps on N0f8 data (unpinned corner)
+    S = np.dtype(S)
+    if S.kind == "b":
+        S = np.dtype(np.int8)
+    if K.kind == "b":
+        K = np.dtype(np.int64)
+    if S.kind == "f" and K.kind in "iu":
+        return S
+    if K.kind == "f" and S.kind in "iu":
+        return K
+    return np.result_type(S, K)
+
+
+def _kernel_dtype(k):
+    if isinstance(k, Laplacian):
+        return None
+    if isinstance(k, (ReshapedOneD, OffsetArray)):
+        return k.dtype
+    return np.asarray(k).dtype
+
+
+def filter_type(img, kernel):
+    S = img if isinstance(img, (np.dtype, type, str)) else _img_eltype(img)
+    ks = kernel if isinstance(kernel, tuple) else (kernel,)
+    T = None
+    for k in ks:
+        if isinstance(k, Laplacian):  # src/imfilter.jl:1134-1139
+            if isinstance(S, str):
+                t = np.dtype(np.float32)
+            else:
+                s = np.dtype(S)
+                t = {"u1": np.dtype(np.int16), "u2": np.dtype(np.int32), "u4": np.dtype(np.int64)}.get(
+                    s.str[1:], np.dtype(np.int8) if s.kind == "b" else s)
+        else:
+            t = _mul_type(S, _kernel_dtype(k))
+        T = t if T is None else np.promote_types(T, t)
+    return T if T is not None else (np.dtype(np.float32) if isinstance(S, str) else np.dtype(S))
+
+
+# ---- step 2: kernel canonicalisation (src/imfilter.jl:1156-1196) ---------------------------------
+def _kernelshift(k):
+    if isinstance(k, OffsetArray):
+        return k
+    warnings.warn("assuming that the origin is at the center of the kernel; to avoid this warning, "
+                  "call `centered(kernel)` or use an OffsetArray", DeprecationWarning, stacklevel=4)
+    return centered(np.asarray(k))
+
+
+def factorkernel(kernel, integer_path=False):
+    if isinstance(kernel, (Laplacian, ReshapedOneD)):
+        return (kernel,)
+    ks = _kernelshift(kernel)
+    if ks.ndim != 2 or integer_path or ks.dtype.kind in "iub":
+        return (ks,)
+    # factorstridedkernel: LAPACK svd, separable iff all but the first singular value < sqrt(eps)
+    U, S, Vt = np.linalg.svd(ks.parent.astype(np.float64 if ks.dtype != np.float32 else np.float32))
+    eps = np.sqrt(np.finfo(S.dtype).eps)
+    if np.any(np.abs(S[1:]) >= eps):
+        dummy = OffsetArray.with_first(np.ones((1, 1), dtype=np.int64), (0, 0))
+        return (dummy, ks)
+    ss = np.sqrt(S[0])
+    u = (ss * U[:, :1]).astype(S.dtype)
+    v = (ss * Vt[:1, :]).astype(S.dtype)
+    return (OffsetArray.with_first(u, (ks.first[0], 0)), OffsetArray.with_first(v, (0, ks.first[1])))
+
+
+def _tap_dtype(dt):
+    dt = np.dtype(dt)
+    if dt.kind == "f":
+        return _abi.TAPS_F32 if dt == np.float32 else _abi.TAPS_F64
+    if dt.kind in "iub":
+        return _abi.TAPS_INT
+    raise NotSupportedError(f"kernel eltype {dt} is not supported")
+
+
+def build_stages(kernel, ndim):
+    """ProcessedKernel tuple -> list of stage dicts for _abi.StageList."""
+    stages = []
+    for k in kernel:
+        if isinstance(k, Laplacian):
+            if k.ndim != ndim:
+                raise DimensionMismatch(f"Laplacian has {k.ndim} dims, image has {ndim}")
+            stages.append(dict(kind=STAGE_LAPLACIAN, ndim=ndim, tap_dtype=_abi.TAPS_INT,
+                               len=[3 if f else 1 for f in k.flags], lo=[-1 if f else 0 for f in k.flags],
+                               taps=np.zeros(1)))
+            continue
+        if isinstance(k, ReshapedOneD):
+            if k.N != ndim:
+                raise DimensionMismatch(f"kernel factor is for {k.N}-d arrays, image has {ndim} dims")
+            ln = [1] * ndim
+            lo = [0] * ndim
+            ln[k.Npre] = k.data.shape[0]
+            lo[k.Npre] = k.data.first[0]
+            stages.append(dict(kind=_abi.STAGE_1D, axis=k.Npre, ndim=ndim, tap_dtype=_tap_dtype(k.dtype),
+                               len=ln, lo=lo, taps=k.data.parent))
+            continue
+        if isinstance(k, OffsetArray):
+            p, first = k.parent, list(k.first)
+        else:  # plain array inside a tuple: axes are 1:n (samedims -> reshape, no centring)
+            p = np.asarray(k)
+            first = [1] * p.ndim
+        if p.ndim > ndim:
+            raise DimensionMismatch(f"kernel has {p.ndim} dims, image has {ndim}")
+        extra = ndim - p.ndim
+        shape = list(p.shape) + [1] * extra
+        first = first + [0 if isinstance(k, OffsetArray) else 1] * extra
+        ext = [d for d in range(ndim) if shape[d] > 1]
+        td = _tap_dtype(p.dtype)
+        if len(ext) <= 1 and all(first[d] == 0 for d in range(ndim) if d not in ext):
+            ax = ext[0] if ext else 0
+            stages.append(dict(kind=_abi.STAGE_1D, axis=ax, ndim=ndim, tap_dtype=td, len=shape, lo=first,
+                               taps=p.reshape(-1, order="F")))
+        else:
+            stages.append(dict(kind=_abi.STAGE_DENSE, ndim=ndim, tap_dtype=td, len=shape, lo=first,
+                               taps=np.asarray(p).reshape(shape, order="F")))
+    return stages
+
+
+def kernel_extent(stages, ndim):
+    """accumulate_padding (src/border.jl:614-642): summed first/last tap index per axis."""
+    first = [0] * ndim
+    last = [0] * ndim
+    for s in stages:
+        for d in range(ndim):
+            if s["kind"] == _abi.STAGE_1D and d != s["axis"]:
+                continue
+            first[d] += s["lo"][d]
+            last[d] += s["lo"][d] + s["len"][d] - 1
+    return first, last
+
+
+# ---- array plumbing -----------------------------------------------------------------------------
+def _as_input(img):
+    """-> (descriptor, ndim, first, shape, keepalive)"""
+    if isinstance(img, DeviceArray):
+        return img.desc(), img.ndim, img.origin, img.dims, img
+    first = None
+    if isinstance(img, OffsetArray):
+        first, img = img.first, img.parent
+    dt = None
+    if isinstance(img, N0f8Array):
+        img, dt = img.raw, _abi.N0F8
+    a = np.asarray(img)
+    if a.dtype == np.bool_:
+        a = a.astype(np.uint8)
+    if a.dtype not in _abi.NP_TO_DTYPE:
+        raise NotSupportedError(f"image eltype {a.dtype} is not supported")
+    a = np.asfortranarray(a) if a.ndim > 1 else np.ascontiguousarray(a)
+    first = tuple(first) if first is not None else (1,) * a.ndim
+    return _abi.numpy_array_desc(a, first, dt), a.ndim, first, a.shape, a
+
+
+def _as_output(out):
+    if isinstance(out, DeviceArray):
+        return out.desc(), out
+    first = None
+    if isinstance(out, OffsetArray):
+        first, out = out.first, out.parent
+    if not isinstance(out, np.ndarray):
+        raise TypeError("out must be a numpy array, OffsetArray or DeviceArray")
+    if out.ndim > 1 and not out.flags.f_contiguous:
+        raise ValueError("out must be Fortran-contiguous (Julia memory order)")
+    return _abi.numpy_array_desc(out, first), out
+
+
+def allocate_output(T, img_first, img_shape, stages, border):
+    """src/border.jl:686-696."""
+    ndim = len(img_shape)
+    T = np.dtype(T)
+    if isinstance(border, Inner):
+        if border.lo:
+            if len(border.lo) != ndim:
+                raise DimensionMismatch(f"dimensionality of img and the border must agree, got {ndim} and {len(border.lo)}")
+            lo = [f + l for f, l in zip(img_first, border.lo)]
+            hi = [f + n - 1 - h for f, n, h in zip(img_first, img_shape, border.hi)]
+        else:
+            kf, kl = kernel_extent(stages, ndim)
+            lo = [max(f, f - a) for f, a in zip(img_first, kf)]
+            hi = [min(f + n - 1, f + n - 1 - b) for f, n, b in zip(img_first, img_shape, kl)]
+        shape = tuple(max(0, h - l + 1) for l, h in zip(lo, hi))
+        return OffsetArray.with_first(np.empty(shape, dtype=T, order="F"), lo)
+    arr = np.empty(img_shape, dtype=T, order="F")
+    if any(f != 1 for f in img_first):
+        return OffsetArray.with_first(arr, img_first)
+    return arr
+
+
+# ---- argument ladder ------------------------------------------------------------------------------
+def _is_type(x):
+    return isinstance(x, (type, np.dtype)) or (isinstance(x, str) and x in ("float32", "float64"))
+
+
+def _check_resource(r):
+    if not isinstance(r, CUDALibs):
+        raise NotSupportedError(
+            f"{r!r}: this package accelerates CUDALibs(Algorithm.FIR()) only and has no CPU execution path")
+    if not isinstance(r.settings, (FIR, FIRTiled)):
+        raise NotSupportedError(f"{r!r}: only Algorithm.FIR() is implemented on the device (FFT/IIR are out of scope)")
+    return r
+
+
+def _split_tail(args):
+    border, alg = "replicate", None
+    rest = list(args)
+    if rest and isinstance(rest[0], (str, AbstractBorder)):
+        border = rest.pop(0)
+    if rest and isinstance(rest[0], Alg):
+        alg = rest.pop(0)
+    if rest:
+        raise TypeError(f"no method matching imfilter(…, {rest})")
+    return borderinstance(border), alg
+
+
+def imfilter(*args, _library=None):
+    """imfilter([r], [T], img, kernel, [border], [alg]) -> filtered array   (src/imfilter.jl:2-49)."""
+    args = list(args)
+    r = args.pop(0) if args and isinstance(args[0], AbstractResource) else None
+    T = args.pop(0) if args and _is_type(args[0]) else None
+    if len(args) < 2:
+        raise TypeError("imfilter needs at least (img, kernel)")
+    img, kernel = args[0], args[1]
+    border, alg = _split_tail(args[2:])
+    if r is not None and alg is not None:
+        raise TypeError("MethodError: a resource and an algorithm cannot both be given")
+    r = _resolve_resource(r, alg)
+    if T is None:
+        T = filter_type(img, kernel)
+    T = np.dtype(T)
+    S = _img_eltype(img)
+    if not isinstance(kernel, tuple):
+        kd = _kernel_dtype(kernel)
+        int_path = (T.kind in "iu" and not isinstance(S, str) and np.dtype(S).kind in "iub"
+                    and kd is not None and np.dtype(kd).kind in "iub")
+        kernel = factorkernel(kernel, int_path)
+    desc, ndim, first, shape, keep = _as_input(img)
+    stages = build_stages(kernel, ndim)
+    out = allocate_output(T, first, shape, stages, border)
+    _run(r, out, desc, ndim, stages, border, None, _library)
+    return out
+
+
+def _resolve_resource(r, alg):
+    if r is None:
+        if alg is not None and not isinstance(alg, (FIR, FIRTiled)):
+            raise NotSupportedError(f"{alg!r} is outside the accelerated FIR path")
+        return CUDALibs(FIR())
+    return _check_resource(r)
+
+
+def imfilter_(*args, _library=None):
+    """imfilter!([r], out, img, kernel, [border], [alg | inds])   (src/imfilter.jl:204-254, 367-395)."""
+    args = list(args)
+    r = args.pop(0) if args and isinstance(args[0], AbstractResource) else None
+    if len(args) < 3:
+        raise TypeError("imfilter_ needs at least (out, img, kernel)")
+    out, img, kernel = args[0], args[1], args[2]
+    rest = args[3:]
+    inds = None
+    if rest and isinstance(rest[-1], (tuple, list)) and rest[-1] and isinstance(rest[-1][0], (range, tuple, list)):
+        inds = rest.pop()
+    border, alg = _split_tail(rest)
+    if r is not None and alg is not None:
+        raise TypeError("MethodError: a resource and an algorithm cannot both be given")
+    r = _resolve_resource(r, alg)
+    if not isinstance(kernel, tuple):
+        kernel = factorkernel(kernel)
+    desc, ndim, first, shape, keep = _as_input(img)
+    stages = build_stages(kernel, ndim)
+    roi = None
+    if inds is not None:
+        lo = [(i.start if isinstance(i, range) else i[0]) for i in inds]
+        hi = [(i.stop - 1 if isinstance(i, range) else i[1]) for i in inds]
+        roi = (lo, hi)
+    _run(r, out, desc, ndim, stages, border, roi, _library)
+    return out
+
+
+def _run(r, out, img_desc, ndim, stages, border, roi, library):
+    from ._lib import lib
+    L = library if library is not None else lib()
+    odesc, keep = _as_output(out)
+    if odesc.ndim != ndim:
+        raise DimensionMismatch(f"out has {odesc.ndim} dims, img has {ndim}")
+    sl = _abi.StageList(stages)
+    L.imfilter(img_desc, odesc, sl, border.to_abi(ndim), roi)
+
+
+def imgradients(img, kernelfun, border="replicate", *, _library=None, T=None):
+    """imgradients(img, kernelfun, border) -> tuple of N gradient arrays  (src/specialty.jl:39-53).
+    One fused device launch reads `img` once for all N planes."""
+    from ._lib import lib
+    L = _library if _library is not None else lib()
+    border = borderinstance(border)
+    desc, ndim, first, shape, keep = _as_input(img)
+    extended = tuple(n > 1 for n in shape)
+    planes = []
+    all_stages = []
+    nst = None
+    for d in range(1, ndim + 1):
+        kern = kernelfun(extended, d)
+        if not isinstance(kern, tuple):
+            kern = factorkernel(kern)
+        st = build_stages(kern, ndim)
+        if nst is None:
+            nst = len(st)
+        elif nst != len(st):
+            raise NotSupportedError("gradient kernels with differing stage counts")
+        Td = np.dtype(T) if T is not None else filter_type(img, kern)
+        planes.append(allocate_output(Td, first, shape, st, border))
+        all_stages += st
+    odescs = [_as_output(p)[0] for p in planes]
+    L.imgradients(desc, odescs, _abi.StageList(all_stages), nst, border.to_abi(ndim))
+    return tuple(planes)
+
+
+def padarray(*args, _library=None):
+    """padarray([T], img, border) (src/border.jl:324-352) — on this package the padded copy is
+    produced by the device library (a cascade of zero stages evaluated over the padded axes)."""
+    args = list(args)
+    T = args.pop(0) if _is_type(args[0]) else None
+    img, border = args
+    border = borderinstance(border)
+    if not isinstance(border, (Pad, Fill)) or not border.lo:
+        raise ArgumentError(f"{border!r} lacks the proper padding sizes for an array with {np.ndim(img) if not hasattr(img, 'ndim') else img.ndim} dimensions")
+    desc, ndim, first, shape, keep = _as_input(img)
+    if len(border.lo) != ndim:
+        raise ArgumentError(f"{border!r} lacks the proper padding sizes for an array with {ndim} dimensions")
+    S = _img_eltype(img)
+    T = np.dtype(T) if T is not None else (np.dtype(np.float32) if isinstance(S, str) else np.dtype(S))
+    lo = [f - l for f, l in zip(first, border.lo)]
+    oshape = tuple(n + l + h for n, l, h in zip(shape, border.lo, border.hi))
+    out = OffsetArray.with_first(np.empty(oshape, dtype=T, order="F"), lo)
+    _run(None, out, desc, ndim, [], border, None, _library)
+    return out

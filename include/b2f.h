@@ -1,0 +1,199 @@
+/* b2f.h — C ABI of the B200-native FIR / running-extrema hot path.
+ *
+ * This is the drop-in boundary for JuliaImages/ImageFiltering.jl's FIR path.  A Julia shim
+ *  reaches these entry points by `ccall` from new methods of
+ *     imfilter!(r::CUDALibs{<:Algorithm.FIR}, out, img, kernel::ProcessedKernel, border)
+ * which sit in front of the reference's own border/scheduler/loop methods
+ * (reference src/imfilter.jl:321-341 [pad], :367-457 [scheduler], :592-739 [loops]) and of
+ *     mapwindow(extrema|minimum|maximum, img, window)      (reference src/mapwindow.jl:75-121,337-481).
+ *
+ * Two libraries export this same ABI:
+ *   libb2f.so         — the product: CUDA sm_100a kernels, no CPU execution path at all.
+ *   libb2f_oracle.so  — TEST INFRASTRUCTURE: a single-threaded CPU restatement of the reference
+ *                       algorithm (oracle/), used only as the parity checker and CPU baseline.
+ *
+ * Conventions (all follow the reference):
+ *   - arrays are dense column-major ("Julia order"): dims[0] is the fastest axis;
+ *   - every array carries `origin[d]` = the index of its first element along axis d
+ *     (Julia `first(axes(A,d))`; 1 for a plain Array, anything for an OffsetArray);
+ *   - filtering is CORRELATION: out[I] = sum_J img[I+J] * kernel[J]   (docs/src/kernels.md:39-50);
+ *   - a kernel stage carries `lo[d]` = index of its first tap along axis d (−h for a centred kernel);
+ *   - stages of a cascade are applied in array order (src/imfilter.jl:438-446);
+ *   - `out`'s axes select the computed region (src/imfilter.jl:604-615);
+ *   - semantics of a cascade = "pad the input ONCE by the accumulated extent of the whole
+ *     cascade, then run every stage as a valid filter over a shrinking region"
+ *     (src/imfilter.jl:331-341,385-395,438-446; src/border.jl:614-642,657-684).
+ */
+#ifndef B2F_H
+#define B2F_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2F_MAXDIM 4
+#define B2F_MAXSTAGES 16
+
+/* element types.  N0F8 = FixedPointNumbers.N0f8: raw byte i means the value i/255
+ * (conversion happens when the reference pads: src/border.jl:343). */
+enum {
+    B2F_U8 = 0,
+    B2F_N0F8 = 1,
+    B2F_I16 = 2,
+    B2F_I32 = 3,
+    B2F_I64 = 4,
+    B2F_F32 = 5,
+    B2F_F64 = 6,
+    B2F_U16 = 7,
+    B2F_U32 = 8
+};
+
+/* where `ptr` lives */
+enum { B2F_HOST = 0, B2F_DEVICE = 1 };
+
+/* border styles.  src/border.jl:564-590 (Pad styles), :383-384 (Fill), :547-550 (Inner),
+ * src/imfilter.jl:256-278 (NoPad). */
+enum {
+    B2F_REPLICATE = 0,
+    B2F_CIRCULAR = 1,
+    B2F_SYMMETRIC = 2,
+    B2F_REFLECT = 3,
+    B2F_FILL = 4,
+    B2F_INNER = 5,
+    B2F_NOPAD = 6
+};
+
+/* stage kinds: a 1-D factor acting along one axis (KernelFactors.ReshapedOneD,
+ * src/kernelfactors.jl:52-131), a dense N-d block (src/imfilter.jl:624-669), or the opaque
+ * Kernel.Laplacian stencil (src/kernel.jl:341-391, loop src/specialty.jl:3-16): len[d] = 3 on the
+ * flagged axes and 1 elsewhere, lo[d] = -1 / 0, taps ignored. */
+enum { B2F_STAGE_1D = 0, B2F_STAGE_DENSE = 1, B2F_STAGE_LAPLACIAN = 2 };
+
+/* tap element type as seen by the reference's accumulator typing (src/imfilter.jl:630-632,
+ * src/utils.jl:122-133).  Taps are always PASSED as double. */
+enum { B2F_TAPS_F64 = 0, B2F_TAPS_F32 = 1, B2F_TAPS_INT = 2 };
+
+/* status codes; the Julia shim maps them back to the reference's exception types */
+enum {
+    B2F_OK = 0,
+    B2F_EDIM = -1,     /* DimensionMismatch   (src/imfilter.jl:604-615) */
+    B2F_EARG = -2,     /* ArgumentError       (src/border.jl:147-155,250-262) */
+    B2F_EINEXACT = -3, /* InexactError        (narrowing store, src/imfilter.jl:233-254) */
+    B2F_ECUDA = -4,    /* CUDA runtime failure */
+    B2F_ENOTSUP = -5,  /* valid reference call that this library does not accelerate */
+    B2F_ENOMEM = -6
+};
+
+typedef struct {
+    void *ptr;
+    int32_t dtype;
+    int32_t ndim;
+    int64_t dims[B2F_MAXDIM];
+    int64_t origin[B2F_MAXDIM];
+    int32_t mem;
+    int32_t reserved;
+} b2f_array;
+
+typedef struct {
+    int32_t kind;               /* B2F_STAGE_1D | B2F_STAGE_DENSE */
+    int32_t axis;               /* 1-D: the axis (0-based) the taps act on */
+    int32_t ndim;               /* dense: number of axes of the block (== array ndim) */
+    int32_t tap_dtype;          /* B2F_TAPS_* */
+    int64_t len[B2F_MAXDIM];    /* taps per axis (1-D: only len[axis] is read) */
+    int64_t lo[B2F_MAXDIM];     /* index of the first tap per axis (1-D: only lo[axis]) */
+    const double *taps;         /* HOST pointer, column-major, prod(len) values */
+} b2f_stage;
+
+typedef struct {
+    int32_t style;              /* B2F_REPLICATE … B2F_NOPAD */
+    int32_t npad;               /* 0: derive the padding from the kernel (Pad{0}, Fill{T,0}, Inner{0});
+                                   ndim: explicit lo/hi below (Pad{N}/Fill{T,N}/Inner{N}) */
+    double fill;                /* B2F_FILL: the value, in image-value units */
+    int64_t lo[B2F_MAXDIM];
+    int64_t hi[B2F_MAXDIM];
+} b2f_border;
+
+/* ---- library-level ---------------------------------------------------------------------- */
+const char *b2f_version(void);
+/* thread-local message for the last non-OK status returned on this thread */
+const char *b2f_last_error(void);
+/* 1 for libb2f.so (CUDA), 0 for the oracle library */
+int b2f_is_device_library(void);
+
+/* ---- device memory helpers (so the Julia side needs no CUDA.jl) --------------------------- */
+int b2f_set_device(int device);
+int b2f_device_count(int *count);
+int b2f_malloc(void **dptr, uint64_t bytes);
+int b2f_free(void *dptr);
+int b2f_host_alloc(void **hptr, uint64_t bytes);   /* pinned */
+int b2f_host_free(void *hptr);
+int b2f_memcpy_h2d(void *dptr, const void *hptr, uint64_t bytes);
+int b2f_memcpy_d2h(void *hptr, const void *dptr, uint64_t bytes);
+int b2f_sync(void);
+
+/* ---- the hot path ------------------------------------------------------------------------ */
+
+/* imfilter!(r, out, img, kernel::ProcessedKernel, border)      replaces src/imfilter.jl:321-341 and
+ * everything below it.  `roi_lo/roi_hi` (inclusive index bounds, may be NULL = axes(out)) is the
+ * `inds` argument of the NoPad form (src/imfilter.jl:367-395).  `stream` is a cudaStream_t (NULL =
+ * default stream).  Host arrays are staged through pinned memory and the call is synchronous;
+ * device arrays are used in place and the call is asynchronous on `stream`.
+ *
+ * Arithmetic follows the reference's typing keyed on eltype(out):
+ *   out F64           — double accumulate, separate multiply and add in tap order (bit-exact
+ *                       against the oracle whenever every axis is filtered by at most one stage);
+ *   out F32           — float FMA accumulate (within 1e-5 * prod_stage(sum|k|) * max|img|);
+ *   out integer types — int64 accumulate; needs integer taps and integer input; a result that
+ *                       does not fit eltype(out) gives B2F_EINEXACT.                            */
+int b2f_imfilter(const b2f_array *img, const b2f_array *out,
+                 const b2f_stage *stages, int32_t nstages,
+                 const b2f_border *border,
+                 const int64_t *roi_lo, const int64_t *roi_hi,
+                 void *stream);
+
+/* imgradients(img, kernelfun, border)  (src/specialty.jl:39-53): `nplanes` independent cascades
+ * of `nstages_each` stages, all reading the same `img`; plane p uses
+ * stages[p*nstages_each … (p+1)*nstages_each-1] and writes outs[p].  The product library reads
+ * img from HBM once for all planes. */
+int b2f_imgradients(const b2f_array *img, const b2f_array *outs, int32_t nplanes,
+                    const b2f_stage *stages, int32_t nstages_each,
+                    const b2f_border *border, void *stream);
+
+/* mapwindow(extrema|minimum|maximum, img, window; border)  (src/mapwindow.jl:75-121,337-481).
+ * The window along axis d covers indices [i+win_lo[d], i+win_hi[d]].  out_min / out_max may each
+ * be NULL; `interleaved` != 0 writes Tuple{T,T} (min,max) pairs into out_min (out_max ignored),
+ * which is the memory layout of the reference's `Array{Tuple{T,T}}` result.
+ * Border: any Pad style == truncation of the window at the array ends (src/mapwindow.jl:310-317);
+ * B2F_FILL includes the fill value where the window leaves the array; B2F_INNER restricts the
+ * outputs to out's axes, which must lie in the interior. */
+int b2f_mapwindow_extrema(const b2f_array *img, const b2f_array *out_min, const b2f_array *out_max,
+                          int32_t interleaved,
+                          const int64_t *win_lo, const int64_t *win_hi,
+                          const b2f_border *border, void *stream);
+
+/* Slab form used by the sharded 3-D path: `img` holds this rank's planes
+ * [slab_first, slab_first + dims[ndim-1]) of a volume whose last axis has `global_last_dim` planes,
+ * PLUS `halo_lo` planes below and `halo_hi` planes above that were received from the neighbouring
+ * ranks (or are absent, = 0, at a global face, where the border style applies).  `out` holds only
+ * the owned planes. */
+int b2f_imfilter_slab(const b2f_array *img, const b2f_array *out,
+                      const b2f_stage *stages, int32_t nstages,
+                      const b2f_border *border,
+                      int64_t global_last_dim, int64_t slab_first,
+                      int64_t halo_lo, int64_t halo_hi,
+                      void *stream);
+
+/* number of CUDA kernels launched by this library on the calling thread since the last reset
+ * (the oracle library always reports 0) */
+int64_t b2f_launch_count(void);
+void b2f_reset_launch_count(void);
+/* name of the kernel family the last b2f_imfilter/b2f_imgradients/b2f_mapwindow_extrema call
+ * on this thread dispatched to ("sep2d", "sep3d", "dense2d", "generic", "extrema", …) */
+const char *b2f_last_path(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2F_H */

@@ -1,0 +1,474 @@
+"""The reference's own tests for the FIR / min-max path, re-expressed against this package's API
+(reference test/border.jl, test/nd.jl, test/2d.jl, test/cascade.jl, test/gradient.jl,
+test/mapwindow.jl; citations at each check).  Every check takes `lib`:
+  * the CPU oracle Library  -> pins the oracle against the reference's goldens (CPU, `-m "not gpu"`)
+  * None                    -> the product CUDA library through the same host code (`-m gpu`)
+"""
+import json
+import os
+import warnings
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+with open(os.path.join(HERE, "golden", "reference_goldens.json")) as f:
+    G = json.load(f)
+
+BORDERS = ("replicate", "circular", "symmetric", "reflect")
+
+
+def approx(a, b, rtol=None, atol=0.0):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    if rtol is None:  # Julia isapprox default: rtol = sqrt(eps) of the narrower type, norm-wise
+        rtol = np.sqrt(np.finfo(np.float32).eps) if False else 1.5e-8
+    return np.linalg.norm((a - b).ravel()) <= max(atol, rtol * max(np.linalg.norm(a.ravel()), np.linalg.norm(b.ravel())))
+
+
+def approx32(a, b):
+    return approx(a, b, rtol=np.sqrt(np.finfo(np.float32).eps))
+
+
+# ---- test/border.jl:35-206 ----------------------------------------------------------------------
+def check_padarray(ifb, lib):
+    g = G["pad_5x5"]
+    A = np.array(g["A"], dtype=np.int64)
+    for Ain, off in ((A, 0), (ifb.OffsetArray(A, -1, -1), -1)):
+        for style in BORDERS:
+            r = ifb.padarray(Ain, ifb.Pad(style, g["lo"], g["hi"]), _library=lib)
+            assert r.first == (-1 + off, -1 + off)
+            assert np.array_equal(r.parent, np.array(g[style])), style
+        r = ifb.padarray(Ain, ifb.Fill(0, g["lo"], g["hi"]), _library=lib)
+        assert np.array_equal(r.parent, np.array(g["fill0"]))
+    g = G["pad_2x2_by3"]
+    A = np.array(g["A"], dtype=np.int64)
+    for style in BORDERS:
+        r = ifb.padarray(A, ifb.Pad(style, g["lo"], g["hi"]), _library=lib)
+        assert r.first == (-2, -2)
+        assert np.array_equal(r.parent, np.array(g[style])), style
+        assert np.array_equal(ifb.padarray(A, ifb.Pad(style, (0, 0), (0, 0)), _library=lib).parent, A)
+    for c in G["pad_asym"]["cases"]:
+        A = np.array(c["A"], dtype=np.int64)
+        b = ifb.Fill(c["fill"], c["lo"], c["hi"]) if c["style"] == "fill" else ifb.Pad(c["style"], c["lo"], c["hi"])
+        r = ifb.padarray(A, b, _library=lib)
+        assert np.array_equal(r.parent, np.array(c["out"])), c
+        assert r.first == tuple(1 - l for l in c["lo"])
+    # error behaviour (test/border.jl:87-94)
+    A = np.arange(1, 26).reshape(5, 5, order="F")
+    for b in (ifb.Fill(0), ifb.Pad("replicate"), ifb.Pad("circular", (1, 1, 1), (1, 1, 1))):
+        try:
+            ifb.padarray(A, b, _library=lib)
+        except ifb.ArgumentError as e:
+            assert "lacks the proper padding" in str(e)
+        else:
+            raise AssertionError("expected ArgumentError")
+    # float eltype and N-d (test/border.jl:207-231 style): 3-d replicate of trues
+    T3 = np.ones((3, 3, 3), dtype=np.uint8)
+    r = ifb.padarray(T3, ifb.Pad("symmetric", (1, 1, 1), (2, 2, 2)), _library=lib)
+    assert r.shape == (6, 6, 6) and np.all(r.parent == 1)
+
+
+# ---- test/nd.jl:14-75 ----------------------------------------------------------------------------
+def check_1d(ifb, lib):
+    g = G["nd_1d"]
+    img = np.arange(1, 9, dtype=np.int64)
+    kern = ifb.centered(np.array([1 / 3, 1 / 3, 1 / 3]))
+    imgf = ifb.imfilter(img, kern, _library=lib)
+    assert imgf.dtype == np.float64
+    r = ifb.CUDALibs(ifb.Algorithm.FIR())
+    for call in (
+        lambda: ifb.imfilter(img, kern, "replicate", _library=lib),
+        lambda: ifb.imfilter(img, (kern,), _library=lib),
+        lambda: ifb.imfilter(img, (kern,), "replicate", ifb.Algorithm.FIR(), _library=lib),
+        lambda: ifb.imfilter(np.float64, img, kern, _library=lib),
+        lambda: ifb.imfilter(np.float64, img, (kern,), "replicate", _library=lib),
+        lambda: ifb.imfilter(r, img, kern, _library=lib),
+        lambda: ifb.imfilter(r, np.float64, img, (kern,), "replicate", _library=lib),
+    ):
+        assert np.array_equal(call(), imgf)
+    try:  # MethodError for r + alg (test/nd.jl:36-37,47)
+        ifb.imfilter(r, img, (kern,), "replicate", ifb.Algorithm.FIR(), _library=lib)
+    except TypeError:
+        pass
+    else:
+        raise AssertionError("expected a MethodError analogue")
+    out = np.empty(8, dtype=np.float64)
+    assert np.array_equal(ifb.imfilter_(out, img, kern, _library=lib), imgf)
+    assert np.array_equal(ifb.imfilter_(r, out, img, (kern,), "replicate", _library=lib), imgf)
+
+    k1 = ifb.OffsetArray.with_first(np.array(g["k1"]), (g["k1_first"],))
+    k2 = ifb.OffsetArray.with_first(np.array(g["k2"]), (g["k2_first"],))
+    assert approx(ifb.imfilter(img, (k1,), _library=lib), g["k1_out"])
+    kc = ifb.centered(np.array([1]))
+    assert approx(ifb.imfilter(img, (kc, k1), _library=lib), g["k1_out"])
+    assert approx(ifb.imfilter(img, (k1, kc), _library=lib), g["k1_out"])
+    # same-axis cascade == pad once, then three Inner stages (test/nd.jl:58-69)
+    casc = ifb.imfilter(img, (k1, k2, k1), _library=lib)
+    A0 = ifb.padarray(img, ifb.Pad("replicate", (g["cascade_pad"]["lo"],), (g["cascade_pad"]["hi"],)), _library=lib)
+    A1 = ifb.imfilter(A0, k1, ifb.Inner(), _library=lib)
+    assert A1.first == (g["A1_first"],) and approx(A1.parent, g["A1"])
+    A2 = ifb.imfilter(A1, k2, ifb.Inner(), _library=lib)
+    assert A2.first == (g["A2_first"],) and approx(A2.parent, g["A2"])
+    A3 = ifb.imfilter(A2, k1, ifb.Inner(), _library=lib)
+    assert approx(casc, A3.parent) and casc.shape == img.shape
+    assert approx(casc, [2.53125, 3.5, 4.5, 5.5, 6.46875, 7.28125, 7.78125, 7.96875])
+
+
+# ---- test/nd.jl:49-56, 118-126 ------------------------------------------------------------------
+def check_widening(ifb, lib):
+    v = np.full(10, 0xFF, dtype=np.uint8)
+    kern = ifb.centered(np.full(3, 0xFF, dtype=np.uint8))
+    try:
+        ifb.imfilter(v, kern, _library=lib)
+    except ifb.InexactError:
+        pass
+    else:
+        raise AssertionError("expected InexactError")
+    vout = ifb.imfilter(np.uint32, v, kern, _library=lib)
+    assert vout.dtype == np.uint32 and np.all(vout == G["nd_1d"]["widen_u32"]["value"])
+    img = np.full((10, 10), np.iinfo(np.int16).max, dtype=np.int16)
+    kern = ifb.centered(np.array([G["widen_i16"]["kernel"]], dtype=np.int16))
+    try:
+        ifb.imfilter(img, kern, _library=lib)
+    except ifb.InexactError:
+        pass
+    else:
+        raise AssertionError("expected InexactError")
+    ret = ifb.imfilter(np.int32, img, kern, _library=lib)
+    assert ret.dtype == np.int32 and np.all(ret == G["widen_i16"]["value"])
+
+
+# ---- test/2d.jl:7-37 ------------------------------------------------------------------------------
+def check_prewitt_tiling(ifb, lib):
+    g = G["prewitt_u8"]
+    n = g["n"]
+    m = np.zeros((n, n), dtype=np.uint8)
+    target = np.zeros((n, n))
+    for i in range(-2, 3):
+        m[np.arange(max(0, -i), min(n, n - i)), np.arange(max(0, i), min(n, n + i))] = 0xFF
+    for i in range(1, 5):
+        idx = np.arange(0, n - i)
+        target[idx, idx + i] = g["dv"][i - 1]
+        target[idx + i, idx] = -g["dv"][i - 1]
+    kernel = ifb.KernelFactors.prewitt((True, True), 1)
+    kp = ifb.Kernel.prewitt((True, True), 1)[0]
+    mf = ifb.imfilter(m, kernel, _library=lib)
+    assert mf.dtype == np.float64 and approx(mf[1:19, 1:19], target[1:19, 1:19])
+    mf = ifb.imfilter(ifb.CUDALibs(ifb.Algorithm.FIR()), m, kernel, _library=lib)
+    assert approx(mf[1:19, 1:19], target[1:19, 1:19])
+    mf = ifb.imfilter(m, (kp,), _library=lib)
+    assert approx(mf[1:19, 1:19], target[1:19, 1:19])
+    rng = np.random.default_rng(7)
+    kf = ifb.kernelfactors((rng.random(7), rng.random(7)))
+    k = ifb.Kernel._bcast_product(kf)
+    assert approx(ifb.imfilter(m, (k,), _library=lib), ifb.imfilter(m, kf, _library=lib))
+
+
+# ---- test/2d.jl:39-226 ----------------------------------------------------------------------------
+def _impulse_images(ifb, pos):
+    imgf = np.zeros((5, 7)); imgf[pos] = 1
+    imgi = np.zeros((5, 7), dtype=np.int64); imgi[pos] = 1
+    raw = np.zeros((5, 7), dtype=np.uint8); raw[pos] = 255
+    return (imgf, np.float64), (imgi, np.float64), (ifb.n0f8(raw), np.float64)
+
+
+def check_impulse_interior(ifb, lib):
+    g = G["impulse"]
+    kern = np.array(g["kern"])
+    dense = ifb.OffsetArray.with_first(kern, (g["kern_axes"][0][0], g["kern_axes"][1][0]))
+    fk = g["factored"]
+    fact = (ifb.OffsetArray.with_first(np.array(fk["k1"]), (fk["k1_first"],)),
+            ifb.OffsetArray.with_first(np.array([fk["k2"]]), (0, fk["k2_first"])))
+    kfact = np.outer(fk["k1"], fk["k2"])
+    for kernel, kmat in ((dense, kern), (fact, kfact)):
+        for img, T in _impulse_images(ifb, (2, 3)):
+            target = np.zeros((5, 7))
+            target[2:4, 1:3] = kmat[::-1, ::-1]
+            res = ifb.imfilter(img, kernel, _library=lib)
+            assert res.dtype == T and approx(res, target)
+            if not isinstance(kernel, tuple):
+                assert approx(ifb.imfilter(img, (kernel,), _library=lib), target)
+            r32 = ifb.imfilter(np.float32, img, kernel, _library=lib)
+            assert r32.dtype == np.float32 and approx32(r32, target.astype(np.float32))
+            ret = np.zeros((5, 7), order="F")
+            assert approx(ifb.imfilter_(ret, img, kernel, _library=lib), target)
+            for border in BORDERS + (ifb.Fill(0),):
+                assert approx(ifb.imfilter(img, kernel, border, _library=lib), target)
+                assert approx32(ifb.imfilter(np.float32, img, kernel, border, _library=lib), target)
+                assert approx(ifb.imfilter(img, kernel, border, ifb.Algorithm.FIR(), _library=lib), target)
+                ret[:] = 0
+                assert approx(ifb.imfilter_(ifb.CUDALibs(), ret, img, kernel, border, _library=lib), target)
+            inner = ifb.imfilter(img, kernel, ifb.Inner(), _library=lib)
+            assert inner.first == (2, 1) and inner.shape == (4, 5)
+            assert approx(inner.parent, target[1:, :-2])
+            inner32 = ifb.imfilter(np.float32, img, kernel, ifb.Inner(), _library=lib)
+            assert approx32(inner32.parent, target[1:, :-2])
+    # "rational" coefficients 1//3 (test/2d.jl:116-144) as Float64 thirds
+    third = np.full(3, 1 / 3)
+    kernel = (ifb.centered(third), ifb.centered(third.reshape(1, 3)))
+    for img, T in _impulse_images(ifb, (2, 3)):
+        target = np.zeros((5, 7)); target[1:4, 2:5] = 1 / 9
+        for border in BORDERS + (ifb.Fill(0),):
+            assert approx(ifb.imfilter(img, kernel, border, _library=lib), target)
+        inner = ifb.imfilter(img, kernel, ifb.Inner(), _library=lib)
+        assert inner.first == (2, 2) and inner.shape == (3, 5) and approx(inner.parent, target[1:-1, 1:-1])
+
+
+def check_impulse_corner(ifb, lib):
+    g = G["impulse"]
+    kern = np.array(g["kern"])
+    dense = ifb.OffsetArray.with_first(kern, (g["kern_axes"][0][0], g["kern_axes"][1][0]))
+    fk = g["factored"]
+    fact = (ifb.OffsetArray.with_first(np.array(fk["k1"]), (fk["k1_first"],)),
+            ifb.OffsetArray.with_first(np.array([fk["k2"]]), (0, fk["k2_first"])))
+    kfact = np.outer(fk["k1"], fk["k2"])
+
+    def target1(k, border):
+        ret = np.zeros((5, 7))
+        if border in ("replicate", "symmetric"):
+            ret[0, 0] = k[0, 0] + k[1, 0]
+            ret[1, 0] = k[0, 0]
+        elif border == "circular":
+            rot = k[::-1, ::-1]   # a[0:1, -1:0] = rot180(kern) on a periodic (FFTView) array
+            for di, i in enumerate((0, 1)):
+                for dj, j in enumerate((-1, 0)):
+                    ret[i % 5, j % 7] = rot[di, dj]
+        else:
+            ret[0, 0] = k[1, 0]
+            ret[1, 0] = k[0, 0]
+        return ret
+
+    for kernel, kmat in ((dense, kern), (fact, kfact)):
+        for img, T in _impulse_images(ifb, (0, 1)):
+            for border in BORDERS + (ifb.Fill(0),):
+                t = target1(kmat, border if isinstance(border, str) else "fill")
+                assert approx(ifb.imfilter(img, kernel, border, _library=lib), t), (border,)
+                assert approx32(ifb.imfilter(np.float32, img, kernel, border, _library=lib), t)
+
+
+# ---- test/nd.jl:84-93 -------------------------------------------------------------------------------
+def check_offset_axes(ifb, lib):
+    img = ifb.OffsetArray(np.zeros(11), range(-5, 6))
+    img[0] = 1
+    k = ifb.centered(np.array([0.25, 0.5, 0.25]))
+    for border in BORDERS + (ifb.Fill(0.0), ifb.Inner((1,))):
+        f = ifb.imfilter(img, k, border, _library=lib)
+        assert isinstance(f, ifb.OffsetArray)
+        assert f[-1] == f[1] == 0.25 and f[0] == 0.5
+        lo, hi = f.axes[0].start, f.axes[0].stop - 1
+        assert all(f[i] == 0 for i in range(lo, -1)) and all(f[i] == 0 for i in range(2, hi + 1))
+
+
+# ---- test/nd.jl:96-109 (non-finite inputs stay local under FIR) -------------------------------------
+def check_nonfinite(ifb, lib):
+    rng = np.random.default_rng(3)
+    for x in (np.nan, np.inf, -np.inf):
+        v = rng.random(100)
+        i = 40
+        w = v.copy(); w[i] = x
+        kern = ifb.centered(np.ones(31))
+        vf = ifb.imfilter(v, kern, ifb.Algorithm.FIR(), _library=lib)
+        wf = ifb.imfilter(w, kern, ifb.Algorithm.FIR(), _library=lib)
+        around = np.abs(np.arange(100) - i) <= 15
+        if np.isnan(x):
+            assert np.all(np.isnan(wf[around]))
+        else:
+            assert np.all(wf[around] == x)
+        assert approx(wf[~around], vf[~around])
+
+
+# ---- test/nd.jl:128-157 -----------------------------------------------------------------------------
+def check_3d_box(ifb, lib):
+    img = np.ones((10, 10, 10), dtype=np.uint8)  # trues(10,10,10)
+    kernel = ifb.centered(np.ones((3, 3, 3)) / 27)
+    for border in BORDERS + (ifb.Fill(1),):
+        assert approx(ifb.imfilter(img, kernel, border, _library=lib), img)
+    target = np.ones((10, 10, 10))
+    e = (0, 9)
+    for i in e:
+        target[:, :, i] = 2 / 3; target[:, i, :] = 2 / 3; target[i, :, :] = 2 / 3
+    for i in e:
+        for j in e:
+            target[:, i, j] = (2 / 3) ** 2; target[i, :, j] = (2 / 3) ** 2; target[i, j, :] = (2 / 3) ** 2
+    for i in e:
+        for j in e:
+            for k in e:
+                target[i, j, k] = (2 / 3) ** 3
+    assert approx(ifb.imfilter(img, kernel, ifb.Fill(0), _library=lib), target)
+    inner = ifb.imfilter(img, kernel, ifb.Inner(), _library=lib)
+    assert inner.first == (2, 2, 2) and inner.shape == (8, 8, 8) and approx(inner.parent, np.ones((8, 8, 8)))
+
+
+# ---- test/cascade.jl:4-39 -----------------------------------------------------------------------------
+def check_cascade(ifb, lib):
+    rng = np.random.default_rng(11)
+    a = rng.random(15)
+    kern = ifb.OffsetArray(np.ones(3), range(-1, 2))
+    kern2 = ifb.OffsetArray(np.array([1.0, 2, 3, 2, 1]), range(-2, 3))
+    for border in BORDERS + (ifb.Fill(0.0),):
+        assert approx(ifb.imfilter(a, (kern, kern), border, _library=lib), ifb.imfilter(a, kern2, border, _library=lib))
+    a = np.asfortranarray(rng.random((15, 15)))
+    kx = ifb.OffsetArray(np.ones((3, 1)), range(-1, 2), range(0, 1))
+    ky = ifb.OffsetArray(np.ones((1, 3)), range(0, 1), range(-1, 2))
+    c = np.array([1.0, 2, 3, 2, 1])
+    k2 = ifb.OffsetArray(np.outer(c, c), range(-2, 3), range(-2, 3))
+    k2x = ifb.OffsetArray(np.outer(c, np.ones(3)), range(-2, 3), range(-1, 2))
+    k2y = ifb.OffsetArray(np.outer(np.ones(3), c), range(-1, 2), range(-2, 3))
+    for border in BORDERS + (ifb.Fill(0.0),):
+        f = lambda k: ifb.imfilter(a, k, border, _library=lib)
+        assert approx(f((kx, ky, kx, ky)), f(k2)), border
+        assert approx(f((kx, kx, ky, ky)), f(k2)), border
+        assert approx(f((kx, kx, ky)), f(k2x)), border
+        assert approx(f((ky, kx, ky)), f(k2y)), border
+
+
+# ---- test/gradient.jl:4-70 ----------------------------------------------------------------------------
+def check_gradients(ifb, lib):
+    y = np.arange(1, 6, dtype=np.float64)[:, None] * np.ones((1, 7))
+    x = np.ones((5, 1)) * np.arange(1, 8, dtype=np.float64)[None, :]
+    KF, K = ifb.KernelFactors, ifb.Kernel
+    for img, ey, ex in ((y.astype(np.int64), 1, 0), (x.astype(np.int64), 0, 1), (y, 1, 0), (x, 0, 1)):
+        for fun in (KF.ando3, KF.sobel, KF.prewitt, KF.ando4, KF.ando5, KF.bickley, KF.scharr,
+                    K.ando3, K.sobel, K.prewitt, K.ando4, K.ando5, K.scharr, K.bickley):
+            gy, gx = ifb.imgradients(img, fun, ifb.Inner(), _library=lib)
+            assert np.all(np.abs(gy.parent - ey) < 1e-4), fun.__name__
+            assert np.all(np.abs(gx.parent - ex) < 1e-4), fun.__name__
+            gy, gx = ifb.imgradients(img, fun, ifb.Pad("replicate"), _library=lib)
+            assert gy.shape == gx.shape == img.shape
+        for fk, fkf in ((K.ando3, KF.ando3), (K.sobel, KF.sobel), (K.prewitt, KF.prewitt),
+                        (K.scharr, KF.scharr), (K.bickley, KF.bickley)):
+            ky, kx = fk()
+            gmy, gmx = ifb.imfilter(img, ky, _library=lib), ifb.imfilter(img, kx, _library=lib)
+            gy, gx = ifb.imgradients(img, fkf, _library=lib)
+            assert approx(gmy, gy, atol=1e-8) and approx(gmx, gx, atol=1e-8)
+    # 3-d
+    sh = (5, 7, 6)
+    ramps = [np.broadcast_to(np.arange(1, n + 1, dtype=np.float64).reshape([n if d == a else 1 for d in range(3)]), sh).copy()
+             for a, n in enumerate(sh)]
+    for a, img in enumerate(ramps):
+        for fun in (KF.ando3, KF.sobel, KF.prewitt, KF.scharr, KF.bickley, K.ando3, K.sobel, K.prewitt, K.scharr, K.bickley):
+            gs = ifb.imgradients(img, fun, ifb.Inner(), _library=lib)
+            for d, gd in enumerate(gs):
+                assert np.all(np.abs(gd.parent - (1 if d == a else 0)) < 1e-4), (fun.__name__, a, d)
+
+
+# ---- test/specialty.jl:6-60 (Laplacian) ----------------------------------------------------------------
+def check_laplacian(ifb, lib):
+    L = ifb.Kernel.Laplacian()
+    for dt, T in ((np.float64, np.float64), (np.float32, np.float32), (np.int64, np.int64), (np.uint8, np.int16)):
+        a = np.zeros((5, 5), dtype=dt); a[2, 2] = 1
+        r = ifb.imfilter(a, L, _library=lib)
+        assert r.dtype == T
+        t = np.zeros((5, 5)); t[2, 2] = -4; t[1, 2] = t[3, 2] = t[2, 1] = t[2, 3] = 1
+        assert np.array_equal(r, t)
+        a = np.zeros((5, 5), dtype=dt); a[0, 0] = 1   # corner: replicate border
+        r = ifb.imfilter(a, L, _library=lib)
+        t = np.zeros((5, 5)); t[0, 0] = -2; t[1, 0] = t[0, 1] = 1
+        assert np.array_equal(r, t)
+        assert np.array_equal(ifb.imfilter(a, L.asarray(), _library=lib), t) or dt == np.uint8
+    # 1 flagged axis in 3-d
+    a = np.zeros((3, 5, 3)); a[1, 2, 1] = 1
+    r = ifb.imfilter(a, ifb.Kernel.Laplacian((2,), 3), _library=lib)
+    t = np.zeros((3, 5, 3)); t[1, 2, 1] = -2; t[1, 1, 1] = t[1, 3, 1] = 1
+    assert np.array_equal(r, t)
+
+
+# ---- test/mapwindow.jl:4-102 ---------------------------------------------------------------------------
+def _groundtruth(f, A, window):
+    """test/mapwindow.jl:5-14: clamp-index ground truth."""
+    Aex = A.copy()
+    hshift = [(w >> 1) + 1 for w in window]
+    for Ishift in np.ndindex(*window):
+        idx = np.indices(A.shape)
+        src = [np.clip(idx[d] + (Ishift[d] + 1) - hshift[d], 0, A.shape[d] - 1) for d in range(A.ndim)]
+        Aex = f(Aex, A[tuple(src)])
+    return Aex
+
+
+def check_extrema_goldens(ifb, lib):
+    for case in G["extrema_1d"]["cases"]:
+        A = np.array(case["A"])
+        mm = ifb.mapwindow(ifb.extrema, A, 1, _library=lib)
+        assert np.array_equal(mm["min"], A) and np.array_equal(mm["max"], A)
+        for w, exp in case["w"].items():
+            mm = ifb.mapwindow(ifb.extrema, A, int(w), _library=lib)
+            e = np.array(exp)
+            assert np.array_equal(mm["min"], e[:, 0]) and np.array_equal(mm["max"], e[:, 1]), w
+    rng = np.random.default_rng(5)
+    A = np.asfortranarray(rng.random((5, 5)) / 10); A[1, 1] = 0.8; A[3, 3] = 0.6
+    for w in ((2, 2), (2, 3), (3, 2), (3, 3), (2, 5)):
+        mm = ifb.mapwindow(ifb.extrema, A, w, _library=lib)
+        assert np.array_equal(mm["max"], _groundtruth(np.maximum, A, w)), w
+        assert np.array_equal(mm["min"], _groundtruth(np.minimum, A, w)), w
+    A = np.asfortranarray(rng.random((5, 5, 5)) / 10); A[1, 1, 1] = 0.7; A[3, 3, 1] = 0.4; A[1, 1, 3] = 0.5
+    for w in ((2, 2, 2), (2, 3, 2), (3, 2, 2), (2, 2, 3), (3, 3, 3), (2, 5, 3)):
+        mm = ifb.mapwindow(ifb.extrema, A, w, _library=lib)
+        assert np.array_equal(mm["max"], _groundtruth(np.maximum, A, w)), w
+        assert np.array_equal(mm["min"], _groundtruth(np.minimum, A, w)), w
+    for bad in (lambda: ifb.mapwindow(ifb.extrema, np.ones((5, 5)), (), _library=lib),):
+        try:
+            bad()
+        except ifb.ArgumentError:
+            pass
+        else:
+            raise AssertionError("expected ArgumentError")
+
+
+def _naive_window(f, a, wlo, whi, border, fill=None):
+    """Independent numpy restatement of mapwindow_kernel! for min/max (src/mapwindow.jl:270-333)."""
+    out = np.empty(a.shape)
+    for I in np.ndindex(*a.shape):
+        vals = []
+        outside = False
+        for J in np.ndindex(*[h - l + 1 for l, h in zip(wlo, whi)]):
+            K = tuple(i + l + j for i, l, j in zip(I, wlo, J))
+            if all(0 <= k < n for k, n in zip(K, a.shape)):
+                vals.append(a[K])
+            else:
+                outside = True
+        if border == "fill" and outside:
+            vals.append(fill)
+        out[I] = f(vals)
+    return out
+
+
+def check_mapwindow_offsets(ifb, lib):
+    """test/mapwindow.jl:78-102: offset invariance, all f, windows, borders, dims (+ values vs a naive form)."""
+    n = 5
+    rng = np.random.default_rng(9)
+    arrays = [rng.random(n), np.asfortranarray(rng.random((n, n))), np.asfortranarray(rng.random((n, n, n)))]
+    fillv = float(rng.standard_normal())
+    for fname, f, npf in (("extrema", ifb.extrema, None), ("max", ifb.maximum, max), ("min", ifb.minimum, min)):
+        for offset in (-5, 0, 3):
+            for window in (1, 3, 5, 7, 9, range(0, 3), range(-2, 1)):
+                for border in ("replicate", "symmetric", ifb.Fill(fillv), ifb.Inner()):
+                    for dim, a in enumerate(arrays, start=1):
+                        windows = (window,) * dim
+                        winlen = window if isinstance(window, int) else len(window)
+                        ao = ifb.OffsetArray(a, *([offset] * dim))
+                        mw = lambda x: ifb.mapwindow(f, x, windows, border=border, _library=lib)
+                        if isinstance(border, ifb.Inner) and winlen > n:
+                            for x in (a, ao):
+                                try:
+                                    mw(x)
+                                except ifb.DimensionMismatch:
+                                    pass
+                                else:
+                                    raise AssertionError("expected DimensionMismatch")
+                            continue
+                        r1, r2 = mw(a), mw(ao)
+                        p1 = r1.parent if isinstance(r1, ifb.OffsetArray) else r1
+                        p2 = r2.parent if isinstance(r2, ifb.OffsetArray) else r2
+                        assert np.array_equal(p1, p2)
+                        f1 = r1.first if isinstance(r1, ifb.OffsetArray) else (1,) * dim
+                        f2 = r2.first if isinstance(r2, ifb.OffsetArray) else (1,) * dim
+                        assert tuple(x + offset for x in f1) == tuple(f2)
+                        if dim <= 2 and npf is not None and not isinstance(border, ifb.Inner):
+                            wlo = [(-(window >> 1)) if isinstance(window, int) else window.start] * dim
+                            whi = [(window >> 1) if isinstance(window, int) else window.stop - 1] * dim
+                            bname = "fill" if isinstance(border, ifb.Fill) else "pad"
+                            assert np.array_equal(p1, _naive_window(npf, a, wlo, whi, bname, fillv)), (fname, window, border)
+
+
+ALL_CHECKS = [check_padarray, check_1d, check_widening, check_prewitt_tiling, check_impulse_interior,
+              check_impulse_corner, check_offset_axes, check_nonfinite, check_3d_box, check_cascade,
+              check_gradients, check_laplacian, check_extrema_goldens, check_mapwindow_offsets]
