@@ -1,0 +1,216 @@
+"""Differential parity: CUDA library vs the CPU oracle on identical seeded inputs, through the C ABI.
+
+Bar (BASELINE.json north_star): bit-exact for Float64 outputs whose axes are filtered at most once,
+for integer kernels on integer data and for min/max; |gpu - oracle| <= 1e-5 * prod_stage(sum|k|) *
+max|img| for Float32 outputs.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+BORDERS = ["replicate", "circular", "symmetric", "reflect"]
+
+
+def _tol(stages_taps, img):
+    s = 1.0
+    for t in stages_taps:
+        s *= np.abs(np.asarray(t, dtype=np.float64)).sum()
+    return 1e-5 * s * float(np.abs(np.asarray(img, dtype=np.float64)).max())
+
+
+def _both(ifb, oracle, *args):
+    a = ifb.imfilter(*args)
+    b = ifb.imfilter(*args, _library=oracle)
+    pa = a.parent if isinstance(a, ifb.OffsetArray) else a
+    pb = b.parent if isinstance(b, ifb.OffsetArray) else b
+    if isinstance(a, ifb.OffsetArray):
+        assert a.first == b.first
+    assert pa.shape == pb.shape and pa.dtype == pb.dtype
+    return pa, pb
+
+
+@pytest.mark.parametrize("border", BORDERS + ["fill", "inner"])
+@pytest.mark.parametrize("shape", [(37, 53), (130, 67), (5, 4), (257, 129, 3)])
+@pytest.mark.parametrize("dt", ["f32", "f64", "n0f8", "u8"])
+def test_separable_f64_bit_exact(ifb, oracle, device, border, shape, dt):
+    rng = np.random.default_rng(hash((border, shape, dt)) % 2**32)
+    if dt == "f32":
+        img = rng.random(shape, dtype=np.float32)
+    elif dt == "f64":
+        img = rng.random(shape)
+    else:
+        raw = rng.integers(0, 256, size=shape, dtype=np.uint8)
+        img = ifb.n0f8(raw) if dt == "n0f8" else raw
+    nd = len(shape)
+    b = {"fill": ifb.Fill(0.25 if dt != "u8" else 3), "inner": ifb.Inner()}.get(border, border)
+    for sig in ((1, 2), (3, 1)):
+        kf = ifb.KernelFactors.gaussian(sig + (0,) * (nd - 2)) if nd > 2 else ifb.KernelFactors.gaussian(sig)
+        for kern in (kf, tuple(reversed(kf))):   # x-first and y-first cascades
+            pa, pb = _both(ifb, oracle, img, kern, b)
+            assert pa.dtype == np.float64
+            assert np.array_equal(pa, pb), (border, shape, dt, sig)
+            assert device.last_path() == "fused2d"
+
+
+@pytest.mark.parametrize("border", BORDERS + ["fill"])
+@pytest.mark.parametrize("shape", [(64, 64), (131, 77), (300, 9), (70, 66, 4)])
+def test_separable_f32_tolerance(ifb, oracle, device, border, shape):
+    rng = np.random.default_rng(hash((border, shape)) % 2**32)
+    img = rng.random(shape, dtype=np.float32)
+    b = ifb.Fill(0.5) if border == "fill" else border
+    nd = len(shape)
+    for sig in ((3, 3), (1, 6)):
+        kf = ifb.KernelFactors.gaussian(sig + (0,) * (nd - 2)) if nd > 2 else ifb.KernelFactors.gaussian(sig)
+        pa, pb = _both(ifb, oracle, np.float32, img, kf, b)
+        assert pa.dtype == np.float32
+        tol = _tol([k.data.parent for k in kf], img)
+        assert np.max(np.abs(pa.astype(np.float64) - pb.astype(np.float64))) <= tol
+        assert device.last_path() == "fused2d"
+        # float32 taps too (KernelFactors.gaussian(σ::Float32))
+        kf32 = ifb.KernelFactors.gaussian(tuple(np.float32(s) for s in sig) + (np.float32(0),) * (nd - 2))
+        pa, pb = _both(ifb, oracle, img, kf32, b)
+        assert pa.dtype == np.float32
+        assert np.max(np.abs(pa.astype(np.float64) - pb.astype(np.float64))) <= tol
+
+
+@pytest.mark.parametrize("border", BORDERS + ["fill", "inner"])
+@pytest.mark.parametrize("fun", ["sobel", "prewitt", "scharr", "ando5"])
+def test_imgradients_n0f8_bit_exact(ifb, oracle, device, border, fun):
+    rng = np.random.default_rng(17)
+    raw = rng.integers(0, 256, size=(203, 91), dtype=np.uint8)
+    img = ifb.n0f8(raw)
+    b = {"fill": ifb.Fill(0.0), "inner": ifb.Inner()}.get(border, border)
+    kfun = getattr(ifb.KernelFactors, fun)
+    ga = ifb.imgradients(img, kfun, b)
+    assert device.last_path() == "fused2d_grad"
+    gb = ifb.imgradients(img, kfun, b, _library=oracle)
+    for a, o in zip(ga, gb):
+        pa = a.parent if isinstance(a, ifb.OffsetArray) else a
+        po = o.parent if isinstance(o, ifb.OffsetArray) else o
+        assert pa.dtype == np.float64 and np.array_equal(pa, po)
+    g32 = ifb.imgradients(img, kfun, b, T=np.float32)
+    for a, o in zip(g32, gb):
+        pa = a.parent if isinstance(a, ifb.OffsetArray) else a
+        po = o.parent if isinstance(o, ifb.OffsetArray) else o
+        assert pa.dtype == np.float32 and np.max(np.abs(pa - po)) <= 1e-5
+
+
+def test_generic_path_cases(ifb, oracle, device):
+    """Everything the fused kernels do not cover goes through the per-stage device path."""
+    rng = np.random.default_rng(23)
+    cases = []
+    a1 = rng.random(50)
+    k1 = ifb.centered(rng.random(5))
+    cases.append((a1, (k1, k1, k1)))                                    # 1-D, same axis three times
+    a2 = np.asfortranarray(rng.random((33, 21)))
+    kx = ifb.OffsetArray(rng.random((3, 1)), range(-1, 2), range(0, 1))
+    ky = ifb.OffsetArray(rng.random((1, 4)), range(0, 1), range(-2, 2))
+    cases.append((a2, (kx, ky, kx, ky)))                                # repeated axes (test/cascade.jl)
+    cases.append((a2, (ky,)))                                           # single 1-D stage
+    cases.append((a2, ifb.OffsetArray(rng.random((3, 4)), range(-1, 2), range(0, 4))))   # dense, asymmetric
+    a3 = np.asfortranarray(rng.random((12, 9, 7)))
+    cases.append((a3, ifb.KernelFactors.gaussian((1, 1, 1))))           # 3-D separable
+    cases.append((a3, ifb.centered(rng.random((3, 3, 3)))))             # 3-D dense
+    a4 = np.asfortranarray(rng.random((6, 5, 4, 3)))
+    cases.append((a4, ifb.centered(rng.random((3, 1, 3, 1)))))          # 4-D
+    for img, kern in cases:
+        for border in BORDERS + [ifb.Fill(0.3), ifb.Inner()]:
+            pa, pb = _both(ifb, oracle, img, kern, border)
+            assert np.array_equal(pa, pb), (img.shape, border)
+            assert device.last_path() in ("generic", "dense2d", "fused3d", "fused2d")
+
+
+def test_integer_exact_and_inexact(ifb, oracle, device):
+    rng = np.random.default_rng(29)
+    img = rng.integers(0, 256, size=(40, 31), dtype=np.uint8)
+    kern = ifb.centered(rng.integers(-3, 4, size=(3, 5)).astype(np.int64))
+    pa, pb = _both(ifb, oracle, img, kern, "reflect")
+    assert pa.dtype == np.int64 and np.array_equal(pa, pb)
+    pa, pb = _both(ifb, oracle, np.int32, img, kern, "circular")
+    assert pa.dtype == np.int32 and np.array_equal(pa, pb)
+    with pytest.raises(ifb.InexactError):
+        ifb.imfilter(np.uint8, img, kern)
+    i16 = rng.integers(-1000, 1000, size=(25, 25)).astype(np.int16)
+    ksep = (ifb.centered(np.array([1, 2, 1], dtype=np.int64)), ifb.centered(np.array([[1, 0, -1]], dtype=np.int64)))
+    pa, pb = _both(ifb, oracle, i16, ksep, "symmetric")
+    assert pa.dtype == np.int64 and np.array_equal(pa, pb)
+
+
+def test_pad_larger_than_image_and_explicit_pads(ifb, oracle, device):
+    rng = np.random.default_rng(31)
+    img = np.asfortranarray(rng.random((3, 2)))
+    kf = ifb.KernelFactors.gaussian((2, 2))          # 9 taps on a 3x2 image: multi-fold remap
+    for border in ["replicate", "circular", "symmetric", "reflect", ifb.Fill(1.5)]:
+        pa, pb = _both(ifb, oracle, img, kf, border)
+        assert np.array_equal(pa, pb), border
+    big = np.asfortranarray(rng.random((20, 20)))
+    pa, pb = _both(ifb, oracle, big, kf, ifb.Pad("reflect", (6, 6), (5, 5)))   # more than needed: fine
+    assert np.array_equal(pa, pb)
+    with pytest.raises(ifb.DimensionMismatch):
+        ifb.imfilter(big, kf, ifb.Pad("reflect", (1, 1), (1, 1)))              # less than needed
+    with pytest.raises(ifb.ArgumentError):
+        ifb.imfilter(np.asfortranarray(rng.random((1, 5))), kf, "reflect")     # DivideError in the reference
+
+
+def test_imfilter_inplace_roi_and_nopad(ifb, oracle, device):
+    rng = np.random.default_rng(37)
+    img = np.asfortranarray(rng.random((30, 40)))
+    kf = ifb.KernelFactors.gaussian((1, 1))
+    inds = (range(4, 20), range(6, 30))
+    outs = []
+    for lib in (None, oracle):
+        out = np.full((30, 40), -7.0, order="F")
+        ifb.imfilter_(ifb.CUDALibs(), out, img, kf, ifb.NoPad(), inds, _library=lib)
+        outs.append(out)
+    assert np.array_equal(outs[0], outs[1])
+    assert np.all(outs[0][:3, :] == -7.0) and np.all(outs[0][19:, :] == -7.0)
+    with pytest.raises(ifb.DimensionMismatch):
+        ifb.imfilter_(ifb.CUDALibs(), np.zeros((30, 40), order="F"), img, kf, ifb.NoPad())
+
+
+def test_device_resident_arrays(ifb, oracle, device):
+    """Zero-copy form: torch CUDA tensors wrapped as DeviceArray, batch of images in one launch."""
+    import torch
+    rng = np.random.default_rng(41)
+    B, H, W = 5, 70, 200
+    host = rng.integers(0, 256, size=(B, H, W), dtype=np.uint8)          # C-order (B,H,W) == Julia dims (W,H,B)
+    t = torch.from_numpy(host).cuda()
+    gx = torch.empty((B, H, W), dtype=torch.float64, device="cuda")
+    gy = torch.empty_like(gx)
+    img_d = ifb.DeviceArray.from_torch(t, n0f8=True)
+    k1 = ifb.KernelFactors.sobel((True, True, False), 1)
+    k2 = ifb.KernelFactors.sobel((True, True, False), 2)
+    from importlib import import_module
+    imf = import_module("imagefiltering_jl_b200.imfilter")
+    st = ifb._abi.StageList(imf.build_stages(k1, 3) + imf.build_stages(k2, 3))
+    device.imgradients(img_d.desc(), [ifb.DeviceArray.from_torch(gx).desc(), ifb.DeviceArray.from_torch(gy).desc()],
+                       st, 3, ifb.Pad("reflect").to_abi(3))
+    torch.cuda.synchronize()
+    assert device.last_path() == "fused2d_grad"
+    himg = ifb.n0f8(np.asfortranarray(host.transpose(2, 1, 0)))
+    o1 = ifb.imfilter(himg, k1, "reflect", _library=oracle)
+    o2 = ifb.imfilter(himg, k2, "reflect", _library=oracle)
+    assert np.array_equal(gx.cpu().numpy().transpose(2, 1, 0), o1)
+    assert np.array_equal(gy.cpu().numpy().transpose(2, 1, 0), o2)
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64, np.uint8, np.int16, np.int32])
+def test_extrema_parity(ifb, oracle, device, dt):
+    rng = np.random.default_rng(43)
+    for shape, window in (((101,), (7,)), ((64, 45), (7, 7)), ((33, 20), (4, 3)), ((20, 19, 6), (3, 5, 1)), ((9, 8, 7), (2, 2, 2))):
+        if np.dtype(dt).kind == "f":
+            img = np.asfortranarray(rng.random(shape).astype(dt))
+        else:
+            img = np.asfortranarray(rng.integers(0, 200, size=shape).astype(dt))
+        a = ifb.mapwindow(ifb.extrema, img, window)
+        b = ifb.mapwindow(ifb.extrema, img, window, _library=oracle)
+        assert np.array_equal(a["min"], b["min"]) and np.array_equal(a["max"], b["max"]), (shape, window)
+        if all(w % 2 == 1 for w in window):
+            for f in (ifb.minimum, ifb.maximum):
+                for border in ("replicate", "reflect", ifb.Fill(5), ifb.Inner()):
+                    x = ifb.mapwindow(f, img, window, border=border)
+                    y = ifb.mapwindow(f, img, window, border=border, _library=oracle)
+                    px = x.parent if isinstance(x, ifb.OffsetArray) else x
+                    py = y.parent if isinstance(y, ifb.OffsetArray) else y
+                    assert np.array_equal(px, py), (shape, window, border)
