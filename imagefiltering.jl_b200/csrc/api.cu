@@ -11,6 +11,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -295,7 +296,11 @@ static int imfilter_planes(const b2f_array *img, const b2f_array *outs, int npla
         std::vector<void *> dout(nplanes);
         std::vector<int> odt(nplanes);
         for (int p = 0; p < nplanes; ++p) { dout[p] = souts[p].dptr; odt[p] = outs[p].dtype; }
-        if (fused2d_applicable(plans.data(), nplanes, img->dtype, odt.data())) {
+        const char *force = getenv("B2F_FORCE_PATH");   // debugging knob: "fused2d" | "generic"
+        const bool allow_stream = !force, allow_fused = !force || !strcmp(force, "fused2d");
+        if (allow_stream && stream2d_applicable(plans.data(), nplanes, img->dtype, odt.data())) {
+            rc = run_stream2d(plans.data(), nplanes, sin.dptr, img->dtype, dout.data(), odt.data(), st);
+        } else if (allow_fused && fused2d_applicable(plans.data(), nplanes, img->dtype, odt.data())) {
             rc = run_fused2d(plans.data(), nplanes, sin.dptr, img->dtype, dout.data(), odt.data(), st);
         } else {
             for (int p = 0; p < nplanes && !rc; ++p)
@@ -348,6 +353,10 @@ int b2f_mapwindow_extrema(const b2f_array *img, const b2f_array *out_min, const 
         for (int d = 0; d < N; ++d)
             if (ob.lo[d] != oa.lo[d] || ob.hi[d] != oa.hi[d]) return fail(B2F_EDIM, "out_min and out_max axes differ");
     }
+    if (border->style == B2F_INNER)
+        for (int d = 0; d < N; ++d)
+            if (win_hi[d] - win_lo[d] + 1 > ia.len(d))
+                return fail(B2F_EDIM, "window is larger than the image along axis %d: no interior for Inner()", d);
     if (ia.empty() || oa.empty()) { set_path("empty"); return 0; }
     for (int d = 0; d < N; ++d) {
         if (oa.lo[d] < ia.lo[d] || oa.hi[d] > ia.hi[d]) return fail(B2F_EDIM, "output axes exceed image axes");

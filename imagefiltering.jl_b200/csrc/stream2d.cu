@@ -1,0 +1,75 @@
+// stream2d.cu — applicability test and parameter set-up of the warp-streamed 2-D separable path
+#include "stream2d.cuh"
+
+namespace b2f {
+
+template <typename CT, int NPL> int launch_stream2d(const S2Params<CT, NPL> &P, int img_dt, cudaStream_t st);
+template <> int launch_stream2d<float, 1>(const S2Params<float, 1> &, int, cudaStream_t);
+template <> int launch_stream2d<float, 2>(const S2Params<float, 2> &, int, cudaStream_t);
+template <> int launch_stream2d<double, 1>(const S2Params<double, 1> &, int, cudaStream_t);
+template <> int launch_stream2d<double, 2>(const S2Params<double, 2> &, int, cudaStream_t);
+
+// On top of fused2d's conditions: stage order x then y, u8/N0f8/f32/f64 input, <= 16 taps (<= 8 for two planes).
+bool stream2d_applicable(const Plan *plans, int nplanes, int img_dt, const int *out_dt) {
+    if (!fused2d_applicable(plans, nplanes, img_dt, out_dt)) return false;
+    if (img_dt != B2F_U8 && img_dt != B2F_N0F8 && img_dt != B2F_F32 && img_dt != B2F_F64) return false;
+    const Plan &P0 = plans[0];
+    const StageInfo &s1 = P0.stages[P0.active[0]], &s2 = P0.stages[P0.active[1]];
+    if (s1.s->axis != 0 || s2.s->axis != 1) return false;
+    const int64_t Lx = s1.s->len[0], Ly = s2.s->len[1];
+    const int64_t L = Lx > Ly ? Lx : Ly;
+    if (L > (nplanes == 1 ? 16 : 8)) return false;
+    return true;
+}
+
+template <typename CT, int NPL>
+static int run_typed(const Plan *plans, const void *d_img, int img_dt, void *const *d_outs, cudaStream_t st) {
+    constexpr int PX = S2Vec<CT>::PX;
+    constexpr int CW = 32 * PX;
+    const Plan &P0 = plans[0];
+    S2Params<CT, NPL> P;
+    memset(&P, 0, sizeof P);
+    P.img = d_img; P.n0f8 = img_dt == B2F_N0F8;
+    P.W = (int)P0.img_ax.len(0); P.H = (int)P0.img_ax.len(1);
+    P.img_plane = (long long)P.W * P.H;
+    P.out_pitch = P0.out_ax.len(0);
+    P.out_plane = P0.out_ax.len(0) * P0.out_ax.len(1);
+    P.out_ox = (int)(P0.out_ax.lo[0] - P0.img_ax.lo[0]);
+    P.out_oy = (int)(P0.out_ax.lo[1] - P0.img_ax.lo[1]);
+    P.rx0 = (int)(P0.roi.lo[0] - P0.img_ax.lo[0]); P.ry0 = (int)(P0.roi.lo[1] - P0.img_ax.lo[1]);
+    P.rw = (int)P0.roi.len(0); P.rh = (int)P0.roi.len(1);
+    P.style = P0.style; P.fill = (CT)P0.fill;
+    bool aligned = (P.out_pitch % PX == 0) && (P.out_plane % PX == 0) && ((P.rx0 - P.out_ox) % PX == 0);
+    for (int p = 0; p < NPL; ++p) {
+        P.out[p] = d_outs[p];
+        aligned = aligned && (reinterpret_cast<uintptr_t>(d_outs[p]) % 16 == 0);
+        const StageInfo &sx = plans[p].stages[plans[p].active[0]], &sy = plans[p].stages[plans[p].active[1]];
+        P.Lx = (int)sx.s->len[0]; P.klox = (int)sx.lo[0];
+        P.Ly = (int)sy.s->len[1]; P.kloy = (int)sy.lo[1];
+        for (int j = 0; j < P.Lx; ++j) P.kx[p][j] = (CT)sx.s->taps[j];
+        for (int d = 0; d < P.Ly; ++d) P.kyr[p][d] = (CT)sy.s->taps[P.Ly - 1 - d];
+    }
+    P.vec_ok = aligned ? 1 : 0;
+    const long long nbatch = P0.img_ax.len(2) * P0.img_ax.len(3);
+    P.nsx = (P.rw + CW - 1) / CW;
+    // strip height: as tall as possible (less y-halo re-read) while still filling the machine with warps
+    const long long want = 148LL * 16 * 2;
+    int SH = 256;
+    while (SH > 32 && (long long)P.nsx * ((P.rh + SH - 1) / SH) * nbatch < want) SH >>= 1;
+    P.SH = SH;
+    P.nsy = (P.rh + SH - 1) / SH;
+    P.nstrips = (long long)P.nsx * P.nsy * nbatch;
+    return launch_stream2d<CT, NPL>(P, img_dt, st);
+}
+
+int run_stream2d(const Plan *plans, int nplanes, const void *d_img, int img_dt, void *const *d_outs,
+                 const int *out_dt, cudaStream_t st) {
+    set_path(nplanes == 1 ? "stream2d" : "stream2d_grad");
+    if (out_dt[0] == B2F_F32)
+        return nplanes == 1 ? run_typed<float, 1>(plans, d_img, img_dt, d_outs, st)
+                            : run_typed<float, 2>(plans, d_img, img_dt, d_outs, st);
+    return nplanes == 1 ? run_typed<double, 1>(plans, d_img, img_dt, d_outs, st)
+                        : run_typed<double, 2>(plans, d_img, img_dt, d_outs, st);
+}
+
+}  // namespace b2f

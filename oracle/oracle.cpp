@@ -730,6 +730,10 @@ int b2f_mapwindow_extrema(const b2f_array *img, const b2f_array *out_min, const 
         return fail(B2F_EARG, "NULL argument");
     if (interleaved && !out_min) return fail(B2F_EARG, "interleaved output needs out_min");
     if (img->ndim < 1 || img->ndim > B2F_MAXDIM) return fail(B2F_ENOTSUP, "ndim %d not supported", img->ndim);
+    if (border->style == B2F_INNER)
+        for (int d = 0; d < img->ndim; ++d)
+            if (win_hi[d] - win_lo[d] + 1 > img->dims[d])
+                return fail(B2F_EDIM, "window is larger than the image along axis %d: no interior for Inner()", d);
     const b2f_array *ref = out_min ? out_min : out_max;
     if (ref->dtype != img->dtype || (out_max && out_max->dtype != img->dtype))
         return fail(B2F_EARG, "extrema outputs must have the image eltype");
