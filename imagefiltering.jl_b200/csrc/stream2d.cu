@@ -3,11 +3,16 @@
 
 namespace b2f {
 
-template <typename CT, int NPL> int launch_stream2d(const S2Params<CT, NPL> &P, int img_dt, cudaStream_t st);
-template <> int launch_stream2d<float, 1>(const S2Params<float, 1> &, int, cudaStream_t);
-template <> int launch_stream2d<float, 2>(const S2Params<float, 2> &, int, cudaStream_t);
-template <> int launch_stream2d<double, 1>(const S2Params<double, 1> &, int, cudaStream_t);
-template <> int launch_stream2d<double, 2>(const S2Params<double, 2> &, int, cudaStream_t);
+template <typename IT, typename CT, int NPL> int launch_stream2d(const S2Params<CT, NPL> &P, cudaStream_t st);
+#define B2F_S2_DECL(IT, CT)                                                                  \
+    template <> int launch_stream2d<IT, CT, 1>(const S2Params<CT, 1> &, cudaStream_t);       \
+    template <> int launch_stream2d<IT, CT, 2>(const S2Params<CT, 2> &, cudaStream_t);
+B2F_S2_DECL(uint8_t, float)
+B2F_S2_DECL(uint8_t, double)
+B2F_S2_DECL(float, float)
+B2F_S2_DECL(float, double)
+B2F_S2_DECL(double, float)
+B2F_S2_DECL(double, double)
 
 // On top of fused2d's conditions: stage order x then y, u8/N0f8/f32/f64 input, <= 16 taps (<= 8 for two planes).
 bool stream2d_applicable(const Plan *plans, int nplanes, int img_dt, const int *out_dt) {
@@ -18,6 +23,7 @@ bool stream2d_applicable(const Plan *plans, int nplanes, int img_dt, const int *
     if (s1.s->axis != 0 || s2.s->axis != 1) return false;
     const int64_t Lx = s1.s->len[0], Ly = s2.s->len[1];
     const int64_t L = Lx > Ly ? Lx : Ly;
+    if (nplanes == 1 && Lx == 17 && Ly == 17) return true;
     if (L > (nplanes == 1 ? 16 : 8)) return false;
     return true;
 }
@@ -29,7 +35,9 @@ static int run_typed(const Plan *plans, const void *d_img, int img_dt, void *con
     const Plan &P0 = plans[0];
     S2Params<CT, NPL> P;
     memset(&P, 0, sizeof P);
-    P.img = d_img; P.n0f8 = img_dt == B2F_N0F8;
+    P.img = d_img;
+    P.n0_r = img_dt == B2F_N0F8 ? (CT)1 / (CT)255 : (CT)1;
+    P.n0_c = img_dt == B2F_N0F8 ? (CT)255 : (CT)1;
     P.W = (int)P0.img_ax.len(0); P.H = (int)P0.img_ax.len(1);
     P.img_plane = (long long)P.W * P.H;
     P.out_pitch = P0.out_ax.len(0);
@@ -53,13 +61,17 @@ static int run_typed(const Plan *plans, const void *d_img, int img_dt, void *con
     const long long nbatch = P0.img_ax.len(2) * P0.img_ax.len(3);
     P.nsx = (P.rw + CW - 1) / CW;
     // strip height: as tall as possible (less y-halo re-read) while still filling the machine with warps
-    const long long want = 148LL * 16 * 2;
+    const long long want = 148LL * 16 * 6;
     int SH = 256;
     while (SH > 32 && (long long)P.nsx * ((P.rh + SH - 1) / SH) * nbatch < want) SH >>= 1;
     P.SH = SH;
     P.nsy = (P.rh + SH - 1) / SH;
     P.nstrips = (long long)P.nsx * P.nsy * nbatch;
-    return launch_stream2d<CT, NPL>(P, img_dt, st);
+    switch (img_dt) {
+        case B2F_U8: case B2F_N0F8: return launch_stream2d<uint8_t, CT, NPL>(P, st);
+        case B2F_F32: return launch_stream2d<float, CT, NPL>(P, st);
+        default: return launch_stream2d<double, CT, NPL>(P, st);
+    }
 }
 
 int run_stream2d(const Plan *plans, int nplanes, const void *d_img, int img_dt, void *const *d_outs,

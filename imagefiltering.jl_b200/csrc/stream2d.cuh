@@ -12,9 +12,12 @@
 //     window read with 128-bit conflict-free LDS;
 //   * stage 2 (along y): output-stationary accumulators in registers.  Row r adds mid[r]*ky[j] to the
 //     LY outputs whose window contains it, in ascending tap order, so the bits match the
-//     reference loop; the accumulator ring rotates at compile time (row loop unrolled by LB), so
+//     reference loop; the accumulator ring rotates at compile time (row loop unrolled by ROT), so
 //     there are no register moves and no shared-memory intermediate;
 //   * a finished output row leaves as one 128-bit store per lane and plane (512 B per warp).
+//
+// Tap counts: LXT/LYT > 0 are compile-time exact (hot sizes: no predicates at all); LXT = LYT = 0 means
+// run-time counts bounded by the bucket LB (uniform predicates around each tap).
 //
 // HBM traffic: each input pixel is read once (+ halo re-reads that hit L2), each output written once.
 #pragma once
@@ -23,13 +26,13 @@
 
 namespace b2f {
 
-constexpr int S2_MAXTAPS = 16;
+constexpr int S2_MAXTAPS = 20;
 constexpr int S2_WARPS = 4;   // warps per CTA (they do not cooperate)
 
 template <typename CT, int NPL>
 struct S2Params {
     const void *img;
-    int n0f8;                 // u8 input means N0f8 (i/255) rather than the integer i
+    CT n0_r, n0_c;            // u8 -> CT: q=x*r; q += fma(-q,c,x)*r.  (1/255,255) for N0f8, (1,1) for raw bytes
     int W, H;
     long long img_plane;
     void *out[NPL];
@@ -52,25 +55,123 @@ template <> struct S2Vec<float> { typedef float4 T; static constexpr int PX = 4;
 template <> struct S2Vec<double> { typedef double2 T; static constexpr int PX = 2; };
 
 template <typename IT, typename CT> struct S2Conv {
-    __device__ static __forceinline__ CT f(IT v, int) { return (CT)v; }
+    __device__ static __forceinline__ CT f(IT v, CT, CT) { return (CT)v; }
 };
-template <> struct S2Conv<uint8_t, double> {
-    __device__ static __forceinline__ double f(uint8_t v, int n0f8) { return n0f8 ? n0f8_to_f64(v) : (double)v; }
+template <> struct S2Conv<uint8_t, double> {   // branch-free, correctly rounded i/255 (or i itself when r=c=1)
+    __device__ static __forceinline__ double f(uint8_t v, double r, double c) {
+        const double x = (double)v;
+        const double q = __dmul_rn(x, r);
+        return fma(fma(-q, c, x), r, q);
+    }
 };
 template <> struct S2Conv<uint8_t, float> {
-    __device__ static __forceinline__ float f(uint8_t v, int n0f8) { return n0f8 ? n0f8_to_f32(v) : (float)v; }
+    __device__ static __forceinline__ float f(uint8_t v, float r, float c) {
+        const float x = (float)v;
+        const float q = __fmul_rn(x, r);
+        return fmaf(fmaf(-q, c, x), r, q);
+    }
 };
 
-template <typename IT, typename CT, int LB, int NPL>
+__device__ __forceinline__ int s2_remap(int style, int i, int n) {   // 32-bit twin of remap_index
+    if ((unsigned)i < (unsigned)n) return i;
+    return (int)remap_index(style, (int64_t)i, (int64_t)n);
+}
+
+// One input row of a strip: stage 1 from the smem ring, stage 2 into the register ring, emit the finished
+// output row.  `u` = rv % ROT; it is a literal after the caller's unrolling, so every acc[][slot][] index is static.
+// CHECKED: rows before s0 / past the end are skipped and outputs that do not exist yet are not stored.
+template <typename CT, int LXT, int LYT, int LB, int NPL, int RB, bool CHECKED>
+__device__ __forceinline__ void s2_row(const int u, const int rv, const S2Params<CT, NPL> &P, const int Lx, const int Ly,
+                                       const int s0, const int vrows, const CT *__restrict__ sblk, const int lane,
+                                       const int tw, const bool lane_full, const bool lane_live,
+                                       CT (&acc)[NPL][(((LYT ? LYT : LB) + RB - 1) / RB) * RB][S2Vec<CT>::PX],
+                                       CT *(&outp)[NPL]) {
+    constexpr int PX = S2Vec<CT>::PX;
+    constexpr int LBX = LXT ? LXT : LB;
+    constexpr int LBY = LYT ? LYT : LB;
+    constexpr int ROT = ((LBY + RB - 1) / RB) * RB;
+    constexpr int WIN = ((PX + LBX - 1 + PX - 1) / PX) * PX;
+    constexpr int PW = 32 * PX + WIN;
+    typedef typename S2Vec<CT>::T V;
+    if (CHECKED && (rv < s0 || rv >= vrows)) return;
+    const CT *srow = sblk + (u % RB) * PW + lane * PX;
+    CT v[WIN];
+#pragma unroll
+    for (int i = 0; i < WIN; i += PX) {
+        if (LXT || i < PX + Lx - 1) {
+            V t = *reinterpret_cast<const V *>(srow + i);
+#pragma unroll
+            for (int q = 0; q < PX; ++q) v[i + q] = ((CT *)&t)[q];
+        }
+    }
+    CT mid[NPL][PX];
+#pragma unroll
+    for (int p = 0; p < NPL; ++p)
+#pragma unroll
+        for (int q = 0; q < PX; ++q) mid[p][q] = (CT)0;
+#pragma unroll
+    for (int j = 0; j < LBX; ++j) {
+        if (LXT || j < Lx) {
+#pragma unroll
+            for (int p = 0; p < NPL; ++p) {
+                const CT kj = P.kx[p][j];
+#pragma unroll
+                for (int q = 0; q < PX; ++q) mid[p][q] = mac<CT>(mid[p][q], v[q + j], kj);
+            }
+        }
+    }
+    // stage 2: this row is tap Ly-1-d of the output held in slot (u+1+d) % ROT
+#pragma unroll
+    for (int d = 0; d < LBY; ++d) {
+        if (LYT || d < Ly) {
+            const int slot = (u + 1 + d) % ROT;
+#pragma unroll
+            for (int p = 0; p < NPL; ++p) {
+                const CT kj = P.kyr[p][d];
+#pragma unroll
+                for (int q = 0; q < PX; ++q) acc[p][slot][q] = mac<CT>(acc[p][slot][q], mid[p][q], kj);
+            }
+        }
+    }
+    // output row o = rv-(ROT-1) is complete: emit it and recycle its slot
+    const int eslot = (u + 1) % ROT;
+    if (!CHECKED || rv >= ROT - 1) {
+        if (lane_full) {
+#pragma unroll
+            for (int p = 0; p < NPL; ++p) {
+                V t;
+#pragma unroll
+                for (int q = 0; q < PX; ++q) ((CT *)&t)[q] = acc[p][eslot][q];
+                *reinterpret_cast<V *>(outp[p]) = t;
+            }
+        } else if (lane_live) {
+#pragma unroll
+            for (int p = 0; p < NPL; ++p)
+#pragma unroll
+                for (int q = 0; q < PX; ++q)
+                    if (lane * PX + q < tw) outp[p][q] = acc[p][eslot][q];
+        }
+#pragma unroll
+        for (int p = 0; p < NPL; ++p) outp[p] += P.out_pitch;
+    }
+#pragma unroll
+    for (int p = 0; p < NPL; ++p)
+#pragma unroll
+        for (int q = 0; q < PX; ++q) acc[p][eslot][q] = (CT)0;
+}
+
+template <typename IT, typename CT, int LXT, int LYT, int LB, int NPL, int RB>
 __global__ void __launch_bounds__(S2_WARPS * 32) stream2d_kernel(const S2Params<CT, NPL> P) {
     constexpr int PX = S2Vec<CT>::PX;
-    constexpr int CW = 32 * PX;                         // strip width
-    constexpr int RB = 4;                               // rows per prefetch block
-    constexpr int G = LB > RB ? LB : RB;                // rows per unrolled outer iteration
-    constexpr int NCL = (CW + LB - 1 + 31) / 32;        // loads per lane per input row
-    constexpr int WIN = ((PX + LB - 1 + PX - 1) / PX) * PX;   // window registers (whole 128-bit granules)
-    constexpr int PW = CW + WIN;                        // smem row pitch (elements), multiple of PX
+    constexpr int CW = 32 * PX;                              // strip width
+    constexpr int LBX = LXT ? LXT : LB;                      // compile-time bound of the x taps
+    constexpr int LBY = LYT ? LYT : LB;
+    constexpr int ROT = ((LBY + RB - 1) / RB) * RB;          // accumulator ring size = unroll of the row loop
+    constexpr int NCL = (CW + LBX - 1 + 31) / 32;            // loads per lane per input row
+    constexpr int WIN = ((PX + LBX - 1 + PX - 1) / PX) * PX; // window registers (whole 128-bit granules)
+    constexpr int PW = CW + WIN;                             // smem row pitch (elements), multiple of PX
     typedef typename S2Vec<CT>::T V;
+    static_assert(LBX <= S2_MAXTAPS && LBY <= S2_MAXTAPS, "too many taps");
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -82,155 +183,122 @@ __global__ void __launch_bounds__(S2_WARPS * 32) stream2d_kernel(const S2Params<
     const int sy = (int)((sid / P.nsx) % P.nsy);
     const long long bz = sid / ((long long)P.nsx * P.nsy);
 
+    const int Lx = LXT ? LXT : P.Lx;
+    const int Ly = LYT ? LYT : P.Ly;
     const int x0 = P.rx0 + sx * CW;
     const int y0 = P.ry0 + sy * P.SH;
     const int tw = min(CW, P.rx0 + P.rw - x0);          // live output columns
     const int th = min(P.SH, P.ry0 + P.rh - y0);        // live output rows
-    const int in_rows = th + P.Ly - 1;
-    const int in_cols = CW + P.Lx - 1;
+    const int in_rows = th + Ly - 1;
+    const int in_cols = CW + Lx - 1;
     const IT *__restrict__ img = reinterpret_cast<const IT *>(P.img) + bz * P.img_plane;
+    const bool is_fill = P.style == B2F_FILL;
 
-    // remapped source column of each of this lane's load slots (-1: Fill, -2: beyond the tile)
+    // Source column of each of this lane's load slots, remapped through the border (src/border.jl:564-590).
+    // Loads are unconditional (slots without a pixel read column 0) and patched when parked.
     int gx[NCL];
+    unsigned colfill = 0, coldead = 0;
 #pragma unroll
     for (int c = 0; c < NCL; ++c) {
         const int col = lane + 32 * c;
-        gx[c] = col < in_cols ? (int)remap_index(P.style, (int64_t)x0 + P.klox + col, P.W) : -2;
+        int g = 0;
+        if (col < in_cols) {
+            g = s2_remap(P.style, x0 + P.klox + col, P.W);
+            if (g < 0) { colfill |= 1u << c; g = 0; }
+        } else {
+            coldead |= 1u << c;
+        }
+        gx[c] = g;
     }
+    const int ytop = y0 + P.kloy;                         // image row of strip-local input row 0
+    const bool y_interior = ytop >= 0 && ytop + in_rows <= P.H;
 
-    // Virtual row index rv = r + s0 with s0 = LB - Ly: then output row o = r - (Ly-1) = rv - (LB-1) always sits in
-    // accumulator slot (rv+1) % LB and row r feeds slot (rv+1+d) % LB with tap ky[Ly-1-d] — every register index
-    // is a compile-time constant once the row loop is unrolled by LB (P.kyr holds the taps reversed).
-    const int s0 = LB - P.Ly;
+    // Virtual row index rv = r + s0 with s0 = ROT - Ly: output row o = r-(Ly-1) = rv-(ROT-1) always sits in
+    // accumulator slot (rv+1) % ROT and row r feeds slot (rv+1+d) % ROT with tap ky[Ly-1-d] (= P.kyr[d]):
+    // every register index is a compile-time constant once the row loop is unrolled by ROT.
+    const int s0 = ROT - Ly;
     const int vrows = in_rows + s0;
+    const int nblk = (vrows + RB - 1) / RB;
 
     IT stage[RB][NCL];
-    int stage_ok[RB];   // bit c set: slot c of that row is a real pixel (else Fill)
+    unsigned rowfill = 0;       // bit rr: staged row rr lies in the Fill region
     auto fetch_block = [&](int blk) {
+        rowfill = 0;
 #pragma unroll
         for (int rr = 0; rr < RB; ++rr) {
-            const int r = blk * RB + rr - s0;
-            int ok = 0;
-            if (r >= 0 && r < in_rows) {
-                const int gy = (int)remap_index(P.style, (int64_t)y0 + P.kloy + r, P.H);
-                const IT *row = img + (long long)gy * P.W;
-#pragma unroll
-                for (int c = 0; c < NCL; ++c) {
-                    if (gy >= 0 && gx[c] >= 0) { stage[rr][c] = __ldg(row + gx[c]); ok |= 1 << c; }
-                }
+            int r = blk * RB + rr - s0;
+            r = min(max(r, 0), in_rows - 1);              // rows outside the strip are never used: clamp the address
+            int gy = ytop + r;
+            if (!y_interior) {
+                gy = s2_remap(P.style, gy, P.H);
+                if (gy < 0) { rowfill |= 1u << rr; gy = 0; }
             }
-            stage_ok[rr] = ok;
+            const IT *row = img + (long long)gy * P.W;
+#pragma unroll
+            for (int c = 0; c < NCL; ++c) stage[rr][c] = __ldg(row + gx[c]);
         }
     };
     auto park_block = [&](int blk) {
-        CT *dst = sbuf + (size_t)(blk & 1) * (RB * PW);
+        CT *dst = sbuf + (blk & 1) * (RB * PW) + lane;
 #pragma unroll
         for (int rr = 0; rr < RB; ++rr) {
 #pragma unroll
             for (int c = 0; c < NCL; ++c) {
-                if (gx[c] != -2) {
-                    CT v = P.fill;
-                    if (stage_ok[rr] >> c & 1) v = S2Conv<IT, CT>::f(stage[rr][c], P.n0f8);
-                    dst[rr * PW + lane + 32 * c] = v;
-                }
+                CT v = S2Conv<IT, CT>::f(stage[rr][c], P.n0_r, P.n0_c);
+                if (is_fill && ((colfill >> c | rowfill >> rr) & 1u)) v = P.fill;
+                if (c < NCL - 1 || !((coldead >> c) & 1u)) dst[rr * PW + 32 * c] = v;
             }
         }
     };
 
-    CT acc[NPL][LB][PX];
+    CT acc[NPL][ROT][PX];
 #pragma unroll
     for (int p = 0; p < NPL; ++p)
 #pragma unroll
-        for (int s = 0; s < LB; ++s)
+        for (int s = 0; s < ROT; ++s)
 #pragma unroll
             for (int q = 0; q < PX; ++q) acc[p][s][q] = (CT)0;
 
-    const int nblk = (vrows + RB - 1) / RB;
+    // output pointers of the row being emitted next (row o = 0 first)
+    CT *outp[NPL];
+#pragma unroll
+    for (int p = 0; p < NPL; ++p)
+        outp[p] = reinterpret_cast<CT *>(P.out[p]) + bz * P.out_plane + (long long)(y0 - P.out_oy) * P.out_pitch +
+                  (x0 + lane * PX - P.out_ox);
+    const bool lane_full = P.vec_ok && (lane * PX + PX <= tw);
+    const bool lane_live = lane * PX < tw;
+
     fetch_block(0);
     park_block(0);
     __syncwarp();
 
-    const bool lane_live = lane * PX < tw;
-    const bool lane_full = P.vec_ok && (lane * PX + PX <= tw);
-    for (int rbase = 0; rbase < vrows; rbase += G) {
+    // ---- main loop: groups of ROT rows (= ROT/RB prefetch blocks); the steady state runs without per-row checks ----
+    for (int rbase = 0; rbase < vrows; rbase += ROT) {
+        const int blk0 = rbase / RB;
+        const bool steady = rbase >= ROT && rbase + ROT <= vrows && blk0 + ROT / RB < nblk;
+        if (steady) {
 #pragma unroll
-        for (int u = 0; u < G; ++u) {
-            const int rv = rbase + u;
-            const int blk = rv / RB;
-            if (u % RB == 0 && blk + 1 < nblk) fetch_block(blk + 1);   // loads fly while this block is computed
-            if (rv >= s0 && rv < vrows) {
-                // ---- stage 1 along x: PX outputs from a register window -------------------------------
-                const CT *srow = sbuf + (size_t)(blk & 1) * (RB * PW) + (u % RB) * PW + lane * PX;
-                CT v[WIN];
-#pragma unroll
-                for (int i = 0; i < WIN; i += PX) {
-                    if (i < PX + P.Lx - 1) {
-                        V t = *reinterpret_cast<const V *>(srow + i);
-#pragma unroll
-                        for (int q = 0; q < PX; ++q) v[i + q] = ((CT *)&t)[q];
-                    }
-                }
-                CT mid[NPL][PX];
-#pragma unroll
-                for (int p = 0; p < NPL; ++p)
-#pragma unroll
-                    for (int q = 0; q < PX; ++q) mid[p][q] = (CT)0;
-#pragma unroll
-                for (int j = 0; j < LB; ++j) {
-                    if (j < P.Lx) {
-#pragma unroll
-                        for (int p = 0; p < NPL; ++p) {
-                            const CT kj = P.kx[p][j];
-#pragma unroll
-                            for (int q = 0; q < PX; ++q) mid[p][q] = mac<CT>(mid[p][q], v[q + j], kj);
-                        }
-                    }
-                }
-                // ---- stage 2 along y: this row is tap Ly-1-d of the output held in slot (u+1+d) % LB -----------
-                // (d descending = the order in which the reference adds taps to each output: ascending j)
-#pragma unroll
-                for (int d = 0; d < LB; ++d) {
-                    if (d < P.Ly) {
-                        const int slot = (u + 1 + d) % LB;
-#pragma unroll
-                        for (int p = 0; p < NPL; ++p) {
-                            const CT kj = P.kyr[p][d];
-#pragma unroll
-                            for (int q = 0; q < PX; ++q) acc[p][slot][q] = mac<CT>(acc[p][slot][q], mid[p][q], kj);
-                        }
-                    }
-                }
-                // ---- output row o = rv-(LB-1) is complete: emit it and recycle its slot -----------------------
-                {
-                    const int slot = (u + 1) % LB;
-                    const int o = rv - (LB - 1);
-                    if (o >= 0 && lane_live) {
-                        const long long off = bz * P.out_plane + (long long)(y0 + o - P.out_oy) * P.out_pitch +
-                                              (x0 + lane * PX - P.out_ox);
-#pragma unroll
-                        for (int p = 0; p < NPL; ++p) {
-                            CT *dst = reinterpret_cast<CT *>(P.out[p]) + off;
-                            if (lane_full) {
-                                V t;
-#pragma unroll
-                                for (int q = 0; q < PX; ++q) ((CT *)&t)[q] = acc[p][slot][q];
-                                *reinterpret_cast<V *>(dst) = t;
-                            } else {
-#pragma unroll
-                                for (int q = 0; q < PX; ++q)
-                                    if (lane * PX + q < tw) dst[q] = acc[p][slot][q];
-                            }
-                        }
-                    }
-#pragma unroll
-                    for (int p = 0; p < NPL; ++p)
-#pragma unroll
-                        for (int q = 0; q < PX; ++q) acc[p][slot][q] = (CT)0;
+            for (int u = 0; u < ROT; ++u) {
+                const int blk = blk0 + u / RB;
+                if (u % RB == 0) fetch_block(blk + 1);            // loads fly while this block is computed
+                s2_row<CT, LXT, LYT, LB, NPL, RB, false>(u, rbase + u, P, Lx, Ly, s0, vrows, sbuf + (blk & 1) * (RB * PW),
+                                                        lane, tw, lane_full, lane_live, acc, outp);
+                if (u % RB == RB - 1) {
+                    park_block(blk + 1);
+                    __syncwarp();
                 }
             }
-            if (u % RB == RB - 1 && blk + 1 < nblk) {
-                park_block(blk + 1);
-                __syncwarp();
+        } else {
+#pragma unroll
+            for (int u = 0; u < ROT; ++u) {
+                const int blk = blk0 + u / RB;
+                if (u % RB == 0 && blk + 1 < nblk) fetch_block(blk + 1);
+                s2_row<CT, LXT, LYT, LB, NPL, RB, true>(u, rbase + u, P, Lx, Ly, s0, vrows, sbuf + (blk & 1) * (RB * PW),
+                                                       lane, tw, lane_full, lane_live, acc, outp);
+                if (u % RB == RB - 1 && blk + 1 < nblk) {
+                    park_block(blk + 1);
+                    __syncwarp();
+                }
             }
         }
     }

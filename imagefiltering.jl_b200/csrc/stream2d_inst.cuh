@@ -1,42 +1,50 @@
-// stream2d_inst.cuh — launcher shared by stream2d_f32.cu / stream2d_f64.cu
+// stream2d_inst.cuh — launcher shared by the stream2d_<in>_<ct>.cu instantiation files
 #pragma once
 #include "stream2d.cuh"
 
 namespace b2f {
 
-template <typename IT, typename CT, int LB, int NPL>
+template <typename IT, typename CT, int LXT, int LYT, int LB, int NPL, int RB>
 static int s2_launch_one(const S2Params<CT, NPL> &P, cudaStream_t st) {
     constexpr int PX = S2Vec<CT>::PX;
-    constexpr int WIN = ((PX + LB - 1 + PX - 1) / PX) * PX;
+    constexpr int LBX = LXT ? LXT : LB;
+    constexpr int WIN = ((PX + LBX - 1 + PX - 1) / PX) * PX;
     constexpr int PW = 32 * PX + WIN;
-    const size_t smem = (size_t)S2_WARPS * 2 * 4 * PW * sizeof(CT);
+    const size_t smem = (size_t)S2_WARPS * 2 * RB * PW * sizeof(CT);
     const long long blocks = (P.nstrips + S2_WARPS - 1) / S2_WARPS;
     if (blocks > 0x7fffffffLL) return fail(B2F_ENOTSUP, "stream2d grid too large");
-    stream2d_kernel<IT, CT, LB, NPL><<<(unsigned)blocks, S2_WARPS * 32, smem, st>>>(P);
+    stream2d_kernel<IT, CT, LXT, LYT, LB, NPL, RB><<<(unsigned)blocks, S2_WARPS * 32, smem, st>>>(P);
     count_launch();
     B2F_CUDA(cudaGetLastError());
     return 0;
 }
 
+// hot tap counts get exact instantiations; everything else runs in a bucket with run-time counts
 template <typename IT, typename CT, int NPL>
-static int s2_launch_lb(const S2Params<CT, NPL> &P, cudaStream_t st) {
-    const int L = P.Lx > P.Ly ? P.Lx : P.Ly;
-    if (L <= 4) return s2_launch_one<IT, CT, 4, NPL>(P, st);
-    if (L <= 8) return s2_launch_one<IT, CT, 8, NPL>(P, st);
-    if constexpr (NPL == 1) return s2_launch_one<IT, CT, 16, 1>(P, st);
-    else return fail(B2F_ENOTSUP, "stream2d: two planes need <= 8 taps");
-}
-
-template <typename CT, int NPL>
-static int s2_launch_it(const S2Params<CT, NPL> &P, int img_dt, cudaStream_t st) {
-    switch (img_dt) {
-        case B2F_U8: case B2F_N0F8: return s2_launch_lb<uint8_t, CT, NPL>(P, st);
-        case B2F_F32: return s2_launch_lb<float, CT, NPL>(P, st);
-        case B2F_F64: return s2_launch_lb<double, CT, NPL>(P, st);
+static int s2_launch(const S2Params<CT, NPL> &P, cudaStream_t st) {
+    const int Lx = P.Lx, Ly = P.Ly;
+    const int L = Lx > Ly ? Lx : Ly;
+    if (Lx == 3 && Ly == 3) return s2_launch_one<IT, CT, 3, 3, 4, NPL, 3>(P, st);
+    if constexpr (NPL == 1) {
+        if (Lx == 5 && Ly == 5) return s2_launch_one<IT, CT, 5, 5, 8, 1, 3>(P, st);
+        if (Lx == 7 && Ly == 7) return s2_launch_one<IT, CT, 7, 7, 8, 1, 4>(P, st);
+        if (Lx == 9 && Ly == 9) return s2_launch_one<IT, CT, 9, 9, 16, 1, 3>(P, st);
+        if (Lx == 13 && Ly == 13) return s2_launch_one<IT, CT, 13, 13, 16, 1, 4>(P, st);
+        if (Lx == 17 && Ly == 17) return s2_launch_one<IT, CT, 17, 17, 20, 1, 3>(P, st);
     }
-    return fail(B2F_ENOTSUP, "stream2d: unsupported image dtype");
+    if (L <= 4) return s2_launch_one<IT, CT, 0, 0, 4, NPL, 4>(P, st);
+    if (L <= 8) return s2_launch_one<IT, CT, 0, 0, 8, NPL, 4>(P, st);
+    if constexpr (NPL == 1) {
+        if (L <= 16) return s2_launch_one<IT, CT, 0, 0, 16, 1, 4>(P, st);
+    }
+    return fail(B2F_ENOTSUP, "stream2d: tap count outside the instantiated range");
 }
 
-template <typename CT, int NPL> int launch_stream2d(const S2Params<CT, NPL> &P, int img_dt, cudaStream_t st);
+// one definition per (input type, compute type) lives in its own .cu file so they compile in parallel
+template <typename IT, typename CT, int NPL> int launch_stream2d(const S2Params<CT, NPL> &P, cudaStream_t st);
+
+#define B2F_S2_INSTANTIATE(IT, CT)                                                                                  \
+    template <> int launch_stream2d<IT, CT, 1>(const S2Params<CT, 1> &P, cudaStream_t st) { return s2_launch<IT, CT, 1>(P, st); } \
+    template <> int launch_stream2d<IT, CT, 2>(const S2Params<CT, 2> &P, cudaStream_t st) { return s2_launch<IT, CT, 2>(P, st); }
 
 }  // namespace b2f

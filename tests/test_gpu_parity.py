@@ -236,3 +236,40 @@ def test_slower_paths_stay_bit_exact(ifb, oracle, device, force, monkeypatch):
     gb = ifb.imgradients(img, ifb.KernelFactors.sobel, "reflect", _library=oracle)
     for a, b in zip(ga, gb):
         assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("taps", [(1, 1), (2, 3), (3, 3), (4, 2), (5, 5), (7, 7), (8, 6), (9, 9), (13, 13), (16, 11), (17, 17), (3, 17)])
+@pytest.mark.parametrize("combo", ["f32-f32", "u8-f64", "f64-f64", "f32-f64", "n0f8-f32"])
+def test_stream2d_tap_sweep(ifb, oracle, device, taps, combo):
+    """Every instantiation of the streamed kernel (exact hot sizes and run-time buckets), ragged strip edges,
+    asymmetric tap offsets, all border styles."""
+    src, dst = combo.split("-")
+    rng = np.random.default_rng(hash((taps, combo)) % 2**32)
+    lx, ly = taps
+    kx = ifb.OffsetArray.with_first(rng.standard_normal(lx), (-(lx // 2) + (lx % 3 == 0),))
+    ky = ifb.OffsetArray.with_first(rng.standard_normal(ly).reshape(1, ly), (0, -(ly // 3)))
+    for shape in ((203, 131, 2), (64, 40), (7, 5)):
+        if src == "f32":
+            img = np.asfortranarray(rng.random(shape, dtype=np.float32))
+        elif src == "f64":
+            img = np.asfortranarray(rng.random(shape))
+        else:
+            raw = np.asfortranarray(rng.integers(0, 256, size=shape, dtype=np.uint8))
+            img = ifb.n0f8(raw) if src == "n0f8" else raw
+        T = np.float32 if dst == "f32" else np.float64
+        kern = (kx, ky) if len(shape) == 2 else (
+            ifb.OffsetArray.with_first(kx.parent.reshape(lx, 1, 1), (kx.first[0], 0, 0)),
+            ifb.OffsetArray.with_first(ky.parent.reshape(1, ly, 1), (0, ky.first[1], 0)))
+        for border in BORDERS + [ifb.Fill(0.5 if src != "u8" else 2), ifb.Inner()]:
+            if isinstance(border, str) and border == "reflect" and min(shape[:2]) < 2:
+                continue
+            pa, pb = _both(ifb, oracle, T, img, kern, border)
+            if pa.size == 0:
+                continue
+            if lx > 1 and ly > 1 and (max(lx, ly) <= 16 or (lx, ly) == (17, 17)):
+                assert device.last_path() == "stream2d", (device.last_path(), taps)
+            if dst == "f64":
+                assert np.array_equal(pa, pb), (taps, combo, shape, border)
+            else:
+                tol = _tol([kx.parent, ky.parent], np.asarray(img))
+                assert np.max(np.abs(pa.astype(np.float64) - pb.astype(np.float64))) <= tol, (taps, combo, shape, border)
