@@ -38,9 +38,9 @@ struct E2Params {
     int vec_ok;
 };
 
-template <int WXT, int WYT, int LB, int MODE, int RB, bool CHECKED>
+template <int WXT, int WYT, int LB, int MODE, int RB>
 __device__ __forceinline__ void e2_row(const int u, const int rv, const E2Params &P, const int Wx, const int Wy,
-                                       const int s0, const int vrows, const float *__restrict__ sblk, const int lane,
+                                       const int th, const float *__restrict__ sblk, const int lane,
                                        const int tw, const bool lane_full, const bool lane_live,
                                        float (&amn)[(((WYT ? WYT : LB) + RB - 1) / RB) * RB][4],
                                        float (&amx)[(((WYT ? WYT : LB) + RB - 1) / RB) * RB][4],
@@ -52,7 +52,6 @@ __device__ __forceinline__ void e2_row(const int u, const int rv, const E2Params
     constexpr int WIN = ((PX + LBX - 1 + PX - 1) / PX) * PX;
     constexpr int PW = 32 * PX + WIN;
     constexpr bool DO_MIN = MODE != EX_MAX, DO_MAX = MODE != EX_MIN;
-    if (CHECKED && (rv < s0 || rv >= vrows)) return;
     const float *srow = sblk + (u % RB) * PW + lane * PX;
     float v[WIN];
 #pragma unroll
@@ -87,7 +86,8 @@ __device__ __forceinline__ void e2_row(const int u, const int rv, const E2Params
         }
     }
     const int eslot = (u + 1) % ROT;
-    if (!CHECKED || rv >= ROT - 1) {
+    const int o = rv - (ROT - 1);
+    if (o >= 0 && o < th) {
         if (MODE == EX_PAIR) {
             if (lane_full) {
                 float4 a = make_float4(amn[eslot][0], amx[eslot][0], amn[eslot][1], amx[eslot][1]);
@@ -170,7 +170,6 @@ __global__ void __launch_bounds__(S2_WARPS * 32) extrema2d_kernel(const E2Params
     const bool y_interior = ytop >= 0 && ytop + in_rows <= P.H;
     const int s0 = ROT - Wy;
     const int vrows = in_rows + s0;
-    const int nblk = (vrows + RB - 1) / RB;
 
     float stage[RB][NCL];
     unsigned rowfill = 0;
@@ -219,26 +218,19 @@ __global__ void __launch_bounds__(S2_WARPS * 32) extrema2d_kernel(const E2Params
     park_block(0);
     __syncwarp();
 
+    // Every group of ROT rows runs the same unchecked code: rows before the strip / past its end are clamped
+    // duplicates whose contributions only reach output rows that are never stored (o < 0 or o >= th).
     for (int rbase = 0; rbase < vrows; rbase += ROT) {
         const int blk0 = rbase / RB;
-        const bool steady = rbase >= ROT && rbase + ROT <= vrows && blk0 + ROT / RB < nblk;
-        if (steady) {
 #pragma unroll
-            for (int u = 0; u < ROT; ++u) {
-                const int blk = blk0 + u / RB;
-                if (u % RB == 0) fetch_block(blk + 1);
-                e2_row<WXT, WYT, LB, MODE, RB, false>(u, rbase + u, P, Wx, Wy, s0, vrows, sbuf + (blk & 1) * (RB * PW), lane,
-                                                     tw, lane_full, lane_live, amn, amx, pmn, pmx);
-                if (u % RB == RB - 1) { park_block(blk + 1); __syncwarp(); }
-            }
-        } else {
-#pragma unroll
-            for (int u = 0; u < ROT; ++u) {
-                const int blk = blk0 + u / RB;
-                if (u % RB == 0 && blk + 1 < nblk) fetch_block(blk + 1);
-                e2_row<WXT, WYT, LB, MODE, RB, true>(u, rbase + u, P, Wx, Wy, s0, vrows, sbuf + (blk & 1) * (RB * PW), lane,
-                                                    tw, lane_full, lane_live, amn, amx, pmn, pmx);
-                if (u % RB == RB - 1 && blk + 1 < nblk) { park_block(blk + 1); __syncwarp(); }
+        for (int u = 0; u < ROT; ++u) {
+            const int blk = blk0 + u / RB;
+            if (u % RB == 0) fetch_block(blk + 1);                // loads fly while this block is computed
+            e2_row<WXT, WYT, LB, MODE, RB>(u, rbase + u, P, Wx, Wy, th, sbuf + (blk & 1) * (RB * PW), lane, tw, lane_full,
+                                          lane_live, amn, amx, pmn, pmx);
+            if (u % RB == RB - 1) {
+                park_block(blk + 1);
+                __syncwarp();
             }
         }
     }

@@ -79,10 +79,10 @@ __device__ __forceinline__ int s2_remap(int style, int i, int n) {   // 32-bit t
 
 // One input row of a strip: stage 1 from the smem ring, stage 2 into the register ring, emit the finished
 // output row.  `u` = rv % ROT; it is a literal after the caller's unrolling, so every acc[][slot][] index is static.
-// CHECKED: rows before s0 / past the end are skipped and outputs that do not exist yet are not stored.
-template <typename CT, int LXT, int LYT, int LB, int NPL, int RB, bool CHECKED>
+// Only output rows 0 <= o < th are stored; everything else is computed and dropped.
+template <typename CT, int LXT, int LYT, int LB, int NPL, int RB>
 __device__ __forceinline__ void s2_row(const int u, const int rv, const S2Params<CT, NPL> &P, const int Lx, const int Ly,
-                                       const int s0, const int vrows, const CT *__restrict__ sblk, const int lane,
+                                       const int th, const CT *__restrict__ sblk, const int lane,
                                        const int tw, const bool lane_full, const bool lane_live,
                                        CT (&acc)[NPL][(((LYT ? LYT : LB) + RB - 1) / RB) * RB][S2Vec<CT>::PX],
                                        CT *(&outp)[NPL]) {
@@ -93,7 +93,6 @@ __device__ __forceinline__ void s2_row(const int u, const int rv, const S2Params
     constexpr int WIN = ((PX + LBX - 1 + PX - 1) / PX) * PX;
     constexpr int PW = 32 * PX + WIN;
     typedef typename S2Vec<CT>::T V;
-    if (CHECKED && (rv < s0 || rv >= vrows)) return;
     const CT *srow = sblk + (u % RB) * PW + lane * PX;
     CT v[WIN];
 #pragma unroll
@@ -135,7 +134,8 @@ __device__ __forceinline__ void s2_row(const int u, const int rv, const S2Params
     }
     // output row o = rv-(ROT-1) is complete: emit it and recycle its slot
     const int eslot = (u + 1) % ROT;
-    if (!CHECKED || rv >= ROT - 1) {
+    const int o = rv - (ROT - 1);
+    if (o >= 0 && o < th) {
         if (lane_full) {
 #pragma unroll
             for (int p = 0; p < NPL; ++p) {
@@ -218,7 +218,6 @@ __global__ void __launch_bounds__(S2_WARPS * 32) stream2d_kernel(const S2Params<
     // every register index is a compile-time constant once the row loop is unrolled by ROT.
     const int s0 = ROT - Ly;
     const int vrows = in_rows + s0;
-    const int nblk = (vrows + RB - 1) / RB;
 
     IT stage[RB][NCL];
     unsigned rowfill = 0;       // bit rr: staged row rr lies in the Fill region
@@ -273,32 +272,19 @@ __global__ void __launch_bounds__(S2_WARPS * 32) stream2d_kernel(const S2Params<
     __syncwarp();
 
     // ---- main loop: groups of ROT rows (= ROT/RB prefetch blocks); the steady state runs without per-row checks ----
+    // Every group of ROT rows runs the same unchecked code: rows before the strip / past its end are clamped
+    // duplicates whose contributions only reach output rows that are never stored (o < 0 or o >= th).
     for (int rbase = 0; rbase < vrows; rbase += ROT) {
         const int blk0 = rbase / RB;
-        const bool steady = rbase >= ROT && rbase + ROT <= vrows && blk0 + ROT / RB < nblk;
-        if (steady) {
 #pragma unroll
-            for (int u = 0; u < ROT; ++u) {
-                const int blk = blk0 + u / RB;
-                if (u % RB == 0) fetch_block(blk + 1);            // loads fly while this block is computed
-                s2_row<CT, LXT, LYT, LB, NPL, RB, false>(u, rbase + u, P, Lx, Ly, s0, vrows, sbuf + (blk & 1) * (RB * PW),
-                                                        lane, tw, lane_full, lane_live, acc, outp);
-                if (u % RB == RB - 1) {
-                    park_block(blk + 1);
-                    __syncwarp();
-                }
-            }
-        } else {
-#pragma unroll
-            for (int u = 0; u < ROT; ++u) {
-                const int blk = blk0 + u / RB;
-                if (u % RB == 0 && blk + 1 < nblk) fetch_block(blk + 1);
-                s2_row<CT, LXT, LYT, LB, NPL, RB, true>(u, rbase + u, P, Lx, Ly, s0, vrows, sbuf + (blk & 1) * (RB * PW),
-                                                       lane, tw, lane_full, lane_live, acc, outp);
-                if (u % RB == RB - 1 && blk + 1 < nblk) {
-                    park_block(blk + 1);
-                    __syncwarp();
-                }
+        for (int u = 0; u < ROT; ++u) {
+            const int blk = blk0 + u / RB;
+            if (u % RB == 0) fetch_block(blk + 1);                // loads fly while this block is computed
+            s2_row<CT, LXT, LYT, LB, NPL, RB>(u, rbase + u, P, Lx, Ly, th, sbuf + (blk & 1) * (RB * PW), lane, tw, lane_full,
+                                           lane_live, acc, outp);
+            if (u % RB == RB - 1) {
+                park_block(blk + 1);
+                __syncwarp();
             }
         }
     }
