@@ -38,17 +38,17 @@ struct E2Params {
     int vec_ok;
 };
 
-template <int WXT, int WYT, int LB, int MODE, int RB>
+template <int WXT, int WYT, int LB, int MODE, int RB, int ROT>
 __device__ __forceinline__ void e2_row(const int u, const int rv, const E2Params &P, const int Wx, const int Wy,
                                        const int th, const float *__restrict__ sblk, const int lane,
                                        const int tw, const bool lane_full, const bool lane_live,
-                                       float (&amn)[(((WYT ? WYT : LB) + RB - 1) / RB) * RB][4],
-                                       float (&amx)[(((WYT ? WYT : LB) + RB - 1) / RB) * RB][4],
+                                       float (&amn)[ROT][4],
+                                       float (&amx)[ROT][4],
                                        float *&pmn, float *&pmx) {
     constexpr int PX = 4;
     constexpr int LBX = WXT ? WXT : LB;
     constexpr int LBY = WYT ? WYT : LB;
-    constexpr int ROT = ((LBY + RB - 1) / RB) * RB;
+    static_assert(ROT >= LBY, "ring shorter than the y window");
     constexpr int WIN = ((PX + LBX - 1 + PX - 1) / PX) * PX;
     constexpr int PW = 32 * PX + WIN;
     constexpr bool DO_MIN = MODE != EX_MAX, DO_MAX = MODE != EX_MIN;
@@ -120,13 +120,13 @@ __device__ __forceinline__ void e2_row(const int u, const int rv, const E2Params
     for (int q = 0; q < PX; ++q) { amn[eslot][q] = FLT_MAX * 2.0f; amx[eslot][q] = -FLT_MAX * 2.0f; }   // +inf / -inf
 }
 
-template <int WXT, int WYT, int LB, int MODE, int RB>
+template <int WXT, int WYT, int LB, int MODE, int RB, int ROT>
 __global__ void __launch_bounds__(S2_WARPS * 32) extrema2d_kernel(const E2Params P) {
     constexpr int PX = 4;
     constexpr int CW = 32 * PX;
     constexpr int LBX = WXT ? WXT : LB;
     constexpr int LBY = WYT ? WYT : LB;
-    constexpr int ROT = ((LBY + RB - 1) / RB) * RB;
+    constexpr int G = (ROT / s2_gcd(ROT, RB)) * RB;
     constexpr int NCL = (CW + LBX - 1 + 31) / 32;
     constexpr int WIN = ((PX + LBX - 1 + PX - 1) / PX) * PX;
     constexpr int PW = CW + WIN;
@@ -220,13 +220,13 @@ __global__ void __launch_bounds__(S2_WARPS * 32) extrema2d_kernel(const E2Params
 
     // Every group of ROT rows runs the same unchecked code: rows before the strip / past its end are clamped
     // duplicates whose contributions only reach output rows that are never stored (o < 0 or o >= th).
-    for (int rbase = 0; rbase < vrows; rbase += ROT) {
+    for (int rbase = 0; rbase < vrows; rbase += G) {
         const int blk0 = rbase / RB;
 #pragma unroll
-        for (int u = 0; u < ROT; ++u) {
+        for (int u = 0; u < G; ++u) {
             const int blk = blk0 + u / RB;
             if (u % RB == 0) fetch_block(blk + 1);                // loads fly while this block is computed
-            e2_row<WXT, WYT, LB, MODE, RB>(u, rbase + u, P, Wx, Wy, th, sbuf + (blk & 1) * (RB * PW), lane, tw, lane_full,
+            e2_row<WXT, WYT, LB, MODE, RB, ROT>(u, rbase + u, P, Wx, Wy, th, sbuf + (blk & 1) * (RB * PW), lane, tw, lane_full,
                                           lane_live, amn, amx, pmn, pmx);
             if (u % RB == RB - 1) {
                 park_block(blk + 1);
@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(S2_WARPS * 32) extrema2d_kernel(const E2Params
     }
 }
 
-template <int WXT, int WYT, int LB, int MODE, int RB>
+template <int WXT, int WYT, int LB, int MODE, int RB, int ROT>
 static int e2_launch_one(const E2Params &P, cudaStream_t st) {
     constexpr int PX = 4;
     constexpr int LBX = WXT ? WXT : LB;
@@ -245,7 +245,7 @@ static int e2_launch_one(const E2Params &P, cudaStream_t st) {
     const size_t smem = (size_t)S2_WARPS * 2 * RB * PW * sizeof(float);
     const long long blocks = (P.nstrips + S2_WARPS - 1) / S2_WARPS;
     if (blocks > 0x7fffffffLL) return fail(B2F_ENOTSUP, "extrema2d grid too large");
-    extrema2d_kernel<WXT, WYT, LB, MODE, RB><<<(unsigned)blocks, S2_WARPS * 32, smem, st>>>(P);
+    extrema2d_kernel<WXT, WYT, LB, MODE, RB, ROT><<<(unsigned)blocks, S2_WARPS * 32, smem, st>>>(P);
     count_launch();
     B2F_CUDA(cudaGetLastError());
     return 0;
@@ -254,13 +254,13 @@ static int e2_launch_one(const E2Params &P, cudaStream_t st) {
 template <int MODE>
 static int e2_launch(const E2Params &P, cudaStream_t st) {
     const int Wx = P.Wx, Wy = P.Wy, L = Wx > Wy ? Wx : Wy;
-    if (Wx == 3 && Wy == 3) return e2_launch_one<3, 3, 4, MODE, 3>(P, st);
-    if (Wx == 5 && Wy == 5) return e2_launch_one<5, 5, 8, MODE, 3>(P, st);
-    if (Wx == 7 && Wy == 7) return e2_launch_one<7, 7, 8, MODE, 4>(P, st);
-    if (Wx == 9 && Wy == 9) return e2_launch_one<9, 9, 16, MODE, 3>(P, st);
-    if (L <= 4) return e2_launch_one<0, 0, 4, MODE, 4>(P, st);
-    if (L <= 8) return e2_launch_one<0, 0, 8, MODE, 4>(P, st);
-    if (L <= 16) return e2_launch_one<0, 0, 16, MODE, 4>(P, st);
+    if (Wx == 3 && Wy == 3) return e2_launch_one<3, 3, 4, MODE, 6, 3>(P, st);
+    if (Wx == 5 && Wy == 5) return e2_launch_one<5, 5, 8, MODE, 3, 6>(P, st);
+    if (Wx == 7 && Wy == 7) return e2_launch_one<7, 7, 8, MODE, 4, 8>(P, st);
+    if (Wx == 9 && Wy == 9) return e2_launch_one<9, 9, 16, MODE, 3, 9>(P, st);
+    if (L <= 4) return e2_launch_one<0, 0, 4, MODE, 4, 4>(P, st);
+    if (L <= 8) return e2_launch_one<0, 0, 8, MODE, 4, 8>(P, st);
+    if (L <= 16) return e2_launch_one<0, 0, 16, MODE, 4, 16>(P, st);
     return fail(B2F_ENOTSUP, "extrema2d: window outside the instantiated range");
 }
 

@@ -72,6 +72,8 @@ template <> struct S2Conv<uint8_t, float> {
     }
 };
 
+constexpr int s2_gcd(int a, int b) { return b == 0 ? a : s2_gcd(b, a % b); }
+
 __device__ __forceinline__ int s2_remap(int style, int i, int n) {   // 32-bit twin of remap_index
     if ((unsigned)i < (unsigned)n) return i;
     return (int)remap_index(style, (int64_t)i, (int64_t)n);
@@ -80,16 +82,16 @@ __device__ __forceinline__ int s2_remap(int style, int i, int n) {   // 32-bit t
 // One input row of a strip: stage 1 from the smem ring, stage 2 into the register ring, emit the finished
 // output row.  `u` = rv % ROT; it is a literal after the caller's unrolling, so every acc[][slot][] index is static.
 // Only output rows 0 <= o < th are stored; everything else is computed and dropped.
-template <typename CT, int LXT, int LYT, int LB, int NPL, int RB>
+template <typename CT, int LXT, int LYT, int LB, int NPL, int RB, int ROT>
 __device__ __forceinline__ void s2_row(const int u, const int rv, const S2Params<CT, NPL> &P, const int Lx, const int Ly,
                                        const int th, const CT *__restrict__ sblk, const int lane,
                                        const int tw, const bool lane_full, const bool lane_live,
-                                       CT (&acc)[NPL][(((LYT ? LYT : LB) + RB - 1) / RB) * RB][S2Vec<CT>::PX],
+                                       CT (&acc)[NPL][ROT][S2Vec<CT>::PX],
                                        CT *(&outp)[NPL]) {
     constexpr int PX = S2Vec<CT>::PX;
     constexpr int LBX = LXT ? LXT : LB;
     constexpr int LBY = LYT ? LYT : LB;
-    constexpr int ROT = ((LBY + RB - 1) / RB) * RB;
+    static_assert(ROT >= LBY, "accumulator ring shorter than the y taps");
     constexpr int WIN = ((PX + LBX - 1 + PX - 1) / PX) * PX;
     constexpr int PW = 32 * PX + WIN;
     typedef typename S2Vec<CT>::T V;
@@ -160,13 +162,13 @@ __device__ __forceinline__ void s2_row(const int u, const int rv, const S2Params
         for (int q = 0; q < PX; ++q) acc[p][eslot][q] = (CT)0;
 }
 
-template <typename IT, typename CT, int LXT, int LYT, int LB, int NPL, int RB>
+template <typename IT, typename CT, int LXT, int LYT, int LB, int NPL, int RB, int ROT>
 __global__ void __launch_bounds__(S2_WARPS * 32) stream2d_kernel(const S2Params<CT, NPL> P) {
     constexpr int PX = S2Vec<CT>::PX;
     constexpr int CW = 32 * PX;                              // strip width
     constexpr int LBX = LXT ? LXT : LB;                      // compile-time bound of the x taps
     constexpr int LBY = LYT ? LYT : LB;
-    constexpr int ROT = ((LBY + RB - 1) / RB) * RB;          // accumulator ring size = unroll of the row loop
+    constexpr int G = (ROT / s2_gcd(ROT, RB)) * RB;         // rows per unrolled group: lcm(ring size, prefetch block)
     constexpr int NCL = (CW + LBX - 1 + 31) / 32;            // loads per lane per input row
     constexpr int WIN = ((PX + LBX - 1 + PX - 1) / PX) * PX; // window registers (whole 128-bit granules)
     constexpr int PW = CW + WIN;                             // smem row pitch (elements), multiple of PX
@@ -272,15 +274,15 @@ __global__ void __launch_bounds__(S2_WARPS * 32) stream2d_kernel(const S2Params<
     __syncwarp();
 
     // ---- main loop: groups of ROT rows (= ROT/RB prefetch blocks); the steady state runs without per-row checks ----
-    // Every group of ROT rows runs the same unchecked code: rows before the strip / past its end are clamped
+    // Every group of G rows runs the same unchecked code: rows before the strip / past its end are clamped
     // duplicates whose contributions only reach output rows that are never stored (o < 0 or o >= th).
-    for (int rbase = 0; rbase < vrows; rbase += ROT) {
+    for (int rbase = 0; rbase < vrows; rbase += G) {
         const int blk0 = rbase / RB;
 #pragma unroll
-        for (int u = 0; u < ROT; ++u) {
+        for (int u = 0; u < G; ++u) {
             const int blk = blk0 + u / RB;
             if (u % RB == 0) fetch_block(blk + 1);                // loads fly while this block is computed
-            s2_row<CT, LXT, LYT, LB, NPL, RB>(u, rbase + u, P, Lx, Ly, th, sbuf + (blk & 1) * (RB * PW), lane, tw, lane_full,
+            s2_row<CT, LXT, LYT, LB, NPL, RB, ROT>(u, rbase + u, P, Lx, Ly, th, sbuf + (blk & 1) * (RB * PW), lane, tw, lane_full,
                                            lane_live, acc, outp);
             if (u % RB == RB - 1) {
                 park_block(blk + 1);

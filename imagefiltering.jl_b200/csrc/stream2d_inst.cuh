@@ -4,7 +4,7 @@
 
 namespace b2f {
 
-template <typename IT, typename CT, int LXT, int LYT, int LB, int NPL, int RB>
+template <typename IT, typename CT, int LXT, int LYT, int LB, int NPL, int RB, int ROT>
 static int s2_launch_one(const S2Params<CT, NPL> &P, cudaStream_t st) {
     constexpr int PX = S2Vec<CT>::PX;
     constexpr int LBX = LXT ? LXT : LB;
@@ -13,7 +13,7 @@ static int s2_launch_one(const S2Params<CT, NPL> &P, cudaStream_t st) {
     const size_t smem = (size_t)S2_WARPS * 2 * RB * PW * sizeof(CT);
     const long long blocks = (P.nstrips + S2_WARPS - 1) / S2_WARPS;
     if (blocks > 0x7fffffffLL) return fail(B2F_ENOTSUP, "stream2d grid too large");
-    stream2d_kernel<IT, CT, LXT, LYT, LB, NPL, RB><<<(unsigned)blocks, S2_WARPS * 32, smem, st>>>(P);
+    stream2d_kernel<IT, CT, LXT, LYT, LB, NPL, RB, ROT><<<(unsigned)blocks, S2_WARPS * 32, smem, st>>>(P);
     count_launch();
     B2F_CUDA(cudaGetLastError());
     return 0;
@@ -24,18 +24,18 @@ template <typename IT, typename CT, int NPL>
 static int s2_launch(const S2Params<CT, NPL> &P, cudaStream_t st) {
     const int Lx = P.Lx, Ly = P.Ly;
     const int L = Lx > Ly ? Lx : Ly;
-    if (Lx == 3 && Ly == 3) return s2_launch_one<IT, CT, 3, 3, 4, NPL, 3>(P, st);
+    if (Lx == 3 && Ly == 3) return s2_launch_one<IT, CT, 3, 3, 4, NPL, 6, 3>(P, st);
     if constexpr (NPL == 1) {
-        if (Lx == 5 && Ly == 5) return s2_launch_one<IT, CT, 5, 5, 8, 1, 3>(P, st);
-        if (Lx == 7 && Ly == 7) return s2_launch_one<IT, CT, 7, 7, 8, 1, 4>(P, st);
-        if (Lx == 9 && Ly == 9) return s2_launch_one<IT, CT, 9, 9, 16, 1, 3>(P, st);
-        if (Lx == 13 && Ly == 13) return s2_launch_one<IT, CT, 13, 13, 16, 1, 4>(P, st);
-        if (Lx == 17 && Ly == 17) return s2_launch_one<IT, CT, 17, 17, 20, 1, 3>(P, st);
+        if (Lx == 5 && Ly == 5) return s2_launch_one<IT, CT, 5, 5, 8, 1, 3, 6>(P, st);
+        if (Lx == 7 && Ly == 7) return s2_launch_one<IT, CT, 7, 7, 8, 1, 4, 8>(P, st);
+        if (Lx == 9 && Ly == 9) return s2_launch_one<IT, CT, 9, 9, 16, 1, 3, 9>(P, st);
+        if (Lx == 13 && Ly == 13) return s2_launch_one<IT, CT, 13, 13, 16, 1, 4, 16>(P, st);
+        if (Lx == 17 && Ly == 17) return s2_launch_one<IT, CT, 17, 17, 20, 1, 3, 18>(P, st);
     }
-    if (L <= 4) return s2_launch_one<IT, CT, 0, 0, 4, NPL, 4>(P, st);
-    if (L <= 8) return s2_launch_one<IT, CT, 0, 0, 8, NPL, 4>(P, st);
+    if (L <= 4) return s2_launch_one<IT, CT, 0, 0, 4, NPL, 4, 4>(P, st);
+    if (L <= 8) return s2_launch_one<IT, CT, 0, 0, 8, NPL, 4, 8>(P, st);
     if constexpr (NPL == 1) {
-        if (L <= 16) return s2_launch_one<IT, CT, 0, 0, 16, 1, 4>(P, st);
+        if (L <= 16) return s2_launch_one<IT, CT, 0, 0, 16, 1, 4, 16>(P, st);
     }
     return fail(B2F_ENOTSUP, "stream2d: tap count outside the instantiated range");
 }
