@@ -303,8 +303,12 @@ static int imfilter_planes(const b2f_array *img, const b2f_array *outs, int npla
         } else if (allow_fused && fused2d_applicable(plans.data(), nplanes, img->dtype, odt.data())) {
             rc = run_fused2d(plans.data(), nplanes, sin.dptr, img->dtype, dout.data(), odt.data(), st);
         } else {
-            for (int p = 0; p < nplanes && !rc; ++p)
-                rc = run_generic(plans[p], sin.dptr, img->dtype, dout[p], odt[p], st);
+            for (int p = 0; p < nplanes && !rc; ++p) {
+                if (!force && dense2d_applicable(plans[p], img->dtype, odt[p]))
+                    rc = run_dense2d(plans[p], sin.dptr, img->dtype, dout[p], odt[p], st);
+                else
+                    rc = run_generic(plans[p], sin.dptr, img->dtype, dout[p], odt[p], st);
+            }
         }
         for (int p = 0; p < nplanes && !rc; ++p)
             if (outs[p].mem == B2F_HOST && souts[p].bytes) {

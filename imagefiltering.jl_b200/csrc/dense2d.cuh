@@ -1,0 +1,183 @@
+// dense2d.cuh — K2: dense (non-separable) 2-D FIR, register-blocked FP32/FP64 FMA.
+//
+// Replaces the reference's dense loop (src/imfilter.jl:624-669: out[I] = sum_J A[I+J]*k[J], J column-major
+// ascending) and the padded copy in front of it (src/border.jl:324-347) for one dense 2-D kernel stage.
+// This is the FP32-pipe-bound kernel of the path (27x27 LoG: 729 FMA per pixel vs 8 bytes).
+//
+// A CTA owns a tile of TX x 32 outputs.  The input tile + halo is loaded once into shared memory through the
+// border remap tables.  Each lane owns R adjacent columns (one 128-bit vector), each warp T=4 output rows.  Per
+// input row the lane loads its register window (R+KX-1 values, 128-bit conflict-free LDS) ONCE and applies it to
+// its T output rows with T different kernel rows; taps come from shared memory as broadcast 128-bit loads.
+//   CT=double: one accumulator per output, taps in the reference's order (J outer, j inner), separate
+//              multiply and add -> bit-exact against the oracle.
+//   CT=float:  FMA; one partial sum per kernel row, then summed (error <= (KX+KY)*2^-24*sum|k|*max|x|, inside the
+//              1e-5 tolerance for any kernel size this kernel accepts).
+#pragma once
+
+#include "common.cuh"
+
+namespace b2f {
+
+constexpr int D2_T = 4;          // output rows per warp
+constexpr int D2_WARPS = 8;
+constexpr int D2_TY = D2_T * D2_WARPS;
+constexpr int D2_MAXKY = 64;
+
+template <typename CT>
+struct D2Params {
+    const void *img;
+    int img_dt;
+    int W, H;
+    long long img_plane;
+    void *out;
+    long long out_pitch, out_plane;
+    int out_ox, out_oy;
+    int rx0, ry0, rw, rh;
+    int style;
+    CT fill;
+    int Kx, Ky, klox, kloy;
+    const CT *taps;           // device, [Ky][KXP] row-major (kernel row J contiguous in j), KXP = roundup(Kx, V)
+    int in_rows, in_cols, P1; // input tile incl. halo, smem pitch
+};
+
+template <typename CT> struct D2Vec;
+template <> struct D2Vec<float> { typedef float4 T; static constexpr int N = 4; };
+template <> struct D2Vec<double> { typedef double2 T; static constexpr int N = 2; };
+
+template <typename CT, int KX>
+__global__ void __launch_bounds__(D2_WARPS * 32) dense2d_kernel(const D2Params<CT> P) {
+    constexpr int R = D2Vec<CT>::N;
+    constexpr int TX = 32 * R;
+    constexpr int KXP = ((KX + R - 1) / R) * R;
+    constexpr int WIN = ((R + KX - 1 + R - 1) / R) * R;
+    typedef typename D2Vec<CT>::T V;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    CT *s_in = reinterpret_cast<CT *>(smem_raw);
+    CT *s_k = s_in + (size_t)P.in_rows * P.P1;
+    int *s_ix = reinterpret_cast<int *>(s_k + (size_t)P.Ky * KXP);
+    int *s_iy = s_ix + P.in_cols;
+
+    const int x0 = P.rx0 + blockIdx.x * TX;
+    const int y0 = P.ry0 + blockIdx.y * D2_TY;
+    const long long bz = blockIdx.z;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    for (int c = threadIdx.x; c < P.in_cols; c += blockDim.x)
+        s_ix[c] = (int)remap_index(P.style, (int64_t)x0 + P.klox + c, P.W);
+    for (int r = threadIdx.x; r < P.in_rows; r += blockDim.x)
+        s_iy[r] = (int)remap_index(P.style, (int64_t)y0 + P.kloy + r, P.H);
+    for (int t = threadIdx.x; t < P.Ky * KXP; t += blockDim.x) s_k[t] = P.taps[t];
+    __syncthreads();
+    {
+        const long long base = bz * P.img_plane;
+        for (int r = warp; r < P.in_rows; r += D2_WARPS) {
+            const int gy = s_iy[r];
+            CT *dst = s_in + (size_t)r * P.P1;
+            const long long rowoff = base + (long long)gy * P.W;
+#pragma unroll 4
+            for (int c = lane; c < P.in_cols; c += 32) {
+                const int gx = s_ix[c];
+                CT v = P.fill;
+                if (gx >= 0 && gy >= 0) v = load_elem<CT>(P.img, P.img_dt, rowoff + gx);
+                dst[c] = v;
+            }
+        }
+    }
+    __syncthreads();
+
+    CT acc[D2_T][R];
+#pragma unroll
+    for (int t = 0; t < D2_T; ++t)
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[t][r] = (CT)0;
+
+    const int Ky = P.Ky;
+    const CT *sbase = s_in + (size_t)(warp * D2_T) * P.P1 + lane * R;
+    for (int ry = 0; ry < D2_T + Ky - 1; ++ry) {
+        CT v[WIN];
+        const CT *srow = sbase + (size_t)ry * P.P1;
+#pragma unroll
+        for (int i = 0; i < WIN; i += R) {
+            V tv = *reinterpret_cast<const V *>(srow + i);
+#pragma unroll
+            for (int q = 0; q < R; ++q) v[i + q] = ((CT *)&tv)[q];
+        }
+#pragma unroll
+        for (int t = 0; t < D2_T; ++t) {
+            const int J = ry - t;
+            if (J >= 0 && J < Ky) {
+                const CT *kr = s_k + J * KXP;
+                CT part[R];
+#pragma unroll
+                for (int r = 0; r < R; ++r) part[r] = sizeof(CT) == 4 ? (CT)0 : acc[t][r];
+#pragma unroll
+                for (int j4 = 0; j4 < KXP; j4 += R) {
+                    V kv = *reinterpret_cast<const V *>(kr + j4);
+#pragma unroll
+                    for (int q = 0; q < R; ++q) {
+                        if (j4 + q < KX) {
+                            const CT kj = ((CT *)&kv)[q];
+#pragma unroll
+                            for (int r = 0; r < R; ++r) part[r] = mac<CT>(part[r], v[r + j4 + q], kj);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < R; ++r) acc[t][r] = sizeof(CT) == 4 ? acc[t][r] + part[r] : part[r];
+            }
+        }
+    }
+
+    const int tw = min(TX, P.rx0 + P.rw - x0);
+    const int th = min(D2_TY, P.ry0 + P.rh - y0);
+#pragma unroll
+    for (int t = 0; t < D2_T; ++t) {
+        const int row = warp * D2_T + t;
+        if (row < th) {
+            CT *o = (CT *)P.out + bz * P.out_plane + (long long)(y0 + row - P.out_oy) * P.out_pitch + (x0 + lane * R - P.out_ox);
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+                if (lane * R + r < tw) o[r] = acc[t][r];
+        }
+    }
+}
+
+template <typename CT, int KX>
+static int d2_launch_one(D2Params<CT> &P, int nbatch, cudaStream_t st) {
+    constexpr int R = D2Vec<CT>::N;
+    constexpr int TX = 32 * R;
+    constexpr int KXP = ((KX + R - 1) / R) * R;
+    constexpr int WIN = ((R + KX - 1 + R - 1) / R) * R;
+    P.in_rows = D2_TY + P.Ky - 1;
+    P.in_cols = TX + KX - 1;
+    P.P1 = TX - R + WIN;                  // window over-read stays inside the row; multiple of R
+    const size_t smem = sizeof(CT) * ((size_t)P.in_rows * P.P1 + (size_t)P.Ky * KXP) + sizeof(int) * (size_t)(P.in_cols + P.in_rows);
+    auto kern = dense2d_kernel<CT, KX>;
+    static thread_local size_t configured = 0;
+    if (smem > 227 * 1024) return fail(B2F_ENOTSUP, "dense2d tile does not fit shared memory");
+    if (smem > configured) {
+        B2F_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    dim3 grid((P.rw + TX - 1) / TX, (P.rh + D2_TY - 1) / D2_TY, nbatch);
+    if (grid.y > 65535 || grid.z > 65535) return fail(B2F_ENOTSUP, "dense2d grid too large");
+    kern<<<grid, D2_WARPS * 32, smem, st>>>(P);
+    count_launch();
+    B2F_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <typename CT, int LO, int HI>
+static int d2_dispatch(D2Params<CT> &P, int nbatch, cudaStream_t st) {
+    if constexpr (LO == HI) {
+        return d2_launch_one<CT, LO>(P, nbatch, st);
+    } else {
+        constexpr int MID = (LO + HI) / 2;
+        return P.Kx <= MID ? d2_dispatch<CT, LO, MID>(P, nbatch, st) : d2_dispatch<CT, MID + 1, HI>(P, nbatch, st);
+    }
+}
+
+int launch_dense2d_f32(D2Params<float> &P, int nbatch, cudaStream_t st);
+int launch_dense2d_f64(D2Params<double> &P, int nbatch, cudaStream_t st);
+
+}  // namespace b2f

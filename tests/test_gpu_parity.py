@@ -273,3 +273,40 @@ def test_stream2d_tap_sweep(ifb, oracle, device, taps, combo):
             else:
                 tol = _tol([kx.parent, ky.parent], np.asarray(img))
                 assert np.max(np.abs(pa.astype(np.float64) - pb.astype(np.float64))) <= tol, (taps, combo, shape, border)
+
+
+@pytest.mark.parametrize("ksize", [(2, 2), (3, 5), (7, 4), (16, 9), (27, 27), (32, 13), (5, 40)])
+def test_dense2d_parity(ifb, oracle, device, ksize):
+    """K2: dense non-separable kernels (Kernel.LoG-like), exact in Float64, tolerance in Float32."""
+    rng = np.random.default_rng(hash(ksize) % 2**32)
+    kx, ky = ksize
+    kern = ifb.OffsetArray.with_first(rng.standard_normal((kx, ky)), (-(kx // 2), -(ky // 3)))
+    for shape, dt in (((150, 70), "f32"), ((64, 64, 2), "f64"), ((33, 90), "u8"), ((9, 7), "f32")):
+        if dt == "f32":
+            img = np.asfortranarray(rng.random(shape, dtype=np.float32))
+        elif dt == "f64":
+            img = np.asfortranarray(rng.random(shape))
+        else:
+            img = np.asfortranarray(rng.integers(0, 256, size=shape, dtype=np.uint8))
+        k = kern if len(shape) == 2 else ifb.OffsetArray.with_first(kern.parent.reshape(kx, ky, 1), kern.first + (0,))
+        for border in BORDERS + [ifb.Fill(1.0), ifb.Inner()]:
+            pa, pb = _both(ifb, oracle, np.float64, img, (k,), border)
+            if pa.size == 0:
+                continue
+            assert device.last_path() == "dense2d", device.last_path()
+            assert np.array_equal(pa, pb), (ksize, shape, dt, border)
+            pa, pb = _both(ifb, oracle, np.float32, img, (k,), border)
+            tol = _tol([kern.parent], np.asarray(img))
+            assert np.max(np.abs(pa.astype(np.float64) - pb.astype(np.float64))) <= tol, (ksize, shape, dt, border)
+
+
+def test_log3_circular_config3_small(ifb, oracle, device):
+    """BASELINE config 3 in miniature: Kernel.LoG(3) (27x27, rank 2 -> dense path) with Pad(:circular)."""
+    rng = np.random.default_rng(3)
+    img = np.asfortranarray(rng.random((200, 160), dtype=np.float32))
+    k = ifb.Kernel.LoG(3)
+    pa, pb = _both(ifb, oracle, np.float32, img, k, "circular")
+    assert device.last_path() == "dense2d"
+    assert np.max(np.abs(pa.astype(np.float64) - pb.astype(np.float64))) <= _tol([k.parent], img)
+    pa, pb = _both(ifb, oracle, img, k, "circular")           # reference-typed Float64 result: bit-exact
+    assert pa.dtype == np.float64 and np.array_equal(pa, pb)
