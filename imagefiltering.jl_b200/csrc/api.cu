@@ -304,7 +304,9 @@ static int imfilter_planes(const b2f_array *img, const b2f_array *outs, int npla
             rc = run_fused2d(plans.data(), nplanes, sin.dptr, img->dtype, dout.data(), odt.data(), st);
         } else {
             for (int p = 0; p < nplanes && !rc; ++p) {
-                if (!force && dense2d_applicable(plans[p], img->dtype, odt[p]))
+                if (!force && sepnd_applicable(plans[p], img->dtype, odt[p]))
+                    rc = run_sepnd(plans[p], sin.dptr, img->dtype, dout[p], odt[p], st);
+                else if (!force && dense2d_applicable(plans[p], img->dtype, odt[p]))
                     rc = run_dense2d(plans[p], sin.dptr, img->dtype, dout[p], odt[p], st);
                 else
                     rc = run_generic(plans[p], sin.dptr, img->dtype, dout[p], odt[p], st);

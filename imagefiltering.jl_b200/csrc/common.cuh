@@ -226,6 +226,9 @@ int run_fused2d(const Plan *plans, int nplanes, const void *d_img, int img_dt, v
 bool stream2d_applicable(const Plan *plans, int nplanes, int img_dt, const int *out_dt);
 int run_stream2d(const Plan *plans, int nplanes, const void *d_img, int img_dt, void *const *d_outs,
                  const int *out_dt, cudaStream_t st);
+// N-d separable cascade as a chain of streamed passes (also the 3-D path)
+bool sepnd_applicable(const Plan &P, int img_dt, int out_dt);
+int run_sepnd(const Plan &P, const void *d_img, int img_dt, void *d_out, int out_dt, cudaStream_t st);
 // dense 2-D single stage (register-blocked FMA)
 bool dense2d_applicable(const Plan &P, int img_dt, int out_dt);
 int run_dense2d(const Plan &P, const void *d_img, int img_dt, void *d_out, int out_dt, cudaStream_t st);

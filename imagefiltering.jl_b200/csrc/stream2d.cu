@@ -39,6 +39,7 @@ static int run_typed(const Plan *plans, const void *d_img, int img_dt, void *con
     P.n0_r = img_dt == B2F_N0F8 ? (CT)1 / (CT)255 : (CT)1;
     P.n0_c = img_dt == B2F_N0F8 ? (CT)255 : (CT)1;
     P.W = (int)P0.img_ax.len(0); P.H = (int)P0.img_ax.len(1);
+    P.Hg = P.H; P.y_first = 0;
     P.img_plane = (long long)P.W * P.H;
     P.out_pitch = P0.out_ax.len(0);
     P.out_plane = P0.out_ax.len(0) * P0.out_ax.len(1);

@@ -33,7 +33,8 @@ template <typename CT, int NPL>
 struct S2Params {
     const void *img;
     CT n0_r, n0_c;            // u8 -> CT: q=x*r; q += fma(-q,c,x)*r.  (1/255,255) for N0f8, (1,1) for raw bytes
-    int W, H;
+    int W, H;                 // extent of the array along x / y (y: rows present in this buffer)
+    int Hg, y_first;          // slab form: the full axis has Hg rows and buffer row 0 is global row y_first
     long long img_plane;
     void *out[NPL];
     long long out_pitch, out_plane;
@@ -82,15 +83,15 @@ __device__ __forceinline__ int s2_remap(int style, int i, int n) {   // 32-bit t
 // One input row of a strip: stage 1 from the smem ring, stage 2 into the register ring, emit the finished
 // output row.  `u` = rv % ROT; it is a literal after the caller's unrolling, so every acc[][slot][] index is static.
 // Only output rows 0 <= o < th are stored; everything else is computed and dropped.
-template <typename CT, int LXT, int LYT, int LB, int NPL, int RB, int ROT>
+template <typename CT, int LXT, int LYT, int LB, int NPL, int RB, int ROT, bool XS, bool YS>
 __device__ __forceinline__ void s2_row(const int u, const int rv, const S2Params<CT, NPL> &P, const int Lx, const int Ly,
                                        const int th, const CT *__restrict__ sblk, const int lane,
                                        const int tw, const bool lane_full, const bool lane_live,
                                        CT (&acc)[NPL][ROT][S2Vec<CT>::PX],
                                        CT *(&outp)[NPL]) {
     constexpr int PX = S2Vec<CT>::PX;
-    constexpr int LBX = LXT ? LXT : LB;
-    constexpr int LBY = LYT ? LYT : LB;
+    constexpr int LBX = XS ? (LXT ? LXT : LB) : 1;
+    constexpr int LBY = YS ? (LYT ? LYT : LB) : 1;
     static_assert(ROT >= LBY, "accumulator ring shorter than the y taps");
     constexpr int WIN = ((PX + LBX - 1 + PX - 1) / PX) * PX;
     constexpr int PW = 32 * PX + WIN;
@@ -110,20 +111,27 @@ __device__ __forceinline__ void s2_row(const int u, const int rv, const S2Params
     for (int p = 0; p < NPL; ++p)
 #pragma unroll
         for (int q = 0; q < PX; ++q) mid[p][q] = (CT)0;
+    if (XS) {
 #pragma unroll
-    for (int j = 0; j < LBX; ++j) {
-        if (LXT || j < Lx) {
+        for (int j = 0; j < LBX; ++j) {
+            if (LXT || j < Lx) {
 #pragma unroll
-            for (int p = 0; p < NPL; ++p) {
-                const CT kj = P.kx[p][j];
+                for (int p = 0; p < NPL; ++p) {
+                    const CT kj = P.kx[p][j];
 #pragma unroll
-                for (int q = 0; q < PX; ++q) mid[p][q] = mac<CT>(mid[p][q], v[q + j], kj);
+                    for (int q = 0; q < PX; ++q) mid[p][q] = mac<CT>(mid[p][q], v[q + j], kj);
+                }
             }
         }
+    } else {   // no stage along x: the row itself feeds stage 2
+#pragma unroll
+        for (int p = 0; p < NPL; ++p)
+#pragma unroll
+            for (int q = 0; q < PX; ++q) mid[p][q] = v[q];
     }
     // stage 2: this row is tap Ly-1-d of the output held in slot (u+1+d) % ROT
 #pragma unroll
-    for (int d = 0; d < LBY; ++d) {
+    for (int d = 0; d < (YS ? LBY : 0); ++d) {
         if (LYT || d < Ly) {
             const int slot = (u + 1 + d) % ROT;
 #pragma unroll
@@ -143,7 +151,7 @@ __device__ __forceinline__ void s2_row(const int u, const int rv, const S2Params
             for (int p = 0; p < NPL; ++p) {
                 V t;
 #pragma unroll
-                for (int q = 0; q < PX; ++q) ((CT *)&t)[q] = acc[p][eslot][q];
+                for (int q = 0; q < PX; ++q) ((CT *)&t)[q] = YS ? acc[p][eslot][q] : mid[p][q];
                 *reinterpret_cast<V *>(outp[p]) = t;
             }
         } else if (lane_live) {
@@ -151,7 +159,7 @@ __device__ __forceinline__ void s2_row(const int u, const int rv, const S2Params
             for (int p = 0; p < NPL; ++p)
 #pragma unroll
                 for (int q = 0; q < PX; ++q)
-                    if (lane * PX + q < tw) outp[p][q] = acc[p][eslot][q];
+                    if (lane * PX + q < tw) outp[p][q] = YS ? acc[p][eslot][q] : mid[p][q];
         }
 #pragma unroll
         for (int p = 0; p < NPL; ++p) outp[p] += P.out_pitch;
@@ -162,12 +170,13 @@ __device__ __forceinline__ void s2_row(const int u, const int rv, const S2Params
         for (int q = 0; q < PX; ++q) acc[p][eslot][q] = (CT)0;
 }
 
-template <typename IT, typename CT, int LXT, int LYT, int LB, int NPL, int RB, int ROT>
+template <typename IT, typename CT, int LXT, int LYT, int LB, int NPL, int RB, int ROT, bool XS = true, bool YS = true>
 __global__ void __launch_bounds__(S2_WARPS * 32) stream2d_kernel(const S2Params<CT, NPL> P) {
     constexpr int PX = S2Vec<CT>::PX;
     constexpr int CW = 32 * PX;                              // strip width
-    constexpr int LBX = LXT ? LXT : LB;                      // compile-time bound of the x taps
-    constexpr int LBY = LYT ? LYT : LB;
+    constexpr int LBX = XS ? (LXT ? LXT : LB) : 1;           // compile-time bound of the x taps (1: no x stage)
+    constexpr int LBY = YS ? (LYT ? LYT : LB) : 1;
+    static_assert(YS || ROT == 1, "no y stage: the ring is a single pass-through slot");
     constexpr int G = (ROT / s2_gcd(ROT, RB)) * RB;         // rows per unrolled group: lcm(ring size, prefetch block)
     constexpr int NCL = (CW + LBX - 1 + 31) / 32;            // loads per lane per input row
     constexpr int WIN = ((PX + LBX - 1 + PX - 1) / PX) * PX; // window registers (whole 128-bit granules)
@@ -185,8 +194,8 @@ __global__ void __launch_bounds__(S2_WARPS * 32) stream2d_kernel(const S2Params<
     const int sy = (int)((sid / P.nsx) % P.nsy);
     const long long bz = sid / ((long long)P.nsx * P.nsy);
 
-    const int Lx = LXT ? LXT : P.Lx;
-    const int Ly = LYT ? LYT : P.Ly;
+    const int Lx = XS ? (LXT ? LXT : P.Lx) : 1;
+    const int Ly = YS ? (LYT ? LYT : P.Ly) : 1;
     const int x0 = P.rx0 + sx * CW;
     const int y0 = P.ry0 + sy * P.SH;
     const int tw = min(CW, P.rx0 + P.rw - x0);          // live output columns
@@ -205,14 +214,14 @@ __global__ void __launch_bounds__(S2_WARPS * 32) stream2d_kernel(const S2Params<
         const int col = lane + 32 * c;
         int g = 0;
         if (col < in_cols) {
-            g = s2_remap(P.style, x0 + P.klox + col, P.W);
+            g = s2_remap(P.style, x0 + (XS ? P.klox : 0) + col, P.W);
             if (g < 0) { colfill |= 1u << c; g = 0; }
         } else {
             coldead |= 1u << c;
         }
         gx[c] = g;
     }
-    const int ytop = y0 + P.kloy;                         // image row of strip-local input row 0
+    const int ytop = y0 + (YS ? P.kloy : 0);              // buffer row of strip-local input row 0
     const bool y_interior = ytop >= 0 && ytop + in_rows <= P.H;
 
     // Virtual row index rv = r + s0 with s0 = ROT - Ly: output row o = r-(Ly-1) = rv-(ROT-1) always sits in
@@ -230,9 +239,10 @@ __global__ void __launch_bounds__(S2_WARPS * 32) stream2d_kernel(const S2Params<
             int r = blk * RB + rr - s0;
             r = min(max(r, 0), in_rows - 1);              // rows outside the strip are never used: clamp the address
             int gy = ytop + r;
-            if (!y_interior) {
-                gy = s2_remap(P.style, gy, P.H);
-                if (gy < 0) { rowfill |= 1u << rr; gy = 0; }
+            if (!y_interior && (unsigned)gy >= (unsigned)P.H) {
+                // outside this buffer: apply the border in GLOBAL row coordinates (slab form; y_first = 0, Hg = H otherwise)
+                gy = s2_remap(P.style, gy + P.y_first, P.Hg);
+                if (gy < 0) { rowfill |= 1u << rr; gy = 0; } else gy -= P.y_first;
             }
             const IT *row = img + (long long)gy * P.W;
 #pragma unroll
@@ -282,7 +292,7 @@ __global__ void __launch_bounds__(S2_WARPS * 32) stream2d_kernel(const S2Params<
         for (int u = 0; u < G; ++u) {
             const int blk = blk0 + u / RB;
             if (u % RB == 0) fetch_block(blk + 1);                // loads fly while this block is computed
-            s2_row<CT, LXT, LYT, LB, NPL, RB, ROT>(u, rbase + u, P, Lx, Ly, th, sbuf + (blk & 1) * (RB * PW), lane, tw, lane_full,
+            s2_row<CT, LXT, LYT, LB, NPL, RB, ROT, XS, YS>(u, rbase + u, P, Lx, Ly, th, sbuf + (blk & 1) * (RB * PW), lane, tw, lane_full,
                                            lane_live, acc, outp);
             if (u % RB == RB - 1) {
                 park_block(blk + 1);

@@ -1,19 +1,21 @@
 // stream2d_inst.cuh — launcher shared by the stream2d_<in>_<ct>.cu instantiation files
 #pragma once
+#include <type_traits>
+
 #include "stream2d.cuh"
 
 namespace b2f {
 
-template <typename IT, typename CT, int LXT, int LYT, int LB, int NPL, int RB, int ROT>
+template <typename IT, typename CT, int LXT, int LYT, int LB, int NPL, int RB, int ROT, bool XS = true, bool YS = true>
 static int s2_launch_one(const S2Params<CT, NPL> &P, cudaStream_t st) {
     constexpr int PX = S2Vec<CT>::PX;
-    constexpr int LBX = LXT ? LXT : LB;
+    constexpr int LBX = XS ? (LXT ? LXT : LB) : 1;
     constexpr int WIN = ((PX + LBX - 1 + PX - 1) / PX) * PX;
     constexpr int PW = 32 * PX + WIN;
     const size_t smem = (size_t)S2_WARPS * 2 * RB * PW * sizeof(CT);
     const long long blocks = (P.nstrips + S2_WARPS - 1) / S2_WARPS;
     if (blocks > 0x7fffffffLL) return fail(B2F_ENOTSUP, "stream2d grid too large");
-    stream2d_kernel<IT, CT, LXT, LYT, LB, NPL, RB, ROT><<<(unsigned)blocks, S2_WARPS * 32, smem, st>>>(P);
+    stream2d_kernel<IT, CT, LXT, LYT, LB, NPL, RB, ROT, XS, YS><<<(unsigned)blocks, S2_WARPS * 32, smem, st>>>(P);
     count_launch();
     B2F_CUDA(cudaGetLastError());
     return 0;
@@ -40,11 +42,38 @@ static int s2_launch(const S2Params<CT, NPL> &P, cudaStream_t st) {
     return fail(B2F_ENOTSUP, "stream2d: tap count outside the instantiated range");
 }
 
+// a single 1-D stage: along x only (no y stage) or along y only (no x stage), one plane
+template <typename IT, typename CT>
+static int s2_launch_single(const S2Params<CT, 1> &P, bool along_x, cudaStream_t st) {
+    if (along_x) {
+        const int L = P.Lx;
+        if constexpr (std::is_same<IT, CT>::value) {
+            if (L == 13) return s2_launch_one<IT, CT, 13, 0, 16, 1, 8, 1, true, false>(P, st);
+            if (L == 17) return s2_launch_one<IT, CT, 17, 0, 20, 1, 8, 1, true, false>(P, st);
+        }
+        if (L <= 4) return s2_launch_one<IT, CT, 0, 0, 4, 1, 8, 1, true, false>(P, st);
+        if (L <= 8) return s2_launch_one<IT, CT, 0, 0, 8, 1, 8, 1, true, false>(P, st);
+        if (L <= 16) return s2_launch_one<IT, CT, 0, 0, 16, 1, 8, 1, true, false>(P, st);
+    } else {
+        const int L = P.Ly;
+        if constexpr (std::is_same<IT, CT>::value) {
+            if (L == 13) return s2_launch_one<IT, CT, 0, 13, 16, 1, 4, 16, false, true>(P, st);
+            if (L == 17) return s2_launch_one<IT, CT, 0, 17, 20, 1, 3, 18, false, true>(P, st);
+        }
+        if (L <= 4) return s2_launch_one<IT, CT, 0, 0, 4, 1, 4, 4, false, true>(P, st);
+        if (L <= 8) return s2_launch_one<IT, CT, 0, 0, 8, 1, 4, 8, false, true>(P, st);
+        if (L <= 16) return s2_launch_one<IT, CT, 0, 0, 16, 1, 4, 16, false, true>(P, st);
+    }
+    return fail(B2F_ENOTSUP, "stream2d: tap count outside the instantiated range");
+}
+
 // one definition per (input type, compute type) lives in its own .cu file so they compile in parallel
 template <typename IT, typename CT, int NPL> int launch_stream2d(const S2Params<CT, NPL> &P, cudaStream_t st);
+template <typename IT, typename CT> int launch_stream1d(const S2Params<CT, 1> &P, bool along_x, cudaStream_t st);
 
 #define B2F_S2_INSTANTIATE(IT, CT)                                                                                  \
     template <> int launch_stream2d<IT, CT, 1>(const S2Params<CT, 1> &P, cudaStream_t st) { return s2_launch<IT, CT, 1>(P, st); } \
-    template <> int launch_stream2d<IT, CT, 2>(const S2Params<CT, 2> &P, cudaStream_t st) { return s2_launch<IT, CT, 2>(P, st); }
+    template <> int launch_stream2d<IT, CT, 2>(const S2Params<CT, 2> &P, cudaStream_t st) { return s2_launch<IT, CT, 2>(P, st); } \
+    template <> int launch_stream1d<IT, CT>(const S2Params<CT, 1> &P, bool ax, cudaStream_t st) { return s2_launch_single<IT, CT>(P, ax, st); }
 
 }  // namespace b2f

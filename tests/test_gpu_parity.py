@@ -118,7 +118,7 @@ def test_generic_path_cases(ifb, oracle, device):
         for border in BORDERS + [ifb.Fill(0.3), ifb.Inner()]:
             pa, pb = _both(ifb, oracle, img, kern, border)
             assert np.array_equal(pa, pb), (img.shape, border)
-            assert device.last_path() in ("generic", "dense2d", "fused3d", "fused2d", "stream2d")
+            assert device.last_path() in ("generic", "dense2d", "sepnd", "fused2d", "stream2d")
 
 
 def test_integer_exact_and_inexact(ifb, oracle, device):
@@ -310,3 +310,90 @@ def test_log3_circular_config3_small(ifb, oracle, device):
     assert np.max(np.abs(pa.astype(np.float64) - pb.astype(np.float64))) <= _tol([k.parent], img)
     pa, pb = _both(ifb, oracle, img, k, "circular")           # reference-typed Float64 result: bit-exact
     assert pa.dtype == np.float64 and np.array_equal(pa, pb)
+
+
+@pytest.mark.parametrize("border", BORDERS + ["fill"])
+def test_sepnd_parity(ifb, oracle, device, border):
+    """N-d separable cascades as chained streamed passes (3-D gaussian = BASELINE config 5 in miniature,
+    single-axis stages, 1-D arrays, 4-D arrays); Fill exercises the pushed-through fill value."""
+    rng = np.random.default_rng(hash(border) % 2**32)
+    b = ifb.Fill(0.7) if border == "fill" else border
+    cases = [
+        (np.asfortranarray(rng.random((70, 50, 40), dtype=np.float32)), ifb.KernelFactors.gaussian((4, 4, 4))),
+        (np.asfortranarray(rng.random((33, 41, 29))), ifb.KernelFactors.gaussian((1, 2, 3))),
+        (np.asfortranarray(rng.random((20, 19, 18))), tuple(reversed(ifb.KernelFactors.gaussian((1, 1, 2))))),   # z, y, x order
+        (rng.random(500), (ifb.centered(rng.random(7)),)),
+        (np.asfortranarray(rng.random((64, 37))), (ifb.OffsetArray.with_first(rng.random((1, 5)), (0, -3)),)),    # axis 1 only
+        (np.asfortranarray(rng.random((64, 37))), (ifb.OffsetArray.with_first(rng.random((4, 1)), (-1, 0)),)),    # axis 0 only
+        (np.asfortranarray(rng.random((12, 11, 10, 9))), ifb.KernelFactors.gaussian((1, 1, 1, 1))),
+        (np.asfortranarray(rng.integers(0, 256, size=(40, 30, 20), dtype=np.uint8)), ifb.KernelFactors.sobel((True, True, True), 3)),
+    ]
+    for img, kern in cases:
+        if border == "fill" and img.dtype == np.uint8:
+            b = ifb.Fill(3)
+        pa, pb = _both(ifb, oracle, np.float64, img, kern, b)
+        assert device.last_path() == "sepnd", (device.last_path(), img.shape)
+        assert np.array_equal(pa, pb), (img.shape, border)
+        pa, pb = _both(ifb, oracle, np.float32, img, kern, b)
+        taps = [k.data.parent if isinstance(k, ifb.ReshapedOneD) else k.parent for k in kern]
+        assert np.max(np.abs(pa.astype(np.float64) - pb.astype(np.float64))) <= _tol(taps, np.asarray(img)), (img.shape, border)
+    g = ifb.imgradients(cases[0][0], ifb.KernelFactors.sobel, b)      # 3-D gradients: three 3-stage cascades
+    go = ifb.imgradients(cases[0][0], ifb.KernelFactors.sobel, b, _library=oracle)
+    for a, o in zip(g, go):
+        assert np.max(np.abs(a.astype(np.float64) - o.astype(np.float64))) <= 1e-5
+
+
+@pytest.mark.parametrize("border", ["symmetric", "replicate", "reflect", "circular", "fill"])
+@pytest.mark.parametrize("T", [np.float32, np.float64])
+def test_slab_form_matches_whole_volume(ifb, oracle, device, border, T):
+    """b2f_imfilter_slab on ONE device: cut a volume into 3 slabs, hand every slab its neighbours' xy-filtered planes
+    as halos (what the NCCL exchange delivers), and compare with the oracle on the whole volume."""
+    import torch
+    from importlib import import_module
+    imf = import_module("imagefiltering_jl_b200.imfilter")
+    rng = np.random.default_rng(53)
+    X, Y, Z, h = 48, 40, 60, 8
+    vol = np.asfortranarray(rng.random((X, Y, Z)).astype(T))
+    kf = ifb.KernelFactors.gaussian((4, 4, 4)) if T == np.float32 else ifb.KernelFactors.gaussian((4.0, 4.0, 4.0))
+    b = ifb.Fill(0.3) if border == "fill" else ifb.Pad(border)
+    ref = ifb.imfilter(T, vol, kf, b, _library=oracle)
+    # xy stages on the whole volume (planes are independent), then the z stage slab by slab
+    xy = (kf[0], kf[1], ifb.ReshapedOneD(3, 2, ifb.centered(np.ones(1))))
+    t_vol = torch.from_numpy(np.ascontiguousarray(vol.transpose(2, 1, 0))).cuda()
+    t_mid = torch.empty_like(t_vol)
+    st_xy = ifb._abi.StageList(imf.build_stages(xy, 3))
+    device.imfilter(ifb.DeviceArray.from_torch(t_vol).desc(), ifb.DeviceArray.from_torch(t_mid).desc(), st_xy, b.to_abi(3))
+    st_z = ifb._abi.StageList(imf.build_stages((kf[2],), 3))
+    zb = b
+    if border == "fill":   # the z stage must see the fill value pushed through the x and y stages
+        v = T(0.3)
+        for k in (kf[0], kf[1]):
+            acc = T(0)
+            for t in k.data.parent:
+                acc = T(acc + T(v * T(t))) if T == np.float64 else np.float32(np.float64(v) * np.float64(np.float32(t)) + np.float64(acc))
+            v = acc
+        zb = ifb.Fill(float(v))
+    out = torch.empty_like(t_vol)
+    bounds = [0, 17, 41, Z]
+    for i in range(3):
+        z0, z1 = bounds[i], bounds[i + 1]
+        circ = border == "circular"
+        lo = h if (i > 0 or circ) else 0
+        hi = h if (i < 2 or circ) else 0
+        planes = [(z % Z) for z in range(z0 - lo, z1 + hi)]
+        buf = t_mid[planes].contiguous()
+        o = torch.empty((z1 - z0, Y, X), dtype=t_vol.dtype, device="cuda")
+        device.imfilter_slab(ifb.DeviceArray.from_torch(buf).desc(), ifb.DeviceArray.from_torch(o).desc(), st_z,
+                             zb.to_abi(3), Z, z0, lo, hi)
+        assert device.last_path() == "slab"
+        out[z0:z1] = o
+    got = out.cpu().numpy().transpose(2, 1, 0)
+    if T == np.float64:
+        assert np.array_equal(got, ref)
+    else:
+        assert np.max(np.abs(got.astype(np.float64) - ref.astype(np.float64))) <= 1e-5
+    with pytest.raises(ifb.DimensionMismatch):     # halo smaller than the kernel needs
+        buf = t_mid[17 - 2:41 + 2].contiguous()
+        o = torch.empty((24, Y, X), dtype=t_vol.dtype, device="cuda")
+        device.imfilter_slab(ifb.DeviceArray.from_torch(buf).desc(), ifb.DeviceArray.from_torch(o).desc(), st_z,
+                             zb.to_abi(3), Z, 17, 2, 2)
