@@ -35,7 +35,7 @@ DTYPE_TO_NP[N0F8] = np.dtype(np.uint8)
 SYMBOLS = [
     "b2f_version", "b2f_last_error", "b2f_is_device_library", "b2f_set_device", "b2f_device_count",
     "b2f_malloc", "b2f_free", "b2f_host_alloc", "b2f_host_free", "b2f_memcpy_h2d", "b2f_memcpy_d2h",
-    "b2f_sync", "b2f_imfilter", "b2f_imgradients", "b2f_mapwindow_extrema", "b2f_imfilter_slab",
+    "b2f_sync", "b2f_ipc_export", "b2f_ipc_open", "b2f_ipc_close", "b2f_imfilter", "b2f_imgradients", "b2f_mapwindow_extrema", "b2f_imfilter_slab",
     "b2f_launch_count", "b2f_reset_launch_count", "b2f_last_path",
 ]
 
@@ -167,6 +167,9 @@ class Library:
         d.b2f_memcpy_d2h.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
         d.b2f_set_device.argtypes = [C.c_int]
         d.b2f_device_count.argtypes = [C.POINTER(C.c_int)]
+        d.b2f_ipc_export.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
+        d.b2f_ipc_open.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]
+        d.b2f_ipc_close.argtypes = [C.c_void_p, C.c_uint64]
         d.b2f_imfilter.argtypes = [
             C.POINTER(b2f_array), C.POINTER(b2f_array), C.POINTER(b2f_stage), C.c_int32,
             C.POINTER(b2f_border), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_void_p]
@@ -178,7 +181,7 @@ class Library:
             C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(b2f_border), C.c_void_p]
         d.b2f_imfilter_slab.argtypes = [
             C.POINTER(b2f_array), C.POINTER(b2f_array), C.POINTER(b2f_stage), C.c_int32,
-            C.POINTER(b2f_border), C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_void_p]
+            C.POINTER(b2f_border), C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]
 
     # -- helpers ---------------------------------------------------------------------------
     def check(self, rc: int):
@@ -201,6 +204,22 @@ class Library:
 
     def reset_launch_count(self):
         self.dll.b2f_reset_launch_count()
+
+    # -- peer mapping ------------------------------------------------------------------------
+    def ipc_export(self, dptr: int):
+        """-> (64-byte handle, offset) naming device memory of this process for b2f_ipc_open elsewhere."""
+        h = C.create_string_buffer(64)
+        off = C.c_uint64()
+        self.check(self.dll.b2f_ipc_export(C.c_void_p(dptr), h, C.byref(off)))
+        return h.raw, int(off.value)
+
+    def ipc_open(self, handle: bytes, offset: int) -> int:
+        p = C.c_void_p()
+        self.check(self.dll.b2f_ipc_open(C.create_string_buffer(handle, 64), offset, C.byref(p)))
+        return int(p.value)
+
+    def ipc_close(self, dptr: int, offset: int):
+        self.check(self.dll.b2f_ipc_close(C.c_void_p(dptr), offset))
 
     # -- raw calls on descriptors -------------------------------------------------------------
     def imfilter(self, img: b2f_array, out: b2f_array, stages: StageList, border: b2f_border,
@@ -229,8 +248,10 @@ class Library:
             C.byref(border), C.c_void_p(stream)))
 
     def imfilter_slab(self, img: b2f_array, out: b2f_array, stages: StageList, border: b2f_border,
-                      global_last_dim: int, slab_first: int, halo_lo: int, halo_hi: int,
-                      stream: int = 0):
+                      global_last_dim: int, slab_first: int, halo_lo: int, n_halo_lo: int,
+                      halo_hi: int, n_halo_hi: int, stream: int = 0):
+        """halo_lo / halo_hi are raw pointers (ints; 0 = none) to n_halo_* input planes below / above the slab."""
         self.check(self.dll.b2f_imfilter_slab(C.byref(img), C.byref(out), stages.arr, stages.n,
-                                              C.byref(border), global_last_dim, slab_first, halo_lo,
-                                              halo_hi, C.c_void_p(stream)))
+                                              C.byref(border), global_last_dim, slab_first,
+                                              C.c_void_p(halo_lo or None), n_halo_lo,
+                                              C.c_void_p(halo_hi or None), n_halo_hi, C.c_void_p(stream)))

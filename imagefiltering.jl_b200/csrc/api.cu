@@ -252,6 +252,42 @@ int b2f_memcpy_d2h(void *hptr, const void *dptr, uint64_t bytes) {
 }
 int b2f_sync(void) { B2F_CUDA(cudaDeviceSynchronize()); return 0; }
 
+// ---- peer mapping of device memory across processes (one process per GPU; the NVLink halo path) ------------------
+// cudaIpcGetMemHandle names the whole ALLOCATION that contains dptr, so the offset of dptr inside it travels along
+// (cuMemGetAddressRange, reached through the runtime so the library has no link-time dependency on libcuda).
+int b2f_ipc_export(const void *dptr, void *handle64, uint64_t *offset) {
+    if (!dptr || !handle64 || !offset) return fail(B2F_EARG, "NULL argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    typedef int (*range_fn)(unsigned long long *, size_t *, unsigned long long);
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    B2F_CUDA(cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &qr));
+    if (!fn || qr != cudaDriverEntryPointSuccess) return fail(B2F_ECUDA, "cuMemGetAddressRange is unavailable");
+    unsigned long long base = 0;
+    size_t size = 0;
+    if (((range_fn)fn)(&base, &size, (unsigned long long)(uintptr_t)dptr) != 0)
+        return fail(B2F_ECUDA, "cuMemGetAddressRange failed (not a device allocation?)");
+    cudaIpcMemHandle_t h;
+    B2F_CUDA(cudaIpcGetMemHandle(&h, (void *)(uintptr_t)base));
+    memcpy(handle64, &h, 64);
+    *offset = (uint64_t)((uintptr_t)dptr - (uintptr_t)base);
+    return 0;
+}
+int b2f_ipc_open(const void *handle64, uint64_t offset, void **dptr) {
+    if (!handle64 || !dptr) return fail(B2F_EARG, "NULL argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    void *base = nullptr;
+    B2F_CUDA(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+    *dptr = (char *)base + offset;
+    return 0;
+}
+int b2f_ipc_close(void *dptr, uint64_t offset) {
+    if (!dptr) return 0;
+    B2F_CUDA(cudaIpcCloseMemHandle((char *)dptr - offset));
+    return 0;
+}
+
 static int check_types(const b2f_array *img, const b2f_array *out, const Plan &P) {
     if (img->dtype < B2F_U8 || img->dtype > B2F_U32) return fail(B2F_EARG, "unsupported image dtype %d", img->dtype);
     if (out->dtype < B2F_U8 || out->dtype > B2F_U32 || out->dtype == B2F_N0F8)
@@ -296,7 +332,7 @@ static int imfilter_planes(const b2f_array *img, const b2f_array *outs, int npla
         std::vector<void *> dout(nplanes);
         std::vector<int> odt(nplanes);
         for (int p = 0; p < nplanes; ++p) { dout[p] = souts[p].dptr; odt[p] = outs[p].dtype; }
-        const char *force = getenv("B2F_FORCE_PATH");   // debugging knob: "fused2d" | "generic"
+        const char *force = getenv("B2F_FORCE_PATH");   // debugging knob: "fused2d" | "sepnd" | "generic"
         const bool allow_stream = !force, allow_fused = !force || !strcmp(force, "fused2d");
         if (allow_stream && stream2d_applicable(plans.data(), nplanes, img->dtype, odt.data())) {
             rc = run_stream2d(plans.data(), nplanes, sin.dptr, img->dtype, dout.data(), odt.data(), st);
@@ -304,7 +340,9 @@ static int imfilter_planes(const b2f_array *img, const b2f_array *outs, int npla
             rc = run_fused2d(plans.data(), nplanes, sin.dptr, img->dtype, dout.data(), odt.data(), st);
         } else {
             for (int p = 0; p < nplanes && !rc; ++p) {
-                if (!force && sepnd_applicable(plans[p], img->dtype, odt[p]))
+                if (!force && stream3d_applicable(plans[p], img->dtype, odt[p]))
+                    rc = run_stream3d(plans[p], sin.dptr, dout[p], st);
+                else if ((!force || !strcmp(force, "sepnd")) && sepnd_applicable(plans[p], img->dtype, odt[p]))
                     rc = run_sepnd(plans[p], sin.dptr, img->dtype, dout[p], odt[p], st);
                 else if (!force && dense2d_applicable(plans[p], img->dtype, odt[p]))
                     rc = run_dense2d(plans[p], sin.dptr, img->dtype, dout[p], odt[p], st);

@@ -187,6 +187,64 @@ static int run_sepnd_typed(const Plan &P, const void *d_img, int img_dt, void *d
     return rc;
 }
 
+// the slab cascade on a gathered buffer of `nplanes` planes whose plane `lo_n` is global plane `slab_first`
+template <typename CT>
+static int run_slab_typed(const Plan &P, int last, const void *d_src, int img_dt, void *d_out, int64_t nplanes, int64_t lo_n,
+                          int64_t own_n, int64_t Zg, int64_t slab_first, cudaStream_t st) {
+    int64_t dims[B2F_MAXDIM];
+    for (int d = 0; d < B2F_MAXDIM; ++d) dims[d] = P.img_ax.len(d);
+    dims[last] = nplanes;
+    int64_t plane = 1;
+    for (int d = 0; d < last; ++d) plane *= dims[d];
+    const size_t bytes = (size_t)(plane * nplanes) * sizeof(CT);
+    void *tmp[2] = {nullptr, nullptr};
+    const void *src = d_src;
+    int src_dt = img_dt;
+    CT fill = (CT)P.fill;
+    int rc = 0;
+    bool sharded_done = false;
+    const int na = (int)P.active.size();
+    int pass = 0;
+    for (int a = 0; a < na && !rc; ++pass) {
+        const StageInfo &s1 = P.stages[P.active[a]];
+        const StageInfo *sx = nullptr, *sy = nullptr;
+        int yaxis = 0, used = 1;
+        if (s1.s->axis == 0 && a + 1 < na && P.stages[P.active[a + 1]].s->axis == 1 && last != 1 &&
+            taps_ok_pair(s1.s->len[0], P.stages[P.active[a + 1]].s->len[1])) {
+            sx = &s1; sy = &P.stages[P.active[a + 1]]; yaxis = 1; used = 2;
+        } else if (s1.s->axis == 0) {
+            sx = &s1;
+        } else {
+            sy = &s1; yaxis = s1.s->axis;
+        }
+        const bool lastpass = a + used == na;
+        void *dst = d_out;
+        if (!lastpass) {
+            void *&t = tmp[pass & 1];
+            if (!t) {
+                cudaError_t e = cudaMallocAsync(&t, bytes, st);
+                if (e != cudaSuccess) { rc = fail(B2F_ENOMEM, "temporary allocation failed: %s", cudaGetErrorString(e)); break; }
+            }
+            dst = t;
+        }
+        if (sy && yaxis == last && !sharded_done) {
+            rc = run_pass<CT>(dims, sx, sy, yaxis, src, src_dt, dst, P.style, fill, Zg, slab_first - lo_n, lo_n, own_n, st);
+            dims[last] = own_n;
+            sharded_done = true;
+        } else {
+            rc = run_pass<CT>(dims, sx, sy, yaxis, src, src_dt, dst, P.style, fill, 0, 0, 0, 0, st);
+        }
+        if (sx) fill = push_fill<CT>(fill, sx->s->taps, sx->s->len[0]);
+        if (sy) fill = push_fill<CT>(fill, sy->s->taps, sy->s->len[yaxis]);
+        src = dst;
+        src_dt = CtDt<CT>::v;
+        a += used;
+    }
+    for (void *t : tmp)
+        if (t) cudaFreeAsync(t, st);
+    return rc;
+}
+
 int run_sepnd(const Plan &P, const void *d_img, int img_dt, void *d_out, int out_dt, cudaStream_t st) {
     set_path("sepnd");
     return out_dt == B2F_F32 ? run_sepnd_typed<float>(P, d_img, img_dt, d_out, st)
@@ -197,56 +255,78 @@ int run_sepnd(const Plan &P, const void *d_img, int img_dt, void *d_out, int out
 
 using namespace b2f;
 
+// Slab form of a separable cascade: the array's LAST axis is sharded.  `img`/`out` hold this rank's owned
+// planes [slab_first, slab_first + own_n); halo_lo / halo_hi hold n_halo_lo / n_halo_hi RAW input planes logically
+// below / above them (receive buffers, or the neighbour's memory mapped over NVLink).  Semantics = the owned planes of
+// b2f_imfilter on the whole array.
 extern "C" int b2f_imfilter_slab(const b2f_array *img, const b2f_array *out, const b2f_stage *stages, int32_t nstages,
                                  const b2f_border *border, int64_t global_last_dim, int64_t slab_first,
-                                 int64_t halo_lo, int64_t halo_hi, void *stream) {
+                                 const void *halo_lo, int64_t n_halo_lo, const void *halo_hi, int64_t n_halo_hi,
+                                 void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (!img || !out || !border || !stages) return fail(B2F_EARG, "NULL argument");
     if (img->mem != B2F_DEVICE || out->mem != B2F_DEVICE) return fail(B2F_EARG, "b2f_imfilter_slab works on device arrays");
     const int N = img->ndim;
     if (N < 2 || N > B2F_MAXDIM || out->ndim != N) return fail(B2F_EDIM, "slab arrays need 2..4 dims and equal rank");
-    if (halo_lo < 0 || halo_hi < 0) return fail(B2F_EARG, "negative halo");
+    if (n_halo_lo < 0 || n_halo_hi < 0) return fail(B2F_EARG, "negative halo");
+    if ((n_halo_lo > 0 && !halo_lo) || (n_halo_hi > 0 && !halo_hi)) return fail(B2F_EARG, "NULL halo pointer");
     const int last = N - 1;
-    const int64_t owned = img->dims[last] - halo_lo - halo_hi;
-    if (owned < 1 || out->dims[last] != owned) return fail(B2F_EDIM, "out must hold exactly the owned planes");
-    for (int d = 0; d < last; ++d)
+    const int64_t own_n = img->dims[last];
+    for (int d = 0; d < N; ++d)
         if (img->dims[d] != out->dims[d]) return fail(B2F_EDIM, "slab and out extents differ along axis %d", d);
-    if (slab_first < 0 || slab_first + owned > global_last_dim) return fail(B2F_EDIM, "slab lies outside the global axis");
+    if (own_n < 1) { set_path("empty"); return 0; }
+    if (slab_first < 0 || slab_first + own_n > global_last_dim) return fail(B2F_EDIM, "slab lies outside the global axis");
     if (out->dtype != B2F_F32 && out->dtype != B2F_F64) return fail(B2F_ENOTSUP, "slab form supports Float32/Float64 outputs");
-    if (img->dtype != out->dtype) return fail(B2F_ENOTSUP, "slab form expects the intermediate in eltype(out)");
     if (border->style > B2F_FILL) return fail(B2F_ENOTSUP, "slab form supports Pad and Fill borders");
-    // exactly one non-copy stage, 1-D along the sharded (last) axis
-    const b2f_stage *zs = nullptr;
-    for (int s = 0; s < nstages; ++s) {
-        const b2f_stage &t = stages[s];
-        if (t.kind != B2F_STAGE_1D) return fail(B2F_ENOTSUP, "slab form takes 1-D stages");
-        if (t.axis < 0 || t.axis >= N) return fail(B2F_EDIM, "stage axis out of range");
-        const bool copy = t.len[t.axis] == 1 && t.lo[t.axis] == 0 && t.taps && t.taps[0] == 1.0;
-        if (copy) continue;
-        if (t.axis != last || zs) return fail(B2F_ENOTSUP, "slab form runs the single stage along the sharded axis; run the other stages with b2f_imfilter first");
-        zs = &t;
-    }
-    if (!zs) return fail(B2F_EARG, "no stage along the sharded axis");
-    const int64_t L = zs->len[last], klo = zs->lo[last];
-    if (!(L <= 16 || L == 17)) return fail(B2F_ENOTSUP, "slab form supports up to 16 (or 17) taps");
-    const int64_t H = img->dims[last], y_first = slab_first - halo_lo;
-    // every plane the owned outputs read must be in the buffer, directly or through the global border
-    for (int64_t i = halo_lo + klo; i <= halo_lo + owned - 1 + klo + L - 1; ++i) {
-        if (i >= 0 && i < H) continue;
-        const int64_t g = remap_index(border->style, i + y_first, global_last_dim);
+    // plan on the GLOBAL array: same validation and border resolution as b2f_imfilter
+    b2f_array gi = *img, go = *out;
+    gi.dims[last] = go.dims[last] = global_last_dim;
+    gi.ptr = go.ptr = nullptr;
+    Plan P;
+    int rc = make_plan(&gi, &go, stages, nstages, border, nullptr, nullptr, P);
+    if (rc) return rc;
+    if (P.img_ax.empty()) { set_path("empty"); return 0; }
+    if (!sepnd_applicable(P, img->dtype, out->dtype))
+        return fail(B2F_ENOTSUP, "slab form takes separable cascades (1-D stages on distinct axes, <= 17 taps)");
+    // the planes the owned outputs read along the sharded axis must be present (own or halo), directly or through
+    // the global border
+    int64_t zlo = 0, zhi = 0;
+    for (int a : P.active) { zlo += P.stages[a].lo[last]; zhi += P.stages[a].hi[last]; }
+    const int64_t have_lo = slab_first - n_halo_lo, have_hi = slab_first + own_n + n_halo_hi;   // logical [lo, hi)
+    for (int64_t z = slab_first + zlo; z < slab_first + own_n + zhi; ++z) {
+        if (z >= have_lo && z < have_hi) continue;
+        const int64_t g = remap_index(border->style, z, global_last_dim);
         if (g < 0) continue;  // Fill
-        if (g - y_first < 0 || g - y_first >= H) return fail(B2F_EDIM, "halo too small: plane %lld is needed but not present", (long long)g);
+        if (g < have_lo || g >= have_hi)
+            return fail(B2F_EDIM, "halo too small: plane %lld is needed but not present", (long long)g);
     }
-    StageInfo si;
-    si.s = zs;
-    for (int d = 0; d < B2F_MAXDIM; ++d) si.lo[d] = si.hi[d] = 0;
-    si.lo[last] = klo; si.hi[last] = klo + L - 1; si.copy = false;
-    int64_t dims[B2F_MAXDIM];
-    for (int d = 0; d < B2F_MAXDIM; ++d) dims[d] = d < N ? img->dims[d] : 1;
+    rc = 0;
+    if (stream3d_applicable(P, img->dtype, out->dtype)) {
+        set_path("stream3d_slab");
+        return run_stream3d_slab(P, img->ptr, halo_lo, n_halo_lo, halo_hi, n_halo_hi, slab_first, own_n, out->ptr, st);
+    }
+    // general separable cascade: gather [halo_lo; own; halo_hi] once, then one streamed pass per stage; the pass along
+    // the sharded axis evaluates the border in GLOBAL plane coordinates and keeps only the owned planes
     set_path("slab");
-    if (out->dtype == B2F_F32)
-        return run_pass<float>(dims, nullptr, &si, last, img->ptr, B2F_F32, out->ptr, border->style, (float)border->fill,
-                               global_last_dim, y_first, halo_lo, owned, st);
-    return run_pass<double>(dims, nullptr, &si, last, img->ptr, B2F_F64, out->ptr, border->style, border->fill,
-                            global_last_dim, y_first, halo_lo, owned, st);
+    const size_t esz = dtype_size(img->dtype);
+    int64_t plane = 1;
+    for (int d = 0; d < last; ++d) plane *= img->dims[d];
+    if (zlo == 0 && zhi == 0) n_halo_lo = n_halo_hi = 0;   // nothing acts along the sharded axis: halos are not read
+    int64_t nplanes = n_halo_lo + own_n + n_halo_hi;
+    void *ext = nullptr;
+    const void *src = img->ptr;
+    if (n_halo_lo + n_halo_hi > 0) {
+        B2F_CUDA(cudaMallocAsync(&ext, (size_t)(plane * nplanes) * esz, st));
+        char *e = (char *)ext;
+        if (n_halo_lo) B2F_CUDA(cudaMemcpyAsync(e, halo_lo, (size_t)(plane * n_halo_lo) * esz, cudaMemcpyDefault, st));
+        B2F_CUDA(cudaMemcpyAsync(e + (size_t)(plane * n_halo_lo) * esz, img->ptr, (size_t)(plane * own_n) * esz, cudaMemcpyDefault, st));
+        if (n_halo_hi)
+            B2F_CUDA(cudaMemcpyAsync(e + (size_t)(plane * (n_halo_lo + own_n)) * esz, halo_hi, (size_t)(plane * n_halo_hi) * esz, cudaMemcpyDefault, st));
+        src = ext;
+    }
+    rc = out->dtype == B2F_F32
+             ? run_slab_typed<float>(P, last, src, img->dtype, out->ptr, nplanes, n_halo_lo, own_n, global_last_dim, slab_first, st)
+             : run_slab_typed<double>(P, last, src, img->dtype, out->ptr, nplanes, n_halo_lo, own_n, global_last_dim, slab_first, st);
+    if (ext) cudaFreeAsync(ext, st);
+    return rc;
 }

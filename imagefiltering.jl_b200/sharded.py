@@ -1,0 +1,263 @@
+"""Slab-sharded N-d separable `imfilter` across GPUs (BASELINE config 5).
+
+The array's LAST Julia axis (the slowest one: whole planes are contiguous) is partitioned over the
+ranks of a `torch.distributed` group, one process per GPU.  Rank p owns planes
+[first_p, first_p + n_p).  A cascade whose stages reach `lo` planes below and `hi` planes above
+(`accumulate_padding`, reference src/border.jl:614-642) needs that many RAW input planes of each
+neighbour; everything else — the other axes' borders, the outer faces of the volume — is local.
+The result equals the owned planes of `imfilter(CPU1(Algorithm.FIR()), whole_array, kernel, border)`.
+
+Two halo transports, same kernel entry (`b2f_imfilter_slab`, include/b2f.h):
+
+  "p2p"       the neighbours' slabs are mapped into this process once (CUDA IPC over NVLink/NVSwitch,
+              `b2f_ipc_export/open`); the filter kernel reads the boundary planes of its neighbours
+              directly with peer loads while it streams its own planes — the exchange is fused into
+              the compute kernel, no halo buffers, no copy kernels.  Per call only a stream-ordered
+              barrier is needed (the neighbours' inputs must be complete before they are read).
+  "sendrecv"  `dist.batch_isend_irecv` of the boundary planes into receive buffers (NCCL over NVLink;
+              gloo on CPU tensors in the tests), then the same kernel with the buffers as halos.
+
+The data path has no other collective.  Tensors are C-contiguous torch tensors whose reversed
+shape is the Julia shape: (Zloc, Y, X) holds the Julia array (X, Y, Zloc).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _abi
+from ._abi import ArgumentError, DimensionMismatch, NotSupportedError
+from .border import Fill, Pad, borderinstance
+from .imfilter import build_stages, factorkernel, kernel_extent
+
+_TORCH_TO_DT = None
+
+
+def _dt_of(t):
+    global _TORCH_TO_DT
+    import torch
+    if _TORCH_TO_DT is None:
+        _TORCH_TO_DT = {torch.uint8: _abi.U8, torch.float32: _abi.F32, torch.float64: _abi.F64}
+    if t.dtype not in _TORCH_TO_DT:
+        raise NotSupportedError(f"slab eltype {t.dtype} is not supported")
+    return _TORCH_TO_DT[t.dtype]
+
+
+def slab_bounds(n_planes: int, world: int, rank: int):
+    """Balanced contiguous partition of `n_planes` planes: -> (first, count) of `rank`."""
+    base, extra = divmod(n_planes, world)
+    first = rank * base + min(rank, extra)
+    return first, base + (1 if rank < extra else 0)
+
+
+def halo_extent(stages, ndim: int):
+    """Planes needed below / above along the last axis (Pad{0}(kernel): src/border.jl:602-606)."""
+    first, last = kernel_extent(stages, ndim)
+    return max(0, -first[ndim - 1]), max(0, last[ndim - 1])
+
+
+def _desc(t, n0f8=False):
+    dt = _abi.N0F8 if n0f8 else _dt_of(t)
+    dims = tuple(reversed(t.shape))
+    return _abi.make_array(t.data_ptr(), dt, dims, (1,) * len(dims), _abi.DEVICE if t.is_cuda else _abi.HOST)
+
+
+class ShardedImfilter:
+    """Plan of one slab-sharded `imfilter` over fixed input/output slabs; `run()` executes it.
+
+        f = ShardedImfilter(slab, KernelFactors.gaussian((4, 4, 4)), Pad("symmetric"), group=g)
+        out = f.run()          # any number of times (the input slab may be refilled in between)
+        f.close()
+    """
+
+    def __init__(self, slab, kernel, border="replicate", *, out=None, group=None, mode="auto",
+                 out_dtype=None, n0f8=False, _library=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        if _library is not None:
+            self.lib = _library
+        else:
+            from ._lib import lib
+            self.lib = lib()                      # raises when the CUDA extension is missing: no CPU path
+        if not slab.is_contiguous():
+            raise ValueError("slab must be contiguous")
+        if slab.dim() < 2 or slab.dim() > _abi.MAXDIM:
+            raise NotSupportedError("slab-sharded arrays need 2..4 dimensions")
+        self.slab, self.n0f8 = slab, n0f8
+        self.ndim = slab.dim()
+        border = borderinstance(border)
+        if not isinstance(border, (Pad, Fill)) or border.lo:
+            raise NotSupportedError("the sharded path takes Pad(style) / Fill(value) borders derived from the kernel")
+        self.border = border
+        if not isinstance(kernel, tuple):
+            kernel = factorkernel(kernel)
+        self.stages_list = build_stages(kernel, self.ndim)
+        self.stages = _abi.StageList(self.stages_list)
+        self.h_lo, self.h_hi = halo_extent(self.stages_list, self.ndim)
+        # who owns what: every rank's plane count
+        n_mine = int(slab.shape[0])
+        counts = [n_mine]
+        if self.world > 1:
+            counts = [None] * self.world
+            dist.all_gather_object(counts, n_mine, group=group)
+        self.counts = counts
+        self.first = int(sum(counts[:self.rank]))
+        self.global_planes = int(sum(counts))
+        circ = isinstance(border, Pad) and border.style == "circular"
+        self.lower = self.rank - 1 if self.rank > 0 else (self.world - 1 if circ and self.world > 1 else None)
+        self.upper = self.rank + 1 if self.rank + 1 < self.world else (0 if circ and self.world > 1 else None)
+        if self.h_lo == 0:
+            self.lower = None
+        if self.h_hi == 0:
+            self.upper = None
+        for nb, need in ((self.lower, self.h_lo), (self.upper, self.h_hi)):
+            if nb is not None and counts[nb] < need:
+                raise DimensionMismatch(f"rank {nb} owns {counts[nb]} planes but its neighbour needs a halo of {need}")
+        if out is None:
+            odt = out_dtype or (slab.dtype if slab.dtype != torch.uint8 else torch.float32)
+            out = torch.empty(slab.shape, dtype=odt, device=slab.device)
+        if tuple(out.shape) != tuple(slab.shape) or not out.is_contiguous():
+            raise DimensionMismatch("out must be a contiguous tensor with the slab's shape")
+        self.out = out
+        self.plane_elems = int(np.prod(slab.shape[1:]))
+        if mode == "auto":
+            mode = "p2p" if (slab.is_cuda and self.world > 1) else "sendrecv"
+        if mode not in ("p2p", "sendrecv"):
+            raise ArgumentError(f"unknown halo transport {mode!r}")
+        self.mode = mode
+        self._opened = []
+        self.halo_lo_ptr = self.halo_hi_ptr = 0
+        self.recv_lo = self.recv_hi = None
+        self._nccl = self.world > 1 and dist.get_backend(group) == "nccl"
+        self._flag = torch.zeros(1, dtype=torch.int32, device=slab.device) if self._nccl else None
+        if self.world > 1 and (self.lower is not None or self.upper is not None or mode == "p2p"):
+            if mode == "p2p":
+                self._setup_p2p()
+            else:
+                self._setup_sendrecv()
+
+    # -- transports -------------------------------------------------------------------------------------
+    def _setup_p2p(self):
+        if not self.slab.is_cuda:
+            raise ArgumentError('halo transport "p2p" needs CUDA tensors')
+        handle, offset = self.lib.ipc_export(self.slab.data_ptr())
+        infos = [None] * self.world
+        self.dist.all_gather_object(infos, (handle, offset), group=self.group)
+        esz = self.slab.element_size()
+        if self.lower is not None:      # the last h_lo planes of the lower neighbour lie just below mine
+            h, off = infos[self.lower]
+            base = self.lib.ipc_open(h, off)
+            self._opened.append((base, off))
+            self.halo_lo_ptr = base + (self.counts[self.lower] - self.h_lo) * self.plane_elems * esz
+        if self.upper is not None:      # the first h_hi planes of the upper neighbour lie just above mine
+            h, off = infos[self.upper]
+            if self.upper == self.lower and self._opened:
+                base = self._opened[0][0]
+            else:
+                base = self.lib.ipc_open(h, off)
+                self._opened.append((base, off))
+            self.halo_hi_ptr = base
+
+    def _setup_sendrecv(self):
+        t = self.torch
+        shp = tuple(self.slab.shape[1:])
+        if self.lower is not None:
+            self.recv_lo = t.empty((self.h_lo,) + shp, dtype=self.slab.dtype, device=self.slab.device)
+            self.halo_lo_ptr = self.recv_lo.data_ptr()
+        if self.upper is not None:
+            self.recv_hi = t.empty((self.h_hi,) + shp, dtype=self.slab.dtype, device=self.slab.device)
+            self.halo_hi_ptr = self.recv_hi.data_ptr()
+
+    def _exchange(self):
+        """Boundary planes -> neighbours' receive buffers.  Message order between a pair of ranks: the
+        sender posts [to lower, to upper], the receiver [from upper, from lower] (a circular wrap with two
+        ranks exchanges two messages between the same pair)."""
+        d = self.dist
+        ops = []
+        n = self.slab.shape[0]
+        # gloo moves host memory only: CUDA slabs are staged through host copies there (tests; NCCL sends in place)
+        stage = self.slab.is_cuda and not self._nccl
+        send_lo = self.slab[:self.h_hi] if self.lower is not None else None           # -> lower neighbour's hi halo
+        send_hi = self.slab[n - self.h_lo:] if self.upper is not None else None       # -> upper neighbour's lo halo
+        recv_hi, recv_lo = self.recv_hi, self.recv_lo
+        if stage:
+            send_lo = send_lo.cpu() if send_lo is not None else None
+            send_hi = send_hi.cpu() if send_hi is not None else None
+            recv_hi = self.torch.empty(recv_hi.shape, dtype=recv_hi.dtype) if recv_hi is not None else None
+            recv_lo = self.torch.empty(recv_lo.shape, dtype=recv_lo.dtype) if recv_lo is not None else None
+        if send_lo is not None:
+            ops.append(d.P2POp(d.isend, send_lo, self._grank(self.lower), group=self.group))
+        if send_hi is not None:
+            ops.append(d.P2POp(d.isend, send_hi, self._grank(self.upper), group=self.group))
+        if recv_hi is not None:
+            ops.append(d.P2POp(d.irecv, recv_hi, self._grank(self.upper), group=self.group))
+        if recv_lo is not None:
+            ops.append(d.P2POp(d.irecv, recv_lo, self._grank(self.lower), group=self.group))
+        if ops:
+            for w in d.batch_isend_irecv(ops):
+                w.wait()
+        if stage:
+            if recv_hi is not None:
+                self.recv_hi.copy_(recv_hi)
+            if recv_lo is not None:
+                self.recv_lo.copy_(recv_lo)
+
+    def _grank(self, r):
+        return self.dist.get_global_rank(self.group, r) if self.group is not None else r
+
+    def barrier(self):
+        """All ranks' inputs are complete / all ranks have finished reading: stream-ordered on NCCL (a
+        4-byte all-reduce on the current stream), host-side otherwise."""
+        if self.world == 1:
+            return
+        if self._nccl:
+            self.dist.all_reduce(self._flag, group=self.group)
+        else:
+            if self.slab.is_cuda:
+                self.torch.cuda.synchronize()
+            self.dist.barrier(group=self.group)
+
+    # -- execution --------------------------------------------------------------------------------------
+    def run(self, sync=True):
+        """One sharded filter pass -> `self.out`.  `sync=False` skips the entry barrier of the p2p transport
+        (only valid when the neighbours' inputs are known to be complete and unchanged)."""
+        t = self.torch
+        stream = t.cuda.current_stream().cuda_stream if self.slab.is_cuda else 0
+        if self.world > 1:
+            if self.mode == "p2p":
+                if sync:
+                    self.barrier()
+            else:
+                self._exchange()
+        self.lib.imfilter_slab(
+            _desc(self.slab, self.n0f8), _desc(self.out), self.stages, self.border.to_abi(self.ndim),
+            self.global_planes, self.first,
+            self.halo_lo_ptr, self.h_lo if self.lower is not None else 0,
+            self.halo_hi_ptr, self.h_hi if self.upper is not None else 0, stream)
+        return self.out
+
+    def close(self):
+        if self.world > 1 and self.mode == "p2p":
+            self.barrier()                      # nobody may still be reading my planes
+            if self.slab.is_cuda:
+                self.torch.cuda.synchronize()
+        for base, off in self._opened:
+            self.lib.ipc_close(base, off)
+        self._opened = []
+
+
+def imfilter_sharded(slab, kernel, border="replicate", *, out=None, group=None, mode="auto", out_dtype=None,
+                     n0f8=False, _library=None):
+    """One-shot form: plan, run once, release.  Returns this rank's planes of the filtered array."""
+    f = ShardedImfilter(slab, kernel, border, out=out, group=group, mode=mode, out_dtype=out_dtype, n0f8=n0f8,
+                        _library=_library)
+    try:
+        res = f.run()
+        if slab.is_cuda:
+            f.torch.cuda.synchronize()
+        return res
+    finally:
+        f.close()

@@ -133,6 +133,14 @@ int b2f_memcpy_h2d(void *dptr, const void *hptr, uint64_t bytes);
 int b2f_memcpy_d2h(void *hptr, const void *dptr, uint64_t bytes);
 int b2f_sync(void);
 
+/* Peer mapping across processes (one process per GPU): export a 64-byte handle + offset for device memory owned by
+ * this process (any pointer inside a cudaMalloc'ed allocation), open it in another process on the same node as a
+ * device pointer usable by kernels and copies (NVLink P2P loads), and close it again.  Used by the sharded path so
+ * that the filter kernel reads its neighbours' boundary planes directly (b2f_imfilter_slab's halo pointers). */
+int b2f_ipc_export(const void *dptr, void *handle64, uint64_t *offset);
+int b2f_ipc_open(const void *handle64, uint64_t offset, void **dptr);
+int b2f_ipc_close(void *dptr, uint64_t offset);
+
 /* ---- the hot path ------------------------------------------------------------------------ */
 
 /* imfilter!(r, out, img, kernel::ProcessedKernel, border)      replaces src/imfilter.jl:321-341 and
@@ -173,16 +181,21 @@ int b2f_mapwindow_extrema(const b2f_array *img, const b2f_array *out_min, const 
                           const int64_t *win_lo, const int64_t *win_hi,
                           const b2f_border *border, void *stream);
 
-/* Slab form used by the sharded 3-D path: `img` holds this rank's planes
- * [slab_first, slab_first + dims[ndim-1]) of a volume whose last axis has `global_last_dim` planes,
- * PLUS `halo_lo` planes below and `halo_hi` planes above that were received from the neighbouring
- * ranks (or are absent, = 0, at a global face, where the border style applies).  `out` holds only
- * the owned planes. */
+/* Slab form of a separable cascade, used by the sharded N-d path: the array's LAST axis is
+ * partitioned across GPUs.  `img` and `out` hold this rank's owned planes [slab_first, slab_first + dims[ndim-1])
+ * of an array whose last axis has `global_last_dim` planes.  `halo_lo` / `halo_hi` point to `n_halo_lo` /
+ * `n_halo_hi` RAW input planes (eltype(img), dense, same plane shape) lying logically just below / above the owned
+ * planes: receive buffers filled by an NCCL send/recv, or the neighbouring GPU's memory mapped into this process
+ * (cudaIpcOpenMemHandle) — in which case the kernel performs the halo exchange itself with P2P loads over NVLink.
+ * At a global face pass 0 planes: the border style is applied there in GLOBAL plane coordinates (a Pad(:circular)
+ * wrap is passed as an ordinary halo).  Result = the owned planes of b2f_imfilter on the whole array
+ * (reference semantics: src/imfilter.jl:321-341 pad once, :385-395 cascade).  Device arrays only; asynchronous. */
 int b2f_imfilter_slab(const b2f_array *img, const b2f_array *out,
                       const b2f_stage *stages, int32_t nstages,
                       const b2f_border *border,
                       int64_t global_last_dim, int64_t slab_first,
-                      int64_t halo_lo, int64_t halo_hi,
+                      const void *halo_lo, int64_t n_halo_lo,
+                      const void *halo_hi, int64_t n_halo_hi,
                       void *stream);
 
 /* number of CUDA kernels launched by this library on the calling thread since the last reset

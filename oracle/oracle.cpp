@@ -703,6 +703,9 @@ int b2f_host_free(void *) { return fail(B2F_ENOTSUP, "oracle library has no pinn
 int b2f_memcpy_h2d(void *, const void *, uint64_t) { return fail(B2F_ENOTSUP, "oracle library has no device memory"); }
 int b2f_memcpy_d2h(void *, const void *, uint64_t) { return fail(B2F_ENOTSUP, "oracle library has no device memory"); }
 int b2f_sync(void) { return 0; }
+int b2f_ipc_export(const void *, void *, uint64_t *) { return fail(B2F_ENOTSUP, "oracle library has no device memory"); }
+int b2f_ipc_open(const void *, uint64_t, void **) { return fail(B2F_ENOTSUP, "oracle library has no device memory"); }
+int b2f_ipc_close(void *, uint64_t) { return fail(B2F_ENOTSUP, "oracle library has no device memory"); }
 int64_t b2f_launch_count(void) { return 0; }
 void b2f_reset_launch_count(void) {}
 const char *b2f_last_path(void) { return "oracle"; }
@@ -751,9 +754,85 @@ int b2f_mapwindow_extrema(const b2f_array *img, const b2f_array *out_min, const 
     return fail(B2F_EARG, "unsupported dtype");
 }
 
-int b2f_imfilter_slab(const b2f_array *, const b2f_array *, const b2f_stage *, int32_t, const b2f_border *,
-                      int64_t, int64_t, int64_t, int64_t, void *) {
-    return fail(B2F_ENOTSUP, "the oracle filters whole volumes; slabs are a product-side decomposition");
+int b2f_oracle_padarray(const b2f_array *img, const b2f_array *out, const b2f_border *border);
+
+// Slab form (include/b2f.h): the owned planes of imfilter on the whole array.  Restated as: materialise exactly the
+// planes the owned outputs read along the sharded axis — each taken from the owned slab, from a halo buffer (matched
+// on its logical index), through the global border remap (padindex, src/border.jl:564-596), or the Fill value —
+// then run the ordinary cascade with `out` = the owned planes; along the sharded axis every read then stays inside
+// the materialised planes, so only the other axes see the border.
+int b2f_imfilter_slab(const b2f_array *img, const b2f_array *out, const b2f_stage *stages, int32_t nstages,
+                      const b2f_border *border, int64_t global_last_dim, int64_t slab_first,
+                      const void *halo_lo, int64_t n_halo_lo, const void *halo_hi, int64_t n_halo_hi, void *) {
+    if (!img || !out || !border || !stages) return fail(B2F_EARG, "NULL argument");
+    const int N = img->ndim, last = N - 1;
+    if (N < 2 || N > B2F_MAXDIM || out->ndim != N) return fail(B2F_EDIM, "slab arrays need 2..4 dims and equal rank");
+    if (border->style > B2F_FILL) return fail(B2F_ENOTSUP, "slab form supports Pad and Fill borders");
+    const int64_t own_n = img->dims[last];
+    if (own_n < 1) return 0;
+    if (slab_first < 0 || slab_first + own_n > global_last_dim) return fail(B2F_EDIM, "slab lies outside the global axis");
+    int64_t zlo = 0, zhi = 0;
+    for (int s = 0; s < nstages; ++s) {
+        if (stages[s].kind != B2F_STAGE_1D) return fail(B2F_ENOTSUP, "slab form takes 1-D stages");
+        if (stages[s].axis == last) { zlo += stages[s].lo[last]; zhi += stages[s].lo[last] + stages[s].len[last] - 1; }
+    }
+    if (zlo > 0) zlo = 0;
+    if (zhi < 0) zhi = 0;
+    int64_t plane = 1;
+    for (int d = 0; d < last; ++d) plane *= img->dims[d];
+    const size_t es = dtype_size(img->dtype), pbytes = (size_t)plane * es;
+    const int64_t nz = own_n - zlo + zhi;
+    std::vector<unsigned char> ext((size_t)nz * pbytes);
+    // Fill planes: the value converted through eltype(img), like padarray does (src/borderarray.jl:11-20)
+    std::vector<unsigned char> fillplane;
+    for (int64_t k = 0; k < nz; ++k) {
+        const int64_t z = slab_first + zlo + k;   // logical plane index
+        const unsigned char *src = nullptr;
+        auto locate = [&](int64_t g) -> const unsigned char * {
+            if (g >= slab_first && g < slab_first + own_n) return (const unsigned char *)img->ptr + (size_t)(g - slab_first) * pbytes;
+            if (g < slab_first && g >= slab_first - n_halo_lo) return (const unsigned char *)halo_lo + (size_t)(g - (slab_first - n_halo_lo)) * pbytes;
+            if (g >= slab_first + own_n && g < slab_first + own_n + n_halo_hi) return (const unsigned char *)halo_hi + (size_t)(g - slab_first - own_n) * pbytes;
+            return nullptr;
+        };
+        src = locate(z);
+        bool is_fill = false;
+        if (!src) {
+            if (z >= 0 && z < global_last_dim) return fail(B2F_EDIM, "halo too small: plane %lld is needed but not present", (long long)z);
+            if (border->style == B2F_FILL) {
+                is_fill = true;
+            } else {
+                int64_t g = 0;
+                if (!pad_source_index(border->style, z, global_last_dim, g)) return fail(B2F_EARG, "reflect padding of a length-1 axis");
+                src = locate(g);
+                if (!src) return fail(B2F_EDIM, "halo too small: plane %lld is needed but not present", (long long)g);
+            }
+        }
+        unsigned char *dst = ext.data() + (size_t)k * pbytes;
+        if (!is_fill) { memcpy(dst, src, pbytes); continue; }
+        if (fillplane.empty()) {   // one padded plane of a 1-plane dummy gives the converted fill value
+            fillplane.resize(pbytes);
+            b2f_array one = *img, pad1 = *img;
+            one.ptr = (void *)img->ptr; one.dims[last] = 1;
+            std::vector<unsigned char> two(2 * pbytes);
+            pad1.ptr = two.data(); pad1.dims[last] = 2;
+            b2f_border fb = *border;
+            fb.npad = N;
+            for (int d = 0; d < B2F_MAXDIM; ++d) fb.lo[d] = fb.hi[d] = 0;
+            fb.hi[last] = 1;
+            int rc = b2f_oracle_padarray(&one, &pad1, &fb);
+            if (rc) return rc;
+            memcpy(fillplane.data(), two.data() + pbytes, pbytes);
+        }
+        memcpy(dst, fillplane.data(), pbytes);
+    }
+    b2f_array e = *img, o = *out;
+    e.ptr = ext.data();
+    e.dims[last] = nz;
+    e.origin[last] = img->origin[last] + zlo;     // the slab's own first plane keeps index img->origin[last]
+    o.origin[last] = img->origin[last];
+    for (int d = 0; d < last; ++d) o.origin[d] = img->origin[d];
+    e.mem = o.mem = B2F_HOST;
+    return imfilter_entry(&e, &o, stages, nstages, border, nullptr, nullptr);
 }
 
 // ---- oracle-only entry points (not in b2f.h) ---------------------------------------------------

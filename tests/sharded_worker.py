@@ -1,0 +1,111 @@
+"""Worker of the slab-sharded tests (spawned once per rank; gloo control plane on 127.0.0.1).
+
+Every rank builds the same seeded whole array, keeps its slab, runs the sharded filter and compares its planes
+with the oracle's result on the WHOLE array (tests/ may use the oracle as the checker).  `use_device` selects the
+product library on cuda:0 (both ranks share the one GPU; CUDA IPC works between processes on one device) or, for
+the CPU suite, the oracle library standing in for the per-slab compute so that the partitioning, neighbour
+selection, message order and halo bookkeeping of sharded.py are what is under test."""
+import os
+import sys
+import traceback
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def cases(ifb):
+    g = ifb.KernelFactors.gaussian
+    rng = np.random.default_rng(11)
+    out = []
+    for border in ("replicate", "circular", "symmetric", "reflect", ifb.Fill(0.4)):
+        out.append(("f32-3d-%s" % (border,), np.float32, (40, 22, 37), g((2, 2, 2)), border, None))
+    out.append(("f64-3d-asym", np.float64, (24, 18, 21), (g((1, 1, 1))[0], g((1, 1, 1))[1],
+                ifb.ReshapedOneD(3, 2, ifb.OffsetArray.with_first(rng.random(4), (-1,)))), "symmetric", None))
+    out.append(("f32-3d-17taps", np.float32, (70, 45, 40), g((4, 4, 4)), "symmetric", None))
+    out.append(("f32-2d", np.float32, (33, 29), g((1, 2)), "reflect", None))
+    out.append(("f32-3d-uneven", np.float32, (20, 12, 31), g((1, 1, 2)), "circular", [20, 11]))
+    out.append(("f64-3d-xy-only", np.float64, (20, 12, 16), (g((1, 1, 0))[0], g((1, 1, 0))[1]), "replicate", None))
+    return out
+
+
+def run(rank, world, port, use_device, modes, errq):
+    try:
+        import torch
+        import torch.distributed as dist
+        import imagefiltering_jl_b200 as ifb
+        from importlib import import_module
+        sh = import_module("imagefiltering_jl_b200.sharded")
+        dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+        oracle = ifb._abi.Library(os.path.join(ROOT, "oracle", "libb2f_oracle.so"))
+        lib = None if use_device else oracle
+        if use_device:
+            torch.cuda.set_device(0)
+        failures = []
+        for name, T, shape, kern, border, counts in cases(ifb):
+            rng = np.random.default_rng(abs(hash(name)) % 2**31 if False else sum(map(ord, name)))
+            whole = np.asfortranarray(rng.random(shape).astype(T))          # Julia order (X, Y, Z)
+            ref = ifb.imfilter(T, whole, kern, border, _library=oracle)
+            nz = shape[-1]
+            if counts is not None and world == len(counts):
+                first, n = sum(counts[:rank]), counts[rank]
+            else:
+                first, n = sh.slab_bounds(nz, world, rank)
+            t_whole = torch.from_numpy(np.ascontiguousarray(whole.transpose()))   # (Z, Y, X), C order
+            slab = t_whole[first:first + n].contiguous()
+            if use_device:
+                slab = slab.cuda()
+            for mode in modes:
+                f = sh.ShardedImfilter(slab, kern, border, mode=mode, _library=lib)
+                assert (f.first, f.global_planes) == (first, nz), (f.first, f.global_planes, first, nz)
+                got = f.run()
+                if use_device:
+                    torch.cuda.synchronize()
+                got = got.cpu().numpy().transpose()
+                f.close()
+                want = ref[..., first:first + n]
+                if T == np.float64:
+                    ok = np.array_equal(got, want)
+                else:
+                    taps = [np.abs(np.asarray(k.data.parent, dtype=np.float64)).sum() for k in kern]
+                    tol = 1e-5 * float(np.prod(taps)) * float(np.abs(whole).max())
+                    ok = got.shape == want.shape and float(np.max(np.abs(got.astype(np.float64) - want.astype(np.float64)))) <= tol
+                    if not use_device:      # the oracle computes slabs exactly like whole arrays
+                        ok = ok and np.array_equal(got, want)
+                if not ok:
+                    failures.append((name, mode, rank))
+        dist.barrier()
+        dist.destroy_process_group()
+        errq.put((rank, failures))
+    except Exception:
+        errq.put((rank, ["EXC: " + traceback.format_exc()]))
+
+
+def launch(world, use_device, modes):
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=run, args=(r, world, port, use_device, modes, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = []
+    try:
+        for _ in procs:
+            results.append(q.get(timeout=180))
+    except Exception:
+        for p in procs:
+            if p.is_alive():
+                p.kill()
+        raise
+    for p in procs:
+        p.join(timeout=30)
+        if p.is_alive():
+            p.kill()
+    return results

@@ -346,8 +346,9 @@ def test_sepnd_parity(ifb, oracle, device, border):
 @pytest.mark.parametrize("border", ["symmetric", "replicate", "reflect", "circular", "fill"])
 @pytest.mark.parametrize("T", [np.float32, np.float64])
 def test_slab_form_matches_whole_volume(ifb, oracle, device, border, T):
-    """b2f_imfilter_slab on ONE device: cut a volume into 3 slabs, hand every slab its neighbours' xy-filtered planes
-    as halos (what the NCCL exchange delivers), and compare with the oracle on the whole volume."""
+    """b2f_imfilter_slab on ONE device: cut a volume into 3 slabs, hand every slab its neighbours' RAW boundary
+    planes as halos (what the NCCL exchange / the peer mapping delivers) and compare with the oracle on the whole
+    volume.  Float32 runs the fused stream3d kernel, Float64 the gathered per-stage slab path (bit-exact)."""
     import torch
     from importlib import import_module
     imf = import_module("imagefiltering_jl_b200.imfilter")
@@ -357,35 +358,22 @@ def test_slab_form_matches_whole_volume(ifb, oracle, device, border, T):
     kf = ifb.KernelFactors.gaussian((4, 4, 4)) if T == np.float32 else ifb.KernelFactors.gaussian((4.0, 4.0, 4.0))
     b = ifb.Fill(0.3) if border == "fill" else ifb.Pad(border)
     ref = ifb.imfilter(T, vol, kf, b, _library=oracle)
-    # xy stages on the whole volume (planes are independent), then the z stage slab by slab
-    xy = (kf[0], kf[1], ifb.ReshapedOneD(3, 2, ifb.centered(np.ones(1))))
     t_vol = torch.from_numpy(np.ascontiguousarray(vol.transpose(2, 1, 0))).cuda()
-    t_mid = torch.empty_like(t_vol)
-    st_xy = ifb._abi.StageList(imf.build_stages(xy, 3))
-    device.imfilter(ifb.DeviceArray.from_torch(t_vol).desc(), ifb.DeviceArray.from_torch(t_mid).desc(), st_xy, b.to_abi(3))
-    st_z = ifb._abi.StageList(imf.build_stages((kf[2],), 3))
-    zb = b
-    if border == "fill":   # the z stage must see the fill value pushed through the x and y stages
-        v = T(0.3)
-        for k in (kf[0], kf[1]):
-            acc = T(0)
-            for t in k.data.parent:
-                acc = T(acc + T(v * T(t))) if T == np.float64 else np.float32(np.float64(v) * np.float64(np.float32(t)) + np.float64(acc))
-            v = acc
-        zb = ifb.Fill(float(v))
+    st = ifb._abi.StageList(imf.build_stages(kf, 3))
     out = torch.empty_like(t_vol)
     bounds = [0, 17, 41, Z]
+    circ = border == "circular"
     for i in range(3):
         z0, z1 = bounds[i], bounds[i + 1]
-        circ = border == "circular"
         lo = h if (i > 0 or circ) else 0
         hi = h if (i < 2 or circ) else 0
-        planes = [(z % Z) for z in range(z0 - lo, z1 + hi)]
-        buf = t_mid[planes].contiguous()
-        o = torch.empty((z1 - z0, Y, X), dtype=t_vol.dtype, device="cuda")
-        device.imfilter_slab(ifb.DeviceArray.from_torch(buf).desc(), ifb.DeviceArray.from_torch(o).desc(), st_z,
-                             zb.to_abi(3), Z, z0, lo, hi)
-        assert device.last_path() == "slab"
+        own = t_vol[z0:z1].contiguous()
+        hlo = t_vol[[(z % Z) for z in range(z0 - lo, z0)]].contiguous() if lo else None
+        hhi = t_vol[[(z % Z) for z in range(z1, z1 + hi)]].contiguous() if hi else None
+        o = torch.empty_like(own)
+        device.imfilter_slab(ifb.DeviceArray.from_torch(own).desc(), ifb.DeviceArray.from_torch(o).desc(), st,
+                             b.to_abi(3), Z, z0, hlo.data_ptr() if lo else 0, lo, hhi.data_ptr() if hi else 0, hi)
+        assert device.last_path() == ("stream3d_slab" if T == np.float32 else "slab")
         out[z0:z1] = o
     got = out.cpu().numpy().transpose(2, 1, 0)
     if T == np.float64:
@@ -393,7 +381,47 @@ def test_slab_form_matches_whole_volume(ifb, oracle, device, border, T):
     else:
         assert np.max(np.abs(got.astype(np.float64) - ref.astype(np.float64))) <= 1e-5
     with pytest.raises(ifb.DimensionMismatch):     # halo smaller than the kernel needs
-        buf = t_mid[17 - 2:41 + 2].contiguous()
-        o = torch.empty((24, Y, X), dtype=t_vol.dtype, device="cuda")
-        device.imfilter_slab(ifb.DeviceArray.from_torch(buf).desc(), ifb.DeviceArray.from_torch(o).desc(), st_z,
-                             zb.to_abi(3), Z, 17, 2, 2)
+        own = t_vol[17:41].contiguous()
+        hlo, hhi = t_vol[15:17].contiguous(), t_vol[41:43].contiguous()
+        o = torch.empty_like(own)
+        device.imfilter_slab(ifb.DeviceArray.from_torch(own).desc(), ifb.DeviceArray.from_torch(o).desc(), st,
+                             b.to_abi(3), Z, 17, hlo.data_ptr(), 2, hhi.data_ptr(), 2)
+
+
+@pytest.mark.parametrize("border", BORDERS + ["fill"])
+def test_stream3d_parity(ifb, oracle, device, border, monkeypatch):
+    """Fused 3-D separable kernel (BASELINE config 5 in miniature): exact 17^3 / 9^3 / 5^3 / 3^3 instantiations and
+    the run-time-count one, tiles with x/y edges, odd widths (scalar loads / stores), arrays thinner than the halo,
+    asymmetric and even-length factors; the two-pass `sepnd` path must agree within the same tolerance."""
+    rng = np.random.default_rng(sum(map(ord, border)))
+    b = ifb.Fill(0.7) if border == "fill" else border
+    g = ifb.KernelFactors.gaussian
+    asym = (ifb.ReshapedOneD(3, 0, ifb.OffsetArray.with_first(rng.random(4).astype(np.float32), (-1,))),
+            ifb.ReshapedOneD(3, 1, ifb.OffsetArray.with_first(rng.random(6).astype(np.float32), (-4,))),
+            ifb.ReshapedOneD(3, 2, ifb.OffsetArray.with_first(rng.random(3).astype(np.float32), (0,))))
+    cases = [
+        ((70, 50, 40), g((4, 4, 4))),
+        ((200, 97, 23), g((4, 4, 4))),
+        ((129, 33, 19), g((2, 2, 2))),
+        ((65, 70, 12), g((1, 1, 1))),
+        ((131, 37, 9), ifb.KernelFactors.sobel((True, True, True), 2)),
+        ((33, 41, 29), g((1, 2, 3))),
+        ((64, 64, 64), g((3, 2, 4))),
+        ((5, 4, 3), g((4, 4, 4))),
+        ((77, 66, 30), asym),
+        ((256, 80, 70), g((4, 4, 4))),
+    ]
+    for shape, kern in cases:
+        if border == "reflect" and min(shape) < 2:
+            continue
+        img = np.asfortranarray(rng.random(shape, dtype=np.float32))
+        pa, pb = _both(ifb, oracle, np.float32, img, kern, b)
+        assert device.last_path() == "stream3d", (device.last_path(), shape)
+        taps = [k.data.parent for k in kern]
+        err = np.max(np.abs(pa.astype(np.float64) - pb.astype(np.float64)))
+        assert err <= _tol(taps, img), (shape, border, err)
+    monkeypatch.setenv("B2F_FORCE_PATH", "sepnd")
+    img = np.asfortranarray(rng.random((70, 50, 40), dtype=np.float32))
+    pa, pb = _both(ifb, oracle, np.float32, img, g((4, 4, 4)), b)
+    assert device.last_path() == "sepnd"
+    assert np.max(np.abs(pa.astype(np.float64) - pb.astype(np.float64))) <= _tol([k.data.parent for k in g((4, 4, 4))], img)
