@@ -21,12 +21,13 @@ def main():
     import torch
     import imagefiltering_jl_b200 as ifb
     from importlib import import_module
-    from bench import peaks
+    from bench import ClockSampler, peaks
     imf = import_module("imagefiltering_jl_b200.imfilter")
     lib = import_module("imagefiltering_jl_b200._lib").lib()
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--only", default="")
+    ap.add_argument("--clocks", action="store_true", help="also sample SM clocks / throttle reasons under each workload")
     args = ap.parse_args()
     only = set(x for x in args.only.split(",") if x)
     dev = torch.device("cuda", 0)
@@ -35,6 +36,8 @@ def main():
     sptr = stream.cuda_stream
     hbm, which = peaks()
     DA = ifb.DeviceArray
+
+    clk = {}
 
     def timeit(fn, steps):
         for _ in range(3):
@@ -46,7 +49,18 @@ def main():
             fn()
         b.record(stream)
         torch.cuda.synchronize()
-        return a.elapsed_time(b) / steps
+        ms = a.elapsed_time(b) / steps
+        if args.clocks:      # a second, longer untimed loop under the clock sampler (~0.6 s of load)
+            sm = ClockSampler(0)
+            sm.start()
+            import time
+            t0 = time.time()
+            while time.time() - t0 < 0.6:
+                for _ in range(5):
+                    fn()
+                torch.cuda.synchronize()
+            clk.update(sm.stop())
+        return ms
 
     def report(name, desc, ms, npx, bytes_px, extra=None):
         gbs = npx * bytes_px / (ms * 1e-3) / 1e9
@@ -55,6 +69,8 @@ def main():
              "peak_source": "of " + which, "path": lib.last_path()}
         if extra:
             d.update(extra)
+        if clk:
+            d["clocks"] = dict(clk)
         print(json.dumps(d), flush=True)
 
     g = torch.Generator(device=dev)

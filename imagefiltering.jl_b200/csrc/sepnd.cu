@@ -123,6 +123,7 @@ static int run_pass(const int64_t *dims, const StageInfo *sx, const StageInfo *s
     if (sx) {
         P.Lx = (int)sx->s->len[0]; P.klox = (int)sx->lo[0];
         for (int j = 0; j < P.Lx; ++j) P.kx[0][j] = (CT)sx->s->taps[j];
+        for (int j = 1; j < P.Lx; ++j) P.kxp[0][j] = make_float2((float)sx->s->taps[j], (float)sx->s->taps[j - 1]);
     }
     if (sy) {
         P.Ly = (int)sy->s->len[yaxis]; P.kloy = (int)sy->lo[yaxis];

@@ -56,6 +56,7 @@ static int run_typed(const Plan *plans, const void *d_img, int img_dt, void *con
         P.Lx = (int)sx.s->len[0]; P.klox = (int)sx.lo[0];
         P.Ly = (int)sy.s->len[1]; P.kloy = (int)sy.lo[1];
         for (int j = 0; j < P.Lx; ++j) P.kx[p][j] = (CT)sx.s->taps[j];
+        for (int j = 1; j < P.Lx; ++j) P.kxp[p][j] = make_float2((float)sx.s->taps[j], (float)sx.s->taps[j - 1]);
         for (int d = 0; d < P.Ly; ++d) P.kyr[p][d] = (CT)sy.s->taps[P.Ly - 1 - d];
     }
     P.vec_ok = aligned ? 1 : 0;

@@ -22,6 +22,8 @@
 // HBM traffic: each input pixel is read once (+ halo re-reads that hit L2), each output written once.
 #pragma once
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace b2f {
@@ -49,7 +51,23 @@ struct S2Params {
     int vec_ok;               // output rows are 16-byte aligned for every strip
     CT kx[NPL][S2_MAXTAPS];
     CT kyr[NPL][S2_MAXTAPS];  // y taps reversed: kyr[d] = ky[Ly-1-d]
+    float2 kxp[NPL][S2_MAXTAPS];  // Float32 compute only: kxp[j] = (kx[j], kx[j-1]), the taps one input carries to two adjacent outputs
 };
+
+// Packed FP32 multiply-add (sm_100a FFMA2: two FMAs per issue slot; every result is the same single-rounded fma as fmaf).
+// s2_fma2: (a.x*k + c.x, a.y*k + c.y), tap broadcast.  s2_fma2b: (v*k.x + c.x, v*k.y + c.y), value broadcast.
+__device__ __forceinline__ float2 s2_fma2(float2 a, float k, float2 c) {
+    unsigned long long ra = *reinterpret_cast<unsigned long long *>(&a), rc = *reinterpret_cast<unsigned long long *>(&c), rb, rd;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(rb) : "f"(k));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    return *reinterpret_cast<float2 *>(&rd);
+}
+__device__ __forceinline__ float2 s2_fma2b(float v, float2 k, float2 c) {
+    unsigned long long rk = *reinterpret_cast<unsigned long long *>(&k), rc = *reinterpret_cast<unsigned long long *>(&c), rv, rd;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(rv) : "f"(v));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(rv), "l"(rk), "l"(rc));
+    return *reinterpret_cast<float2 *>(&rd);
+}
 
 template <typename CT> struct S2Vec;
 template <> struct S2Vec<float> { typedef float4 T; static constexpr int PX = 4; };
@@ -75,9 +93,20 @@ template <> struct S2Conv<uint8_t, float> {
 
 constexpr int s2_gcd(int a, int b) { return b == 0 ? a : s2_gcd(b, a % b); }
 
-__device__ __forceinline__ int s2_remap(int style, int i, int n) {   // 32-bit twin of remap_index
+// 32-bit twin of remap_index.  The out-of-range branch is kept OUT OF LINE: it runs for border strips only, and inlined
+// into every unrolled row it spread the hot loop over 79 KB of code (instruction-cache misses were the top stall).
+static __device__ __noinline__ int s2_remap_slow(int style, int i, int n) {
+    if (style == B2F_REPLICATE) return i < 0 ? 0 : n - 1;
+    if (style == B2F_FILL) return -1;
+    int p = style == B2F_CIRCULAR ? n : (style == B2F_SYMMETRIC ? 2 * n : 2 * n - 2);
+    int m = i % p;
+    if (m < 0) m += p;
+    if (style == B2F_CIRCULAR || m < n) return m;
+    return style == B2F_SYMMETRIC ? p - 1 - m : p - m;
+}
+__device__ __forceinline__ int s2_remap(int style, int i, int n) {
     if ((unsigned)i < (unsigned)n) return i;
-    return (int)remap_index(style, (int64_t)i, (int64_t)n);
+    return s2_remap_slow(style, i, n);
 }
 
 // One input row of a strip: stage 1 from the smem ring, stage 2 into the register ring, emit the finished
@@ -111,7 +140,31 @@ __device__ __forceinline__ void s2_row(const int u, const int rv, const S2Params
     for (int p = 0; p < NPL; ++p)
 #pragma unroll
         for (int q = 0; q < PX; ++q) mid[p][q] = (CT)0;
-    if (XS) {
+    if constexpr (XS && std::is_same<CT, float>::value) {
+        // Float32: input-major packed form.  Window value v[i] feeds outputs (2c, 2c+1) with the tap pair
+        // (k[j], k[j-1]), j = i - 2c, as one FFMA2; the two end taps touch one output only (scalar FFMA).  Per output
+        // the taps still arrive in ascending order, so the bits equal the scalar fmaf loop.
+#pragma unroll
+        for (int i = 0; i < PX + LBX - 1; ++i) {
+#pragma unroll
+            for (int c = 0; c < PX / 2; ++c) {
+                const int j = i - 2 * c;
+                if (j >= 0 && j <= LBX && (LXT || j <= Lx)) {
+#pragma unroll
+                    for (int p = 0; p < NPL; ++p) {
+                        if (j == 0) {
+                            mid[p][2 * c] = fmaf(v[i], P.kx[p][0], mid[p][2 * c]);
+                        } else if (j < LBX && (LXT || j < Lx)) {
+                            const float2 r = s2_fma2b(v[i], P.kxp[p][j], make_float2(mid[p][2 * c], mid[p][2 * c + 1]));
+                            mid[p][2 * c] = r.x; mid[p][2 * c + 1] = r.y;
+                        } else if (LXT || j == Lx) {
+                            mid[p][2 * c + 1] = fmaf(v[i], P.kx[p][j - 1], mid[p][2 * c + 1]);
+                        }
+                    }
+                }
+            }
+        }
+    } else if constexpr (XS) {
 #pragma unroll
         for (int j = 0; j < LBX; ++j) {
             if (LXT || j < Lx) {
@@ -137,8 +190,17 @@ __device__ __forceinline__ void s2_row(const int u, const int rv, const S2Params
 #pragma unroll
             for (int p = 0; p < NPL; ++p) {
                 const CT kj = P.kyr[p][d];
+                if constexpr (std::is_same<CT, float>::value) {
 #pragma unroll
-                for (int q = 0; q < PX; ++q) acc[p][slot][q] = mac<CT>(acc[p][slot][q], mid[p][q], kj);
+                    for (int q = 0; q < PX; q += 2) {
+                        const float2 r = s2_fma2(make_float2(mid[p][q], mid[p][q + 1]), kj,
+                                                 make_float2(acc[p][slot][q], acc[p][slot][q + 1]));
+                        acc[p][slot][q] = r.x; acc[p][slot][q + 1] = r.y;
+                    }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < PX; ++q) acc[p][slot][q] = mac<CT>(acc[p][slot][q], mid[p][q], kj);
+                }
             }
         }
     }

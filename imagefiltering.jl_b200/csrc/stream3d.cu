@@ -24,18 +24,55 @@ bool stream3d_applicable(const Plan &P, int img_dt, int out_dt) {
     return true;
 }
 
+// cuTensorMapEncodeTiled through the runtime (no link-time dependency on libcuda)
+typedef CUresult (*s3_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                 const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static s3_encode_fn s3_encoder() {
+    static s3_encode_fn fn = [] {
+        void *f = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qr) != cudaSuccess ||
+            qr != cudaDriverEntryPointSuccess)
+            f = nullptr;
+        return (s3_encode_fn)f;
+    }();
+    return fn;
+}
+
+// 3-D map over `nplanes` dense W x H Float32 planes; box = (S3_RWP, rows, 1): one raw tile incl. halo, delivered with the
+// shared-memory pitch the x stage expects; elements outside the array read as zero
+static bool s3_make_map(CUtensorMap *m, const void *base, int W, int H, long long nplanes, int rows) {
+    s3_encode_fn enc = s3_encoder();
+    if (!enc || !base || nplanes < 1) return false;
+    cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)nplanes};
+    cuuint64_t strides[2] = {(cuuint64_t)W * 4, (cuuint64_t)W * H * 4};
+    cuuint32_t box[3] = {(cuuint32_t)S3_RWP, (cuuint32_t)rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void *>(base), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <int LXT, int LYT, int LZT>
-static int s3_launch_one(const S3Params &P, long long nblocks, cudaStream_t st) {
-    constexpr int LBY = LYT ? LYT : S3_MAXTAPS;
-    constexpr int RH = S3_T + LBY - 1;
-    const size_t smem = sizeof(float) * (size_t)(S3_NRAW * RH * S3_RWP + S3_NXF * RH * S3_XFP + S3_RING * S3_T * S3_T) + sizeof(int) * RH;
+static int s3_launch_one(S3Params &P, long long nblocks, cudaStream_t st) {
+    typedef S3C<LXT, LYT, LZT> C;
+    const size_t smem = C::SMEM + 1024;     // + alignment slack for the 1024-byte aligned base
     auto kern = stream3d_kernel<LXT, LYT, LZT>;
     static thread_local bool configured = false;
     if (!configured) {
         B2F_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    kern<<<(unsigned)nblocks, S3_NT, smem, st>>>(P);
+    alignas(64) CUtensorMap m_own, m_lo, m_hi;
+    memset(&m_own, 0, sizeof m_own); memset(&m_lo, 0, sizeof m_lo); memset(&m_hi, 0, sizeof m_hi);
+    static const bool no_tma = getenv("B2F_S3_NO_TMA") != nullptr;      // debugging knob: force the barrier path
+    bool tma = !no_tma && P.vec_in && (P.style != B2F_FILL || P.fill == 0.0f);
+    tma = tma && s3_make_map(&m_own, P.own, P.W, P.H, P.own_n, C::RH);
+    if (tma && P.lo_n > 0) tma = s3_make_map(&m_lo, P.lo, P.W, P.H, P.lo_n, C::RH);
+    if (tma && P.hi_n > 0) tma = s3_make_map(&m_hi, P.hi, P.W, P.H, P.hi_n, C::RH);
+    P.use_tma = tma ? 1 : 0;
+    kern<<<(unsigned)nblocks, S3_NT, smem, st>>>(P, m_own, m_lo, m_hi);
     count_launch();
     B2F_CUDA(cudaGetLastError());
     return 0;
@@ -58,6 +95,7 @@ int run_stream3d_slab(const Plan &Pl, const void *own, const void *lo, int64_t l
     P.Ly = (int)sy.s->len[1]; P.kloy = (int)sy.lo[1];
     P.Lz = (int)sz.s->len[2]; P.kloz = (int)sz.lo[2];
     for (int j = 0; j < P.Lx; ++j) P.kx[j] = (float)sx.s->taps[j];
+    for (int j = 1; j < P.Lx; ++j) P.kxp[j] = make_float2(P.kx[j], P.kx[j - 1]);
     for (int j = 0; j < P.Ly; ++j) P.ky[j] = (float)sy.s->taps[j];
     for (int j = 0; j < P.Lz; ++j) P.kz[j] = (float)sz.s->taps[j];
     auto al16 = [](const void *p) { return reinterpret_cast<uintptr_t>(p) % 16 == 0; };
