@@ -48,6 +48,7 @@ static bool s3_make_map(CUtensorMap *m, const void *base, int W, int H, long lon
     cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)nplanes};
     cuuint64_t strides[2] = {(cuuint64_t)W * 4, (cuuint64_t)W * H * 4};
     cuuint32_t box[3] = {(cuuint32_t)S3_RWP, (cuuint32_t)rows, 1};
+    if (W < S3_RWP || H < rows) return false;            // tiny arrays take the gather loader
     cuuint32_t estr[3] = {1, 1, 1};
     return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void *>(base), dims, strides, box, estr,
                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -55,23 +56,32 @@ static bool s3_make_map(CUtensorMap *m, const void *base, int W, int H, long lon
 }
 
 template <int LXT, int LYT, int LZT>
-static int s3_launch_one(S3Params &P, long long nblocks, cudaStream_t st) {
+static int s3_launch_one(S3Params &P, const float *kz, long long nch, cudaStream_t st) {
+    long long nblocks;
     typedef S3C<LXT, LYT, LZT> C;
-    const size_t smem = C::SMEM + 1024;     // + alignment slack for the 1024-byte aligned base
+    const size_t smem = C::SMEM;
     auto kern = stream3d_kernel<LXT, LYT, LZT>;
     static thread_local bool configured = false;
     if (!configured) {
         B2F_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
+    for (int j = 0; j < S3_MAXTAPS; ++j) P.kzr[j] = 0.f;
+    for (int j = 0; j < P.Lz; ++j) P.kzr[C::LBZ - P.Lz + j] = kz[j];      // right-aligned in the LBZ slots
     alignas(64) CUtensorMap m_own, m_lo, m_hi;
     memset(&m_own, 0, sizeof m_own); memset(&m_lo, 0, sizeof m_lo); memset(&m_hi, 0, sizeof m_hi);
-    static const bool no_tma = getenv("B2F_S3_NO_TMA") != nullptr;      // debugging knob: force the barrier path
-    bool tma = !no_tma && P.vec_in && (P.style != B2F_FILL || P.fill == 0.0f);
+    static const bool no_tma = getenv("B2F_S3_NO_TMA") != nullptr;      // debugging knob: force the gather loader
+    bool tma = !no_tma && P.use_tma && (P.style != B2F_FILL || P.fill == 0.0f);
     tma = tma && s3_make_map(&m_own, P.own, P.W, P.H, P.own_n, C::RH);
     if (tma && P.lo_n > 0) tma = s3_make_map(&m_lo, P.lo, P.W, P.H, P.lo_n, C::RH);
     if (tma && P.hi_n > 0) tma = s3_make_map(&m_hi, P.hi, P.W, P.H, P.hi_n, C::RH);
     P.use_tma = tma ? 1 : 0;
+    // cp.async.bulk.tensor wants the box to start on a 16-byte boundary of the innermost axis (found the hard way:
+    // "illegal instruction" otherwise), so the tile grid is shifted left by xsh = klox mod 4 columns
+    P.xsh = tma ? ((P.klox % 4) + 4) % 4 : 0;
+    if (P.xsh & 1) P.vec_out = 0;
+    P.ntx = (P.W + P.xsh + S3_TX - 1) / S3_TX;
+    nblocks = (long long)P.ntx * P.nty * nch;
     kern<<<(unsigned)nblocks, S3_NT, smem, st>>>(P, m_own, m_lo, m_hi);
     count_launch();
     B2F_CUDA(cudaGetLastError());
@@ -94,32 +104,36 @@ int run_stream3d_slab(const Plan &Pl, const void *own, const void *lo, int64_t l
     P.Lx = (int)sx.s->len[0]; P.klox = (int)sx.lo[0];
     P.Ly = (int)sy.s->len[1]; P.kloy = (int)sy.lo[1];
     P.Lz = (int)sz.s->len[2]; P.kloz = (int)sz.lo[2];
+    float kz[S3_MAXTAPS];
     for (int j = 0; j < P.Lx; ++j) P.kx[j] = (float)sx.s->taps[j];
     for (int j = 1; j < P.Lx; ++j) P.kxp[j] = make_float2(P.kx[j], P.kx[j - 1]);
     for (int j = 0; j < P.Ly; ++j) P.ky[j] = (float)sy.s->taps[j];
-    for (int j = 0; j < P.Lz; ++j) P.kz[j] = (float)sz.s->taps[j];
+    for (int j = 0; j < P.Lz; ++j) kz[j] = (float)sz.s->taps[j];
     auto al16 = [](const void *p) { return reinterpret_cast<uintptr_t>(p) % 16 == 0; };
-    P.vec_in = (P.W % 4 == 0) && al16(own) && (lo_n == 0 || al16(lo)) && (hi_n == 0 || al16(hi));
+    P.use_tma = (P.W % 4 == 0) && al16(own) && (lo_n == 0 || al16(lo)) && (hi_n == 0 || al16(hi));
     P.vec_out = (P.W % 2 == 0) && reinterpret_cast<uintptr_t>(d_out) % 8 == 0;
-    P.ntx = (P.W + S3_T - 1) / S3_T;
-    P.nty = (P.H + S3_T - 1) / S3_T;
-    // z-chunks: one march per tile unless the xy tiling alone cannot fill the machine (each chunk re-runs Lz-1 planes)
+    P.ntx = (P.W + S3_TX - 1) / S3_TX;
+    P.nty = (P.H + S3_TY - 1) / S3_TY;
+    // z-chunks: every chunk re-runs Lz-1 planes of stages x and y, so take the split that minimises
+    // waves(tiles * nch) * (planes per chunk + Lz - 1) on the 148 SMs (1 CTA per SM)
     const long long tiles = (long long)P.ntx * P.nty;
-    long long nch = 1;
-    if (tiles < 2 * 148) {
-        nch = (2 * 148 + tiles - 1) / tiles;
-        const long long maxch = own_n / 32 > 0 ? own_n / 32 : 1;
-        if (nch > maxch) nch = maxch;
+    long long best = 1;
+    double best_cost = 0;
+    for (long long nch = 1; nch <= 64 && nch <= own_n; ++nch) {
+        const long long zc = (own_n + nch - 1) / nch;
+        if (nch > 1 && zc < 16) break;
+        const long long waves = (tiles * ((own_n + zc - 1) / zc) + 147) / 148;
+        const double cost = (double)waves * (double)(zc + P.Lz - 1 + 3);
+        if (nch == 1 || cost < best_cost * 0.97) { best = nch; best_cost = cost; }
     }
-    P.zchunk = (int)((own_n + nch - 1) / nch);
-    nch = (own_n + P.zchunk - 1) / P.zchunk;
-    const long long nblocks = tiles * nch;
-    if (nblocks > 0x7fffffffLL) return fail(B2F_ENOTSUP, "stream3d grid too large");
-    if (P.Lx == 17 && P.Ly == 17 && P.Lz == 17) return s3_launch_one<17, 17, 17>(P, nblocks, st);
-    if (P.Lx == 9 && P.Ly == 9 && P.Lz == 9) return s3_launch_one<9, 9, 9>(P, nblocks, st);
-    if (P.Lx == 5 && P.Ly == 5 && P.Lz == 5) return s3_launch_one<5, 5, 5>(P, nblocks, st);
-    if (P.Lx == 3 && P.Ly == 3 && P.Lz == 3) return s3_launch_one<3, 3, 3>(P, nblocks, st);
-    return s3_launch_one<0, 0, 0>(P, nblocks, st);
+    P.zchunk = (int)((own_n + best - 1) / best);
+    const long long nch = (own_n + P.zchunk - 1) / P.zchunk;
+    if ((tiles + P.nty) * nch > 0x7fffffffLL) return fail(B2F_ENOTSUP, "stream3d grid too large");
+    if (P.Lx == 17 && P.Ly == 17 && P.Lz == 17) return s3_launch_one<17, 17, 17>(P, kz, nch, st);
+    if (P.Lx == 9 && P.Ly == 9 && P.Lz == 9) return s3_launch_one<9, 9, 9>(P, kz, nch, st);
+    if (P.Lx == 5 && P.Ly == 5 && P.Lz == 5) return s3_launch_one<5, 5, 5>(P, kz, nch, st);
+    if (P.Lx == 3 && P.Ly == 3 && P.Lz == 3) return s3_launch_one<3, 3, 3>(P, kz, nch, st);
+    return s3_launch_one<0, 0, 0>(P, kz, nch, st);
 }
 
 int run_stream3d(const Plan &P, const void *d_img, void *d_out, cudaStream_t st) {

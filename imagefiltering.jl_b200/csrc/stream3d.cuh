@@ -4,29 +4,31 @@
 // reference's padarray + three full-volume passes through padded temporaries (src/imfilter.jl:321-341, 385-395,
 // 438-446, loops :724-739): every input voxel is read from HBM once, every output voxel written once.
 //
-//   * a CTA owns a 32 x 32 tile of the xy-plane and MARCHES along z over its chunk of planes, one plane per barrier
-//     interval ("phase"); its 12 warps are specialised, all three roles run concurrently on different planes:
-//       - loader (the y warps): plane q+2 -> cp.async (LDGSTS, 16-byte chunks on x-interior tiles) into a 3-deep ring
-//         of raw tiles (tile + halo).  This is where the border remap / Fill of src/border.jl:564-590 is applied, in
-//         x, y AND z, i.e. "pad the input once", exactly the reference's semantics;
-//       - x warps (6): stage x of plane q: 8 adjacent outputs per thread from a 24-value register window (6 LDS.128;
-//         the tile pitches are an odd number of 16-byte chunks, so a quarter-warp spanning two rows hits every bank
-//         once) -> xf tile (double buffered);
-//       - y warps (4): stage y of plane q-1: a thread owns 2 columns x 4 rows, 20 LDS.64 feed 4 register accumulators
-//         per column pair -> slot (q-1) % 32 of a ring of xy-filtered planes in shared memory;
-//       - z warps (2): stage z, register-blocked along z: a thread produces 8 consecutive output planes of its column
-//         pair from a 24-plane register window read out of the ring (24 LDS.64 for 8 x 2 outputs) and stores them
-//         (one 8-byte store per thread and plane, 128-byte rows).  The 16 row pairs of the tile take turns, two per
-//         phase (their 8-plane blocks are staggered), so every phase carries the same work;
-//   * every tap loop is unrolled with static register indices and ascending tap order (the reference's order); all
-//     multiply-adds are packed FFMA2 (fma.rn.f32x2: two voxels per instruction, the tap broadcast from a uniform
-//     register): the kernel sits at the FP32 ridge (51 FMA per 8 B of HBM traffic), and halving the FMA issue slots
-//     is what leaves room for the LDS / LDGSTS / STG stream;
-//   * one __syncthreads per plane; about 150 KB of shared memory, 1 CTA (12 warps) per SM.
+// Config 5 (17+17+17 taps, 8 B/voxel) sits on the FP32 ridge of the machine, and the binding on-chip resources are the
+// FMA issue slots and the shared-memory bandwidth, so the design minimises both per voxel:
+//
+//   * a CTA (256 threads, all warps alike — no role specialisation, one __syncthreads per plane) owns a 32 x 48 tile
+//     of the xy-plane and MARCHES along z over its chunk of planes;
+//   * raw planes (tile + halo, 48 x 64 floats) arrive through an 8-deep TMA ring (cp.async.bulk.tensor, mbarrier
+//     completion, issued 8 planes ahead by one thread; out-of-range cells read as zero).  Border tiles are patched in
+//     shared memory one plane before use from a per-CTA gather list built once through the border remap
+//     (src/border.jl:564-590 semantics in x, y; z is remapped by choosing the source plane): "pad the input once",
+//     exactly the reference's semantics, with no padded copy;
+//   * stage x: each thread makes 8 adjacent outputs of one raw row from a 24-value register window (6 LDS.128,
+//     conflict-free because the tile pitches are an odd number of 16-byte chunks) -> xf tile (double buffered);
+//   * stage y: each thread owns 2 columns x 3 rows: 19 LDS.64 feed 3 float2 outputs from a register window;
+//   * stage z runs in TRANSPOSED (systolic) form, entirely in registers: the thread keeps the Lz-1 partial sums of each
+//     of its 6 voxel columns (3 x 16 float2); a new xy-filtered value m completes the oldest output (stored at once, one
+//     8-byte store per row) and every other partial sum moves one slot up while it takes its tap,
+//     acc[j+1] = m * k[j] + acc[j].  No z ring in shared memory, no z re-reads, no register moves, static indices
+//     without unrolling the plane loop (an Lz-fold unrolled loop overflows the 32 KB instruction cache: measured 2
+//     no_instruction stalls per issue);
+//   * every tap loop is unrolled with static register indices and ascending tap order per output (the reference's
+//     order); all multiply-adds are packed FFMA2 (fma.rn.f32x2, tap broadcast from a uniform register).
 //
 // Slab form (multi-GPU): the planes of the last axis may live in three buffers — this rank's owned planes
 // plus `lo`/`hi` halo planes, which are either receive buffers or PEER memory of the neighbouring GPU mapped over
-// NVLink (the kernel then performs the halo exchange itself, by P2P loads, fused with the filter).
+// NVLink (the kernel then performs the halo exchange itself, by TMA / P2P loads, fused with the filter).
 #pragma once
 
 #include <cuda.h>
@@ -35,17 +37,15 @@
 
 namespace b2f {
 
-constexpr int S3_T = 32;           // tile edge (outputs): 32 x 32
+constexpr int S3_TX = 32, S3_TY = 64;   // tile (outputs)
+constexpr int S3_R = 2;                 // rows per thread in stages y / z
 constexpr int S3_MAXTAPS = 17;
-constexpr int S3_RZ = 4;           // output planes per z block
-constexpr int S3_RING = 32;        // xy-filtered planes kept in shared memory (>= RZ + MAXTAPS - 1 + 1; power of two)
-constexpr int S3_RWP = 52;         // raw tile pitch in floats: 13 chunks of 16 B (odd)
-constexpr int S3_XFP = 36;         // x-filtered tile pitch: 9 chunks (odd)
-constexpr int S3_XW = 6, S3_YW = 4, S3_ZW = 4;             // warps per role
-constexpr int S3_NP = 2;                                   // planes per phase: two warp groups, one plane each
-constexpr int S3_GW = S3_XW + S3_YW + S3_ZW;               // warps per group (14)
-constexpr int S3_NT = 32 * (S3_NP * S3_GW + 1);            // 928 threads: two worker groups + the TMA producer warp
-constexpr int S3_NRAW = 3 * S3_NP, S3_NXF = 2 * S3_NP;     // raw / xf tile buffers
+constexpr int S3_RWP = 52;              // raw tile pitch in floats: 13 chunks of 16 B (odd)
+constexpr int S3_XFP = 36;              // x-filtered tile pitch: 9 chunks (odd)
+constexpr int S3_NT = 512;
+constexpr int S3_NRAW = 8;              // raw ring depth (power of two)
+constexpr int S3_AHEAD = S3_NRAW - 2;   // the TMA of plane p is issued in interval p - 2 - AHEAD
+constexpr int S3_PT = 64, S3_PTA = 32, S3_PTB = 16;   // plane-source ring: entries, look-ahead and block of its refill
 
 struct S3Params {
     const float *own, *lo, *hi;    // owned planes / halo planes below / above (dense W x H planes)
@@ -57,9 +57,11 @@ struct S3Params {
     float fill;
     int Lx, Ly, Lz, klox, kloy, kloz;
     int zchunk, ntx, nty;          // output planes per z-chunk, tiles along x / y
-    int vec_in, vec_out;           // 16-byte loads / 8-byte stores are aligned
-    int use_tma;                   // the tensor maps are valid: interior tiles take the pipelined path
-    float kx[S3_MAXTAPS], ky[S3_MAXTAPS], kz[S3_MAXTAPS];
+    int vec_out;                   // 8-byte stores are aligned
+    int xsh;                       // tiles start at x = 32*tx - xsh, so that the TMA box starts on a 16-byte boundary
+    int use_tma;                   // the tensor maps are valid (else every cell comes through the gather loader)
+    float kx[S3_MAXTAPS], ky[S3_MAXTAPS];
+    float kzr[S3_MAXTAPS];         // z taps RIGHT-aligned in the instantiation's LBZ slots
     float2 kxp[S3_MAXTAPS];        // kxp[j] = (kx[j], kx[j-1]): the taps one input value carries to two adjacent outputs
 };
 
@@ -76,28 +78,21 @@ __device__ __forceinline__ float2 s3_fma2b(float v, float2 k, float2 c) {
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(rv), "l"(rk), "l"(rc));
     return *reinterpret_cast<float2 *>(&rd);
 }
-__device__ __forceinline__ void s3_cp16(float *dst, const float *src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src));
-}
-__device__ __forceinline__ void s3_cp4(float *dst, const float *src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src));
-}
-__device__ __forceinline__ void s3_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void s3_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // source of global plane index zi: halo buffers are matched on the LOGICAL index first (a circular wrap arrives as
-// an ordinary halo), then the border remap is applied in global coordinates.  nullptr = Fill plane.
-__device__ __forceinline__ const float *s3_plane(const S3Params &P, int zi) {
-    const int rel = zi - P.own_first;
-    if ((unsigned)rel < (unsigned)P.own_n) return P.own + (long long)rel * P.plane;
-    if (rel < 0 && rel >= -P.lo_n) return P.lo + (long long)(rel + P.lo_n) * P.plane;
-    if (rel >= P.own_n && rel < P.own_n + P.hi_n) return P.hi + (long long)(rel - P.own_n) * P.plane;
+// an ordinary halo), then the border remap is applied in global coordinates.  which: 0 own, 1 lo, 2 hi, -1 Fill plane.
+__device__ __forceinline__ void s3_locate(const S3Params &P, int zi, int &which, int &zc) {
+    int rel = zi - P.own_first;
+    which = 0;
+    if ((unsigned)rel < (unsigned)P.own_n) { zc = rel; return; }
+    if (rel < 0 && rel >= -P.lo_n) { which = 1; zc = rel + P.lo_n; return; }
+    if (rel >= P.own_n && rel < P.own_n + P.hi_n) { which = 2; zc = rel - P.own_n; return; }
     const int g = (int)remap_index(P.style, (int64_t)zi, (int64_t)P.Zg);
-    if (g < 0) return nullptr;
-    const int r2 = g - P.own_first;
-    if ((unsigned)r2 < (unsigned)P.own_n) return P.own + (long long)r2 * P.plane;
-    if (r2 < 0) return P.lo + (long long)(r2 + P.lo_n) * P.plane;      // host validated that it is present
-    return P.hi + (long long)(r2 - P.own_n) * P.plane;
+    rel = g - P.own_first;
+    if (g < 0) { which = -1; zc = 0; }
+    else if ((unsigned)rel < (unsigned)P.own_n) { zc = rel; }
+    else if (rel < 0) { which = 1; zc = rel + P.lo_n; }        // host validated that it is present
+    else { which = 2; zc = rel - P.own_n; }
 }
 
 // ---- mbarrier / TMA primitives (sm_90+ PTX) ----------------------------------------------------------------------------
@@ -105,20 +100,14 @@ __device__ __forceinline__ unsigned s3_sa(const void *p) { return (unsigned)__cv
 __device__ __forceinline__ void s3_mbar_init(uint64_t *b, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s3_sa(b)), "r"(count) : "memory");
 }
-__device__ __forceinline__ void s3_mbar_arrive(uint64_t *b) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s3_sa(b)) : "memory");
-}
 __device__ __forceinline__ void s3_mbar_expect_tx(uint64_t *b, unsigned bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s3_sa(b)), "r"(bytes) : "memory");
 }
-// Blocks in hardware until the phase with `parity` completes (the suspend-time hint keeps a waiting warp off the issue
-// port instead of spinning: re-polling warps were taking a quarter of all issue slots).
 __device__ __forceinline__ void s3_mbar_wait(uint64_t *b, unsigned parity) {
     unsigned ok;
     do {
-        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\nselp.u32 %0, 1, 0, p;\n}"
-                     : "=r"(ok) : "r"(s3_sa(b)), "r"(parity), "r"(1000000u) : "memory");
-        if (!ok) __nanosleep(100);
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(s3_sa(b)), "r"(parity) : "memory");
     } while (!ok);
 }
 __device__ __forceinline__ void s3_tma_load3d(float *dst, const void *tmap, uint64_t *bar, int c0, int c1, int c2) {
@@ -126,32 +115,27 @@ __device__ __forceinline__ void s3_tma_load3d(float *dst, const void *tmap, uint
                  ::"r"(s3_sa(dst)), "l"(tmap), "r"(s3_sa(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 
-__device__ __forceinline__ void s3_tma_prefetch3d(const void *tmap, int c0, int c1, int c2) {   // global -> L2 only
-    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];" ::"l"(tmap), "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
-
-// compile-time geometry shared by both execution paths
+// compile-time geometry
 template <int LXT, int LYT, int LZT> struct S3C {
-    static constexpr int T = S3_T;
     static constexpr int LBX = LXT ? LXT : S3_MAXTAPS, LBY = LYT ? LYT : S3_MAXTAPS, LBZ = LZT ? LZT : S3_MAXTAPS;
-    static constexpr int RH = T + LBY - 1;                        // raw / xf tile rows (compile-time bound)
-    static constexpr int RAWSZ = RH * S3_RWP, XFSZ = RH * S3_XFP, MIDSZ = T * T;
+    static constexpr int RH = S3_TY + LBY - 1;                    // raw / xf tile rows (compile-time bound), <= 64
+    static constexpr int RAWBYTES = RH * S3_RWP * 4;              // one TMA box
+    static constexpr int RAWSZ = ((RAWBYTES + 127) / 128) * 32;   // buffer stride in floats (128-byte multiple)
+    static constexpr int XFSZ = RH * S3_XFP;
     static constexpr int WINX = ((8 + LBX - 1 + 3) / 4) * 4;      // x window registers (whole 16-byte chunks), <= 24
-    static constexpr int WINZ = S3_RZ + LBZ - 1;                  // z window planes, <= 20
-    static constexpr int NBAR = 2 * S3_NRAW + 2 * S3_NXF + 2 * S3_RING;
-    static constexpr size_t SMEM = sizeof(float) * (size_t)(S3_NRAW * RAWSZ + S3_NXF * XFSZ + S3_RING * MIDSZ) +
-                                   sizeof(int) * (size_t)((RH + 1) & ~1) + sizeof(uint64_t) * NBAR;
-    static_assert(T + LBX - 1 <= S3_RWP && 8 * 3 + WINX <= S3_RWP, "raw pitch too small");
-    static_assert(WINZ + 2 * S3_NP <= S3_RING, "ring too short");
+    static constexpr int NCELL = ((RH * (S3_TX + LBX - 1) + 3) / 4) * 4;   // gather list capacity: the whole raw tile
+    static constexpr size_t SMEM = sizeof(float) * (size_t)(S3_NRAW * RAWSZ + 2 * XFSZ) + (sizeof(int) + sizeof(short)) * NCELL +
+                                   sizeof(int) * 2 * S3_PT + sizeof(uint64_t) * S3_NRAW;
+    static_assert(RH <= 8 * (S3_NT / 32) && S3_TX + LBX - 1 <= S3_RWP && 8 * 3 + WINX <= S3_RWP, "tile geometry");
 };
 
-// ---- stage x: 8 rows of the tile per warp.  A quarter-warp covers two rows x 32 columns (4 groups of 8 outputs) ----
+// ---- stage x: one row group of 8 outputs per thread.  A quarter-warp covers two rows x 32 columns ----------------------
 template <int LXT, int LYT, int LZT>
 __device__ __forceinline__ void s3_x_task(const S3Params &P, const float *__restrict__ rb, float *__restrict__ xb,
-                                          const int row0, const int in_rows, const int Lx, const int lane) {
+                                          const int in_rows, const int Lx, const int warp, const int lane) {
     typedef S3C<LXT, LYT, LZT> C;
     const int l8 = lane & 7, qw = lane >> 3;
-    const int xg = l8 & 3, row = row0 + 2 * qw + (l8 >> 2);
+    const int xg = l8 & 3, row = 8 * warp + 2 * qw + (l8 >> 2);
     if (row >= in_rows) return;
     const float *src = rb + row * S3_RWP + 8 * xg;
     float v[C::WINX];
@@ -183,80 +167,60 @@ __device__ __forceinline__ void s3_x_task(const S3Params &P, const float *__rest
     *reinterpret_cast<float4 *>(d + 4) = make_float4(a[2].x, a[2].y, a[3].x, a[3].y);
 }
 
-// ---- stage y: a half-warp covers 32 columns (16 pairs) of one 4-row group; 8 row groups over 4 warps ----------------------
+// ---- stage y: 2 columns x S3_R rows per thread; a half-warp covers the 32 columns of one row group -----------------------
 template <int LXT, int LYT, int LZT>
-__device__ __forceinline__ void s3_y_task(const S3Params &P, const float *__restrict__ xfb, float *__restrict__ slot,
-                                          const int yw, const int Ly, const int lane) {
+__device__ __forceinline__ void s3_y_task(const S3Params &P, const float *__restrict__ xb, float2 (&m)[S3_R], const int Ly) {
     typedef S3C<LXT, LYT, LZT> C;
-    const int yc = lane & 15, yg = 2 * yw + (lane >> 4);
-    const float *xb = xfb + (4 * yg) * S3_XFP + 2 * yc;
-    float2 m[4];
 #pragma unroll
-    for (int o = 0; o < 4; ++o) m[o] = make_float2(0.f, 0.f);
+    for (int o = 0; o < S3_R; ++o) m[o] = make_float2(0.f, 0.f);
 #pragma unroll
-    for (int i = 0; i < 4 + C::LBY - 1; ++i) {
-        if (LYT || i < 4 + Ly - 1) {
+    for (int i = 0; i < S3_R + C::LBY - 1; ++i) {
+        if (LYT || i < S3_R + Ly - 1) {
             const float2 s = *reinterpret_cast<const float2 *>(xb + i * S3_XFP);
 #pragma unroll
-            for (int o = 0; o < 4; ++o) {
+            for (int o = 0; o < S3_R; ++o) {
                 const int j = i - o;
                 if (j >= 0 && j < C::LBY && (LYT || j < Ly)) m[o] = s3_fma2(s, P.ky[j], m[o]);
             }
         }
     }
-    float *mb = slot + (4 * yg) * C::T + 2 * yc;
-#pragma unroll
-    for (int o = 0; o < 4; ++o) *reinterpret_cast<float2 *>(mb + o * C::T) = m[o];
 }
 
-// ---- stage z: the block of RZ output planes starting at (chunk-local) o0; a warp covers one row pair (2 rows x 16 column
-// pairs); rows 8*st .. 8*st+7 form the stagger class st = o0 mod RZ, 4 warps cover it --------------------------------------
+// ---- stage z in transposed (systolic) form: acc[j] is the partial sum of the output that takes tap j next.  The new
+// xy-filtered value m completes the oldest output (tap LBZ-1: stored) and moves every other partial sum one slot up
+// WHILE adding its tap — acc[j+1] = m * k[j] + acc[j] — so the rotation costs nothing: all register indices are static,
+// the plane loop is not unrolled, and each output still receives its taps in ascending order.  Run-time tap counts are
+// right-aligned in the LBZ slots: a new output enters at slot LBZ - Lz (the slots below stay zero) ---------------------------
 template <int LXT, int LYT, int LZT>
-__device__ __forceinline__ void s3_z_task(const S3Params &P, const float *__restrict__ mid, const int o0, const int zw,
-                                          const int x0, const int y0, const int zo0, const int nout, const int Lz,
-                                          const int lane) {
+__device__ __forceinline__ void s3_z_update(const S3Params &P, float2 (&acc)[S3_R][S3C<LXT, LYT, LZT>::LBZ],
+                                            const float2 (&m)[S3_R], const int Lz, float *__restrict__ op, const int W,
+                                            const int nrow, const int smode, const bool emit) {
     typedef S3C<LXT, LYT, LZT> C;
-    const int olo = max(o0, 0), ohi = min(o0 + S3_RZ, nout);
-    if (olo >= ohi) return;
-    const int st = o0 & (S3_RZ - 1);
-    const int zc = lane & 15;
-    const int row = 8 * st + 2 * zw + (lane >> 4);
-    const int gx = x0 + 2 * zc, gy = y0 + row;
-    const int smode = gx >= P.W ? 0 : (gx + 1 >= P.W ? 1 : (P.vec_out ? 3 : 2));   // 3: 8-byte store, 2: two scalars, 1: one
-    // ring walk in byte offsets: one add and one mask per plane (the ring is a power of two long)
-    constexpr unsigned MIDB = C::MIDSZ * 4u, RINGB = S3_RING * MIDB;
-    const unsigned off0 = (unsigned)(o0 & (S3_RING - 1)) * MIDB + (unsigned)(row * C::T + 2 * zc) * 4u;
-    const char *mbase = reinterpret_cast<const char *>(mid);
-    float2 w[C::WINZ];
+    float2 fin[S3_R];
+    {
+        const float k = P.kzr[C::LBZ - 1];
 #pragma unroll
-    for (int i = 0; i < C::WINZ; ++i)
-        if (LZT || i < S3_RZ + Lz - 1) w[i] = *reinterpret_cast<const float2 *>(mbase + ((off0 + i * MIDB) & (RINGB - 1)));
-    if (gy >= P.H || smode == 0) return;
-    float *op = P.out + (long long)(zo0 - P.own_first + o0) * P.plane + (long long)gy * P.W + gx;
-    float2 acc[S3_RZ];
+        for (int o = 0; o < S3_R; ++o) fin[o] = s3_fma2(m[o], k, acc[o][C::LBZ - 1]);
+    }
 #pragma unroll
-    for (int o = 0; o < S3_RZ; ++o) acc[o] = make_float2(0.f, 0.f);
+    for (int j = C::LBZ - 2; j >= 0; --j) {
+        if (LZT || j >= C::LBZ - Lz) {
+            const float k = P.kzr[j];
 #pragma unroll
-    for (int j = 0; j < C::LBZ; ++j) {
-        if (LZT || j < Lz) {
-            const float k = P.kz[j];
-#pragma unroll
-            for (int o = 0; o < S3_RZ; ++o) acc[o] = s3_fma2(w[o + j], k, acc[o]);
+            for (int o = 0; o < S3_R; ++o) acc[o][j + 1] = s3_fma2(m[o], k, acc[o][j]);
         }
     }
-    if (smode == 3 && olo == o0 && ohi == o0 + S3_RZ) {       // whole block, aligned rows: the common case
+    if (emit) {
+        if (smode == 3) {
 #pragma unroll
-        for (int o = 0; o < S3_RZ; ++o) *reinterpret_cast<float2 *>(op + (long long)o * P.plane) = acc[o];
-    } else {
+            for (int o = 0; o < S3_R; ++o)
+                if (o < nrow) *reinterpret_cast<float2 *>(op + o * W) = fin[o];
+        } else if (smode != 0) {
 #pragma unroll
-        for (int o = 0; o < S3_RZ; ++o) {
-            if (o0 + o >= olo && o0 + o < ohi) {
-                float *qp = op + (long long)o * P.plane;
-                if (smode == 3) {
-                    *reinterpret_cast<float2 *>(qp) = acc[o];
-                } else {
-                    qp[0] = acc[o].x;
-                    if (smode == 2) qp[1] = acc[o].y;
+            for (int o = 0; o < S3_R; ++o) {
+                if (o < nrow) {
+                    if (smode != 4) op[o * W] = fin[o].x;
+                    if (smode != 1) op[o * W + 1] = fin[o].y;
                 }
             }
         }
@@ -269,208 +233,149 @@ __global__ void __launch_bounds__(S3_NT, 1)
 stream3d_kernel(const __grid_constant__ S3Params P, const __grid_constant__ CUtensorMap m_own,
                 const __grid_constant__ CUtensorMap m_lo, const __grid_constant__ CUtensorMap m_hi) {
     typedef S3C<LXT, LYT, LZT> C;
-    constexpr int T = C::T, RAWSZ = C::RAWSZ, XFSZ = C::XFSZ, MIDSZ = C::MIDSZ, RH = C::RH;
+    constexpr int TX = S3_TX, TY = S3_TY, RAWSZ = C::RAWSZ, XFSZ = C::XFSZ, LBZ = C::LBZ, N = S3_NRAW;
 
     extern __shared__ __align__(1024) float s3_smem[];
-    float *raw = s3_smem;                       // S3_NRAW x RAWSZ
-    float *xf = raw + S3_NRAW * RAWSZ;          // S3_NXF x XFSZ
-    float *mid = xf + S3_NXF * XFSZ;            // S3_RING x MIDSZ
-    int *yoff = reinterpret_cast<int *>(mid + S3_RING * MIDSZ);   // RH source rows (-1: Fill)
-    uint64_t *bars = reinterpret_cast<uint64_t *>(yoff + ((RH + 1) & ~1));
+    float *raw = s3_smem;                       // N x RAWSZ
+    float *xf = raw + N * RAWSZ;                // 2 x XFSZ
+    int *cell_src = reinterpret_cast<int *>(xf + 2 * XFSZ);          // gather list: source offset inside a plane (-1: Fill)
+    unsigned short *cell_dst = reinterpret_cast<unsigned short *>(cell_src + C::NCELL);   // ... and raw-tile offset
+    int *ptw = reinterpret_cast<int *>(cell_dst + C::NCELL);         // ring of plane sources: buffer (0 own, 1 lo, 2 hi, -1 Fill)
+    int *ptz = ptw + S3_PT;                                           // ... and plane index inside it
+    uint64_t *full = reinterpret_cast<uint64_t *>(ptz + S3_PT);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int Lx = LXT ? LXT : P.Lx, Ly = LYT ? LYT : P.Ly, Lz = LZT ? LZT : P.Lz;
     const int bid = blockIdx.x;
     const int tx = bid % P.ntx, ty = (bid / P.ntx) % P.nty, ch = bid / (P.ntx * P.nty);
-    const int x0 = tx * T, y0 = ty * T;
-    const int in_cols = T + Lx - 1, in_rows = T + Ly - 1;
+    const int x0 = tx * TX - P.xsh, y0 = ty * TY;
+    const int in_cols = TX + Lx - 1, in_rows = TY + Ly - 1;
     const int zo0 = P.own_first + ch * P.zchunk;                         // first output plane of this chunk (global)
     const int nout = min(P.zchunk, P.own_first + P.own_n - zo0);
     const int in_planes = nout + Lz - 1;
     const int zin0 = zo0 + P.kloz;                                       // global index of input plane p = 0
     const int xa = x0 + P.klox, ya = y0 + P.kloy;
+    const bool tma = P.use_tma != 0;
 
-    const int grp = warp / S3_GW, wr = warp % S3_GW;      // plane group (2 = the producer warp), role index inside the group
-    const bool worker = grp < S3_NP;
-    const bool is_x = worker && wr < S3_XW, is_y = worker && wr >= S3_XW && wr < S3_XW + S3_YW,
-               is_z = worker && wr >= S3_XW + S3_YW;
-    const int yw = wr - S3_XW, zw = wr - S3_XW - S3_YW;
-
-    // ================================================================================================================
-    // Pipelined path (tiles whose input window needs no border remap in x / y): TMA loads, mbarrier hand-offs between
-    // the roles, no CTA-wide barrier in the plane loop.
-    //   producer lane : plane p -> raw[p % NRAW]         (cp.async.bulk.tensor; out-of-range rows/planes read as zero)
-    //   x warps (grp g = p % 2): raw -> xf[p % NXF];  y warps: xf -> ring slot p % RING;  z warps: ring -> out
-    // ================================================================================================================
-    if (P.use_tma && xa >= 0 && xa + in_cols <= P.W && ya >= 0 && ya + in_rows <= P.H) {
-        uint64_t *raw_full = bars, *raw_empty = raw_full + S3_NRAW, *xf_full = raw_empty + S3_NRAW,
-                 *xf_empty = xf_full + S3_NXF, *ring_full = xf_empty + S3_NXF, *zdone = ring_full + S3_RING;
-        if (tid == 0) {
-            for (int i = 0; i < S3_NRAW; ++i) { s3_mbar_init(raw_full + i, 1); s3_mbar_init(raw_empty + i, S3_XW); }
-            for (int i = 0; i < S3_NXF; ++i) { s3_mbar_init(xf_full + i, S3_XW); s3_mbar_init(xf_empty + i, S3_YW); }
-            for (int i = 0; i < S3_RING; ++i) { s3_mbar_init(ring_full + i, S3_YW); s3_mbar_init(zdone + i, S3_ZW); }
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    // in-range part of the raw tile: columns [cl, cr), rows [rt, rb); every other cell goes on the gather list
+    int cl = min(max(-xa, 0), in_cols), cr = min(max(P.W - xa, 0), in_cols);
+    const int rt = tma ? min(max(-ya, 0), in_rows) : 0, rb = tma ? min(max(P.H - ya, 0), in_rows) : in_rows;
+    if (!tma) cl = cr = in_cols;                                         // every column is "out of range": gather it all
+    const bool fix = !tma || (P.style != B2F_FILL && (cl > 0 || cr < in_cols || rt > 0 || rb < in_rows));
+    // column strips [0,cl) u [cr,in_cols) on every row, then row strips [0,rt) u [rb,in_rows) on the in-range columns
+    const int ncs = cl + (in_cols - cr), n1 = ncs * in_rows, wc = cr - cl, ncell = fix ? n1 + (rt + (in_rows - rb)) * wc : 0;
+    for (int idx = tid; idx < ncell; idx += S3_NT) {
+        int r, c;
+        if (idx < n1) {
+            r = idx / ncs;
+            const int k = idx - r * ncs;
+            c = k < cl ? k : cr + (k - cl);
+        } else {
+            const int i2 = idx - n1;
+            const int rr = i2 / wc;
+            c = cl + (i2 - rr * wc);
+            r = rr < rt ? rr : rb + (rr - rt);
         }
-        __syncthreads();
-        const int s_first = -(S3_RZ - 1);                   // first block start that owns a valid output
-        const int nblocks = nout - s_first;                 // block starts s_first .. nout-1
-        if (!worker) {
-            if (lane == 0) {
-                // source of plane p: own / halo buffers matched on the logical index, else the border remap
-                auto locate = [&](int p, const void *&map, int &zc) {
-                    const int zi = zin0 + p;
-                    int rel = zi - P.own_first;
-                    map = &m_own;
-                    if ((unsigned)rel < (unsigned)P.own_n) { zc = rel; return; }
-                    if (rel < 0 && rel >= -P.lo_n) { map = &m_lo; zc = rel + P.lo_n; return; }
-                    if (rel >= P.own_n && rel < P.own_n + P.hi_n) { map = &m_hi; zc = rel - P.own_n; return; }
-                    const int g = (int)remap_index(P.style, (int64_t)zi, (int64_t)P.Zg);
-                    rel = g - P.own_first;
-                    if (g < 0) { zc = P.own_n; }                                   // Fill(0): out of range reads zero
-                    else if ((unsigned)rel < (unsigned)P.own_n) { zc = rel; }
-                    else if (rel < 0) { map = &m_lo; zc = rel + P.lo_n; }
-                    else { map = &m_hi; zc = rel - P.own_n; }
-                };
-                // the shared-memory ring holds S3_NRAW planes (about one DRAM latency of work); planes further ahead are
-                // pulled into L2 by TMA prefetches, so the loads that fill the ring are L2 hits
-                constexpr int PF = 10;
-                const void *map;
-                int zc;
-                for (int p = 0; p < min(PF, in_planes); ++p) { locate(p, map, zc); s3_tma_prefetch3d(map, xa, ya, zc); }
-                for (int p = 0; p < in_planes; ++p) {
-                    const int b = p % S3_NRAW, k = p / S3_NRAW;
-                    if (p + PF < in_planes) { locate(p + PF, map, zc); s3_tma_prefetch3d(map, xa, ya, zc); }
-                    s3_mbar_wait(raw_empty + b, (k & 1) ^ 1);
-                    locate(p, map, zc);
-                    s3_mbar_expect_tx(raw_full + b, (unsigned)(RAWSZ * sizeof(float)));
-                    s3_tma_load3d(raw + b * RAWSZ, map, raw_full + b, xa, ya, zc);
-                }
-            }
-        } else if (is_x) {
-            for (int p = grp; p < in_planes; p += S3_NP) {
-                const int b = p % S3_NRAW, xbuf = p % S3_NXF;
-                s3_mbar_wait(raw_full + b, (p / S3_NRAW) & 1);
-                s3_mbar_wait(xf_empty + xbuf, ((p / S3_NXF) & 1) ^ 1);
-                s3_x_task<LXT, LYT, LZT>(P, raw + b * RAWSZ, xf + xbuf * XFSZ, 8 * wr, in_rows, Lx, lane);
-                __syncwarp();
-                if (lane == 0) { s3_mbar_arrive(xf_full + xbuf); s3_mbar_arrive(raw_empty + b); }
-            }
-        } else if (is_y) {
-            for (int p = grp; p < in_planes; p += S3_NP) {
-                const int xbuf = p % S3_NXF, slot = p & (S3_RING - 1);
-                // the slot still holds plane p - RING: every z block that reads it (starts <= p - RING) must be done;
-                // blocks of one group finish in order, so the newest block of each group is enough
-                const int bw = p - S3_RING - s_first;
-                if (bw >= 0) s3_mbar_wait(zdone + (bw & (S3_RING - 1)), (bw / S3_RING) & 1);
-                if (bw >= 1) s3_mbar_wait(zdone + ((bw - 1) & (S3_RING - 1)), ((bw - 1) / S3_RING) & 1);
-                s3_mbar_wait(xf_full + xbuf, (p / S3_NXF) & 1);
-                s3_y_task<LXT, LYT, LZT>(P, xf + xbuf * XFSZ, mid + slot * MIDSZ, yw, Ly, lane);
-                __syncwarp();
-                if (lane == 0) { s3_mbar_arrive(ring_full + slot); s3_mbar_arrive(xf_empty + xbuf); }
-            }
-        } else if (is_z) {
-            for (int b = grp; b < nblocks; b += S3_NP) {
-                const int o0 = s_first + b;
-                const int pn = min(o0 + S3_RZ + Lz - 2, in_planes - 1);      // newest plane the block reads
-                s3_mbar_wait(ring_full + (pn & (S3_RING - 1)), (pn / S3_RING) & 1);
-                if (pn >= 1) s3_mbar_wait(ring_full + ((pn - 1) & (S3_RING - 1)), ((pn - 1) / S3_RING) & 1);
-                s3_z_task<LXT, LYT, LZT>(P, mid, o0, zw, x0, y0, zo0, nout, Lz, lane);
-                __syncwarp();
-                if (lane == 0) s3_mbar_arrive(zdone + (b & (S3_RING - 1)));
-            }
-        }
-        return;
+        const int sx = (int)remap_index(P.style, (int64_t)xa + c, (int64_t)P.W);
+        const int sy = (int)remap_index(P.style, (int64_t)ya + r, (int64_t)P.H);
+        cell_src[idx] = (sx < 0 || sy < 0) ? -1 : sy * P.W + sx;
+        cell_dst[idx] = (unsigned short)(r * S3_RWP + c);
+    }
+    if (tma && tid == 0) {
+        for (int i = 0; i < N; ++i) s3_mbar_init(full + i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
 
-    // ================================================================================================================
-    // Barrier path (border tiles, Fill(v != 0), unaligned arrays): cp.async loads through the border remap, one
-    // __syncthreads per phase of two planes.
-    // ================================================================================================================
-    for (int r = tid; r < in_rows; r += S3_NT) yoff[r] = (int)remap_index(P.style, (int64_t)ya + r, (int64_t)P.H);
+    const int qb = -2;                          // first interval of the plane loop
+    // plane sources: entry p & (S3_PT-1) describes input plane p; filled S3_PTA planes ahead of the loop
+    auto locate_block = [&](int p0, int n) {
+        if (tid < n) {
+            const int p = p0 + tid;
+            int which = -1, zc = 0;
+            if (p >= 0 && p < in_planes) s3_locate(P, zin0 + p, which, zc);
+            ptw[p & (S3_PT - 1)] = which;
+            ptz[p & (S3_PT - 1)] = zc;
+        }
+    };
+    locate_block(qb, S3_PTA);               // planes -2 .. PTA-3; the loop refills PTB planes at a time, PTA ahead
     __syncthreads();
 
-    // ---- loader state (y warps): 16-byte path when the whole window lies inside the row and is aligned --------------
-    const int in_cols4 = (in_cols + 3) & ~3;
-    const bool vec = P.vec_in && xa >= 0 && xa + in_cols4 <= P.W && (xa & 3) == 0;
-    const int nchunk = in_cols4 >> 2;                     // <= 12
-    // vector path: lane -> (row parity, chunk): 2 rows x 16 chunk slots per warp iteration
-    const int lrow = lane >> 4, lchk = lane & 15;
-    int xo[2] = {-2, -2};                                 // scalar path: source columns of this lane (-1 Fill, -2 none)
-    if (is_y && !vec) {
+    auto issue = [&](int p) {                   // one thread: TMA of input plane p into its ring buffer
+        const int which = ptw[p & (S3_PT - 1)];
+        const int zc = which < 0 ? P.own_n : ptz[p & (S3_PT - 1)];         // Fill(0) plane: out of range reads zero
+        const void *map = which == 1 ? (const void *)&m_lo : which == 2 ? (const void *)&m_hi : (const void *)&m_own;
+        const int b = p & (N - 1);
+        s3_mbar_expect_tx(full + b, (unsigned)C::RAWBYTES);
+        s3_tma_load3d(raw + b * RAWSZ, map, full + b, xa, ya, zc);
+    };
+    auto fixup = [&](int p) {                   // all threads: the gather list of input plane p
+        const int which = ptw[p & (S3_PT - 1)];
+        const float *src = which < 0 ? nullptr
+                                     : (which == 1 ? P.lo : which == 2 ? P.hi : P.own) + (long long)ptz[p & (S3_PT - 1)] * P.plane;
+        float *dst = raw + (p & (N - 1)) * RAWSZ;
+        for (int base = tid; base < ncell; base += 4 * S3_NT) {       // four gathers in flight per thread
+            float v[4];
+            int d[4];
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            const int c = lane + 32 * k;
-            if (c < in_cols) xo[k] = (int)remap_index(P.style, (int64_t)xa + c, (int64_t)P.W);
-        }
-    }
-    // vector path: this lane's (row, chunk) slots are the same for every plane: keep their source offsets in registers
-    constexpr int NLD = (RH + 2 * S3_YW - 1) / (2 * S3_YW);       // rows per lane and plane (6 for 17 taps)
-    int goff[NLD];                                                // element offset inside a plane; -1: Fill; -2: none
-#pragma unroll
-    for (int i = 0; i < NLD; ++i) {
-        const int r = 2 * yw + lrow + 2 * S3_YW * i;
-        goff[i] = -2;
-        if (is_y && vec && r < in_rows && lchk < nchunk) {
-            const int yo = yoff[r];
-            goff[i] = yo < 0 ? -1 : yo * P.W + xa + 4 * lchk;
-        }
-    }
-    auto load_plane = [&](int p, int buf) {
-        if (p < in_planes) {
-            const float *src = s3_plane(P, zin0 + p);
-            float *dst = raw + buf * RAWSZ;
-            if (vec) {
-                float *d = dst + (2 * yw + lrow) * S3_RWP + 4 * lchk;
-#pragma unroll
-                for (int i = 0; i < NLD; ++i) {
-                    if (goff[i] != -2) {
-                        if (src != nullptr && goff[i] >= 0) s3_cp16(d, src + goff[i]);
-                        else *reinterpret_cast<float4 *>(d) = make_float4(P.fill, P.fill, P.fill, P.fill);
-                    }
-                    d += 2 * S3_YW * S3_RWP;
-                }
-            } else {
-                for (int r = yw; r < in_rows; r += S3_YW) {
-                    const int yo = yoff[r];
-                    const float *srow = src + (long long)(yo < 0 ? 0 : yo) * P.W;
-#pragma unroll
-                    for (int k = 0; k < 2; ++k) {
-                        if (xo[k] != -2) {
-                            float *d = dst + r * S3_RWP + lane + 32 * k;
-                            if (src != nullptr && yo >= 0 && xo[k] >= 0) s3_cp4(d, srow + xo[k]);
-                            else *d = P.fill;
-                        }
-                    }
+            for (int k = 0; k < 4; ++k) {
+                const int idx = base + k * S3_NT;
+                d[k] = -1;
+                if (idx < ncell) {
+                    const int so = cell_src[idx];
+                    d[k] = cell_dst[idx];
+                    v[k] = (src != nullptr && so >= 0) ? __ldg(src + so) : P.fill;
                 }
             }
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (d[k] >= 0) dst[d[k]] = v[k];
         }
-        s3_commit();
+        if (tma) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     };
 
-    // Phase q: group g runs stage x on plane 2q+g, stage y on plane 2q-2+g, stage z on the block whose last input
-    // plane is 2q-4+g, and prefetches plane 2q+4+g.
-    if (is_y) { load_plane(grp, grp % S3_NRAW); load_plane(S3_NP + grp, (S3_NP + grp) % S3_NRAW); }
+    if (tma && tid == 0)
+        for (int p = 0; p < min(S3_AHEAD, in_planes); ++p) issue(p);
 
-    const int nphase = (in_planes + S3_RZ + 3) / S3_NP + 2;      // the last phases only drain partial z blocks
-    for (int q = 0; q < nphase; ++q) {
-        if (is_y) s3_wait<1>();
-        __syncthreads();
-        if (is_x) {
-            const int px = S3_NP * q + grp;
-            if (px < in_planes)
-                s3_x_task<LXT, LYT, LZT>(P, raw + (px % S3_NRAW) * RAWSZ, xf + (px % S3_NXF) * XFSZ, 8 * wr, in_rows, Lx, lane);
-        } else if (is_y) {
-            const int pl = S3_NP * (q + 2) + grp;
-            load_plane(pl, pl % S3_NRAW);
-            const int py = S3_NP * (q - 1) + grp;
-            if (py >= 0 && py < in_planes)
-                s3_y_task<LXT, LYT, LZT>(P, xf + (py % S3_NXF) * XFSZ, mid + (py & (S3_RING - 1)) * MIDSZ, yw, Ly, lane);
-        } else if (is_z) {
-            const int o0 = S3_NP * (q - 2) + grp - (S3_RZ - 1) - (Lz - 1);   // its last input plane is o0 + RZ-1 + Lz-1
-            s3_z_task<LXT, LYT, LZT>(P, mid, o0, zw, x0, y0, zo0, nout, Lz, lane);
+    // this thread's 2 x S3_R voxel columns in stages y / z
+    const int pc = tid & 15, rg = tid >> 4;
+    const int gx = x0 + 2 * pc, gy = y0 + S3_R * rg;
+    // 3: 8-byte store, 2: two scalars, 1: the first only, 4: the second only, 0: none
+    const int smode = (gx >= P.W || gx < -1) ? 0 : gx == -1 ? 4 : (gx + 1 >= P.W ? 1 : (P.vec_out ? 3 : 2));
+    const int nrow = min(S3_R, P.H - gy);                                           // <= 0: nothing to store
+    // output pointer of the plane completed by input plane q: advanced by one plane per interval
+    float *op = P.out + ((long long)(zo0 - P.own_first) + (qb - (Lz - 1))) * P.plane + (long long)gy * P.W + gx;
+    const int yoff = (S3_R * rg) * S3_XFP + 2 * pc;
+
+    float2 acc[S3_R][LBZ];
+#pragma unroll
+    for (int o = 0; o < S3_R; ++o)
+#pragma unroll
+        for (int j = 0; j < LBZ; ++j) acc[o][j] = make_float2(0.f, 0.f);
+
+    // Interval q: gather-patch plane q+2, stage x on plane q+1, stages y+z on plane q; TMA of plane q+2+AHEAD goes out.
+    for (int q = -2; q < in_planes; ++q) {
+        if (((q + 2) & (S3_PTB - 1)) == 0) locate_block(q + S3_PTA, S3_PTB);   // visible after this interval's barrier
+        if (tma && tid == 0 && q + 2 + S3_AHEAD < in_planes) issue(q + 2 + S3_AHEAD);
+        if (fix && q + 2 < in_planes) {
+            const int p = q + 2;
+            if (tma) s3_mbar_wait(full + (p & (N - 1)), (p / N) & 1);
+            fixup(p);
         }
+        if (q + 1 < in_planes) {
+            const int p = q + 1;
+            if (p >= 0) {
+                if (tma && !fix) s3_mbar_wait(full + (p & (N - 1)), (p / N) & 1);
+                s3_x_task<LXT, LYT, LZT>(P, raw + (p & (N - 1)) * RAWSZ, xf + (p & 1) * XFSZ, in_rows, Lx, warp, lane);
+            }
+        }
+        if (q >= 0) {
+            float2 m[S3_R];
+            s3_y_task<LXT, LYT, LZT>(P, xf + (q & 1) * XFSZ + yoff, m, Ly);
+            s3_z_update<LXT, LYT, LZT>(P, acc, m, Lz, op, P.W, nrow, smode, q >= Lz - 1 && nrow > 0);
+        }
+        op += P.plane;
+        __syncthreads();
     }
-    if (is_y) s3_wait<0>();
 }
 
 }  // namespace b2f
