@@ -7,18 +7,18 @@
 // Config 5 (17+17+17 taps, 8 B/voxel) sits on the FP32 ridge of the machine, and the binding on-chip resources are the
 // FMA issue slots and the shared-memory bandwidth, so the design minimises both per voxel:
 //
-//   * a CTA (256 threads, all warps alike — no role specialisation, one __syncthreads per plane) owns a 32 x 48 tile
-//     of the xy-plane and MARCHES along z over its chunk of planes;
-//   * raw planes (tile + halo, 48 x 64 floats) arrive through an 8-deep TMA ring (cp.async.bulk.tensor, mbarrier
+//   * a CTA (512 threads, all warps alike — no role specialisation, one split mbarrier hand-off per plane) owns a
+//     32 x 64 tile of the xy-plane and MARCHES along z over its chunk of planes;
+//   * raw planes (tile + halo, 48 x 80 floats) arrive through an 8-deep TMA ring (cp.async.bulk.tensor, mbarrier
 //     completion, issued 8 planes ahead by one thread; out-of-range cells read as zero).  Border tiles are patched in
 //     shared memory one plane before use from a per-CTA gather list built once through the border remap
 //     (src/border.jl:564-590 semantics in x, y; z is remapped by choosing the source plane): "pad the input once",
 //     exactly the reference's semantics, with no padded copy;
 //   * stage x: each thread makes 8 adjacent outputs of one raw row from a 24-value register window (6 LDS.128,
 //     conflict-free because the tile pitches are an odd number of 16-byte chunks) -> xf tile (double buffered);
-//   * stage y: each thread owns 2 columns x 3 rows: 19 LDS.64 feed 3 float2 outputs from a register window;
+//   * stage y: each thread owns 2 columns x 2 rows: 18 LDS.64 feed 2 float2 outputs from a register window;
 //   * stage z runs in TRANSPOSED (systolic) form, entirely in registers: the thread keeps the Lz-1 partial sums of each
-//     of its 6 voxel columns (3 x 16 float2); a new xy-filtered value m completes the oldest output (stored at once, one
+//     of its 4 voxel columns (2 x 16 float2); a new xy-filtered value m completes the oldest output (stored at once, one
 //     8-byte store per row) and every other partial sum moves one slot up while it takes its tap,
 //     acc[j+1] = m * k[j] + acc[j].  No z ring in shared memory, no z re-reads, no register moves, static indices
 //     without unrolling the plane loop (an Lz-fold unrolled loop overflows the 32 KB instruction cache: measured 2
@@ -44,6 +44,7 @@ constexpr int S3_RWP = 52;              // raw tile pitch in floats: 13 chunks o
 constexpr int S3_XFP = 36;              // x-filtered tile pitch: 9 chunks (odd)
 constexpr int S3_NT = 512;
 constexpr int S3_NRAW = 8;              // raw ring depth (power of two)
+constexpr int S3_NXF = 3;               // x-filtered tile ring depth
 constexpr int S3_AHEAD = S3_NRAW - 2;   // the TMA of plane p is issued in interval p - 2 - AHEAD
 constexpr int S3_PT = 64, S3_PTA = 32, S3_PTB = 16;   // plane-source ring: entries, look-ahead and block of its refill
 
@@ -100,6 +101,9 @@ __device__ __forceinline__ unsigned s3_sa(const void *p) { return (unsigned)__cv
 __device__ __forceinline__ void s3_mbar_init(uint64_t *b, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s3_sa(b)), "r"(count) : "memory");
 }
+__device__ __forceinline__ void s3_mbar_arrive(uint64_t *b) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s3_sa(b)) : "memory");
+}
 __device__ __forceinline__ void s3_mbar_expect_tx(uint64_t *b, unsigned bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s3_sa(b)), "r"(bytes) : "memory");
 }
@@ -124,8 +128,8 @@ template <int LXT, int LYT, int LZT> struct S3C {
     static constexpr int XFSZ = RH * S3_XFP;
     static constexpr int WINX = ((8 + LBX - 1 + 3) / 4) * 4;      // x window registers (whole 16-byte chunks), <= 24
     static constexpr int NCELL = ((RH * (S3_TX + LBX - 1) + 3) / 4) * 4;   // gather list capacity: the whole raw tile
-    static constexpr size_t SMEM = sizeof(float) * (size_t)(S3_NRAW * RAWSZ + 2 * XFSZ) + (sizeof(int) + sizeof(short)) * NCELL +
-                                   sizeof(int) * 2 * S3_PT + sizeof(uint64_t) * S3_NRAW;
+    static constexpr size_t SMEM = sizeof(float) * (size_t)(S3_NRAW * RAWSZ + S3_NXF * XFSZ) + (sizeof(int) + sizeof(short)) * NCELL +
+                                   sizeof(int) * 2 * S3_PT + sizeof(uint64_t) * (S3_NRAW + S3_NXF);
     static_assert(RH <= 8 * (S3_NT / 32) && S3_TX + LBX - 1 <= S3_RWP && 8 * 3 + WINX <= S3_RWP, "tile geometry");
 };
 
@@ -237,12 +241,13 @@ stream3d_kernel(const __grid_constant__ S3Params P, const __grid_constant__ CUte
 
     extern __shared__ __align__(1024) float s3_smem[];
     float *raw = s3_smem;                       // N x RAWSZ
-    float *xf = raw + N * RAWSZ;                // 2 x XFSZ
-    int *cell_src = reinterpret_cast<int *>(xf + 2 * XFSZ);          // gather list: source offset inside a plane (-1: Fill)
+    float *xf = raw + N * RAWSZ;                // S3_NXF x XFSZ
+    int *cell_src = reinterpret_cast<int *>(xf + S3_NXF * XFSZ);          // gather list: source offset inside a plane (-1: Fill)
     unsigned short *cell_dst = reinterpret_cast<unsigned short *>(cell_src + C::NCELL);   // ... and raw-tile offset
     int *ptw = reinterpret_cast<int *>(cell_dst + C::NCELL);         // ring of plane sources: buffer (0 own, 1 lo, 2 hi, -1 Fill)
     int *ptz = ptw + S3_PT;                                           // ... and plane index inside it
-    uint64_t *full = reinterpret_cast<uint64_t *>(ptz + S3_PT);
+    uint64_t *full = reinterpret_cast<uint64_t *>(ptz + S3_PT);       // raw ring: TMA landed
+    uint64_t *xfull = full + N;                                       // xf ring: every warp is through stage x of the plane
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int Lx = LXT ? LXT : P.Lx, Ly = LYT ? LYT : P.Ly, Lz = LZT ? LZT : P.Lz;
@@ -281,8 +286,9 @@ stream3d_kernel(const __grid_constant__ S3Params P, const __grid_constant__ CUte
         cell_src[idx] = (sx < 0 || sy < 0) ? -1 : sy * P.W + sx;
         cell_dst[idx] = (unsigned short)(r * S3_RWP + c);
     }
-    if (tma && tid == 0) {
+    if (tid == 0) {
         for (int i = 0; i < N; ++i) s3_mbar_init(full + i, 1);
+        for (int i = 0; i < S3_NXF; ++i) s3_mbar_init(xfull + i, S3_NT / 32);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
 
@@ -353,28 +359,44 @@ stream3d_kernel(const __grid_constant__ S3Params P, const __grid_constant__ CUte
         for (int j = 0; j < LBZ; ++j) acc[o][j] = make_float2(0.f, 0.f);
 
     // Interval q: gather-patch plane q+2, stage x on plane q+1, stages y+z on plane q; TMA of plane q+2+AHEAD goes out.
+    // The only CTA-wide synchronisation is a SPLIT barrier per plane: a warp arrives on xfull[p % 3] when it is through
+    // stage x of plane p (and, in program order before that, the gather of plane p+1 and stages y/z of plane p-2), and
+    // waits for it one interval later, just before it needs plane p in stage y.  That one hand-off orders everything:
+    // xf[p % 3] is complete, xf[(p+1) % 3] (plane p-2) and raw[p % 8] (plane p) are free, the gather of p+1 has landed.
+    // Between arrive and wait lies a whole y/z stage, so warps drift apart by up to a plane instead of idling in lockstep.
+    // Stage x needs XW of the NW warps; even planes take warps 0.., odd planes warps NW-XW.., which evens the FMA load
+    // of the four schedulers over two planes.
+    constexpr int NW = S3_NT / 32, XW = (C::RH + 7) / 8, XOFF = NW > XW ? NW - XW : 0;
+    int wb = 0, wph = 0, ab = 0;                // xf slot / phase of plane q, xf slot of plane q + 1
     for (int q = -2; q < in_planes; ++q) {
-        if (((q + 2) & (S3_PTB - 1)) == 0) locate_block(q + S3_PTA, S3_PTB);   // visible after this interval's barrier
+        if (((q + 2) & (S3_PTB - 1)) == 0) locate_block(q + S3_PTA, S3_PTB);   // read >= S3_PTA - S3_AHEAD - 2 intervals later
+        if (q >= 0) s3_mbar_wait(xfull + wb, wph);
         if (tma && tid == 0 && q + 2 + S3_AHEAD < in_planes) issue(q + 2 + S3_AHEAD);
         if (fix && q + 2 < in_planes) {
             const int p = q + 2;
             if (tma) s3_mbar_wait(full + (p & (N - 1)), (p / N) & 1);
             fixup(p);
         }
-        if (q + 1 < in_planes) {
+        if (q + 1 < in_planes && q + 1 >= 0) {
             const int p = q + 1;
-            if (p >= 0) {
+            const int xw = (p & 1) ? warp - XOFF : warp;
+            if (xw >= 0) {
                 if (tma && !fix) s3_mbar_wait(full + (p & (N - 1)), (p / N) & 1);
-                s3_x_task<LXT, LYT, LZT>(P, raw + (p & (N - 1)) * RAWSZ, xf + (p & 1) * XFSZ, in_rows, Lx, warp, lane);
+                s3_x_task<LXT, LYT, LZT>(P, raw + (p & (N - 1)) * RAWSZ, xf + ab * XFSZ, in_rows, Lx, xw, lane);
             }
+            __syncwarp();
+            if (lane == 0) s3_mbar_arrive(xfull + ab);
+            ab = ab == S3_NXF - 1 ? 0 : ab + 1;
         }
-        if (q >= 0) {
+        if (q < 0) {
+            __syncthreads();                    // prologue: the gathers of planes 0 and 1 land before stage x reads them
+        } else {
             float2 m[S3_R];
-            s3_y_task<LXT, LYT, LZT>(P, xf + (q & 1) * XFSZ + yoff, m, Ly);
+            s3_y_task<LXT, LYT, LZT>(P, xf + wb * XFSZ + yoff, m, Ly);
             s3_z_update<LXT, LYT, LZT>(P, acc, m, Lz, op, P.W, nrow, smode, q >= Lz - 1 && nrow > 0);
+            if (wb == S3_NXF - 1) { wb = 0; wph ^= 1; } else ++wb;
         }
         op += P.plane;
-        __syncthreads();
     }
 }
 
