@@ -127,7 +127,7 @@ static int run_pass(const int64_t *dims, const StageInfo *sx, const StageInfo *s
     }
     if (sy) {
         P.Ly = (int)sy->s->len[yaxis]; P.kloy = (int)sy->lo[yaxis];
-        for (int d = 0; d < P.Ly; ++d) P.kyr[0][d] = (CT)sy->s->taps[P.Ly - 1 - d];
+        for (int j = 0; j < P.Ly; ++j) P.ky[0][j] = (CT)sy->s->taps[j];
     }
     P.vec_ok = (W % PX == 0) && (reinterpret_cast<uintptr_t>(dst) % 16 == 0);
     strip_geometry(P, nbatch);

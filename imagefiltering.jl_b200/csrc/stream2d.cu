@@ -57,7 +57,7 @@ static int run_typed(const Plan *plans, const void *d_img, int img_dt, void *con
         P.Ly = (int)sy.s->len[1]; P.kloy = (int)sy.lo[1];
         for (int j = 0; j < P.Lx; ++j) P.kx[p][j] = (CT)sx.s->taps[j];
         for (int j = 1; j < P.Lx; ++j) P.kxp[p][j] = make_float2((float)sx.s->taps[j], (float)sx.s->taps[j - 1]);
-        for (int d = 0; d < P.Ly; ++d) P.kyr[p][d] = (CT)sy.s->taps[P.Ly - 1 - d];
+        for (int j = 0; j < P.Ly; ++j) P.ky[p][j] = (CT)sy.s->taps[j];
     }
     P.vec_ok = aligned ? 1 : 0;
     const long long nbatch = P0.img_ax.len(2) * P0.img_ax.len(3);

@@ -10,10 +10,12 @@
 //     per-warp double-buffered shared-memory ring (this is where the border remap is applied);
 //   * stage 1 (along x): each lane produces PX adjacent outputs of a row from a register sliding
 //     window read with 128-bit conflict-free LDS;
-//   * stage 2 (along y): output-stationary accumulators in registers.  Row r adds mid[r]*ky[j] to the
-//     LY outputs whose window contains it, in ascending tap order, so the bits match the
-//     reference loop; the accumulator ring rotates at compile time (row loop unrolled by ROT), so
-//     there are no register moves and no shared-memory intermediate;
+//   * stage 2 (along y) runs in TRANSPOSED (systolic) form, in registers: acc[j] is the partial sum of the output
+//     that takes tap j next; a new x-filtered row `mid` completes the oldest output (tap Ly-1: emitted) and moves
+//     every other partial sum one slot up while it adds its tap, acc[j+1] = mid*ky[j] + acc[j].  Each output still
+//     receives its taps in ascending order, so the bits match the reference loop; the register indices are static
+//     without unrolling the row loop by the tap count (that version spread the hot loop over 59 KB of code and
+//     stalled on instruction fetch), no register moves, no shared-memory intermediate;
 //   * a finished output row leaves as one 128-bit store per lane and plane (512 B per warp).
 //
 // Tap counts: LXT/LYT > 0 are compile-time exact (hot sizes: no predicates at all); LXT = LYT = 0 means
@@ -50,7 +52,8 @@ struct S2Params {
     long long nstrips;        // nsx * nsy * batch
     int vec_ok;               // output rows are 16-byte aligned for every strip
     CT kx[NPL][S2_MAXTAPS];
-    CT kyr[NPL][S2_MAXTAPS];  // y taps reversed: kyr[d] = ky[Ly-1-d]
+    CT ky[NPL][S2_MAXTAPS];   // y taps, ascending (filled by the host set-up)
+    CT kyt[NPL][S2_MAXTAPS];  // the same taps RIGHT-aligned in the instantiation's LBY slots (filled by the launcher)
     float2 kxp[NPL][S2_MAXTAPS];  // Float32 compute only: kxp[j] = (kx[j], kx[j-1]), the taps one input carries to two adjacent outputs
 };
 
@@ -109,19 +112,18 @@ __device__ __forceinline__ int s2_remap(int style, int i, int n) {
     return s2_remap_slow(style, i, n);
 }
 
-// One input row of a strip: stage 1 from the smem ring, stage 2 into the register ring, emit the finished
-// output row.  `u` = rv % ROT; it is a literal after the caller's unrolling, so every acc[][slot][] index is static.
-// Only output rows 0 <= o < th are stored; everything else is computed and dropped.
+// One input row r of a strip (u = r % RB, a literal after the caller's unrolling): stage 1 from the smem ring, stage 2
+// through the register pipeline, emit the finished output row o = r - (Ly-1).  Only output rows 0 <= o < th are
+// stored; everything else is computed and dropped.
 template <typename CT, int LXT, int LYT, int LB, int NPL, int RB, int ROT, bool XS, bool YS>
-__device__ __forceinline__ void s2_row(const int u, const int rv, const S2Params<CT, NPL> &P, const int Lx, const int Ly,
+__device__ __forceinline__ void s2_row(const int u, const int r, const S2Params<CT, NPL> &P, const int Lx, const int Ly,
                                        const int th, const CT *__restrict__ sblk, const int lane,
                                        const int tw, const bool lane_full, const bool lane_live,
-                                       CT (&acc)[NPL][ROT][S2Vec<CT>::PX],
+                                       CT (&acc)[NPL][YS ? (LYT ? LYT : LB) : 1][S2Vec<CT>::PX],
                                        CT *(&outp)[NPL]) {
     constexpr int PX = S2Vec<CT>::PX;
     constexpr int LBX = XS ? (LXT ? LXT : LB) : 1;
     constexpr int LBY = YS ? (LYT ? LYT : LB) : 1;
-    static_assert(ROT >= LBY, "accumulator ring shorter than the y taps");
     constexpr int WIN = ((PX + LBX - 1 + PX - 1) / PX) * PX;
     constexpr int PW = 32 * PX + WIN;
     typedef typename S2Vec<CT>::T V;
@@ -182,38 +184,60 @@ __device__ __forceinline__ void s2_row(const int u, const int rv, const S2Params
 #pragma unroll
             for (int q = 0; q < PX; ++q) mid[p][q] = v[q];
     }
-    // stage 2: this row is tap Ly-1-d of the output held in slot (u+1+d) % ROT
+    // stage 2, transposed form (taps right-aligned in the LBY slots: a new output enters at slot LBY - Ly, whose
+    // accumulator is never written and stays zero)
+    CT fin[NPL][PX];
+    if constexpr (YS) {
 #pragma unroll
-    for (int d = 0; d < (YS ? LBY : 0); ++d) {
-        if (LYT || d < Ly) {
-            const int slot = (u + 1 + d) % ROT;
+        for (int p = 0; p < NPL; ++p) {
+            const CT kj = P.kyt[p][LBY - 1];
+            if constexpr (std::is_same<CT, float>::value) {
 #pragma unroll
-            for (int p = 0; p < NPL; ++p) {
-                const CT kj = P.kyr[p][d];
-                if constexpr (std::is_same<CT, float>::value) {
+                for (int q = 0; q < PX; q += 2) {
+                    const float2 t = s2_fma2(make_float2(mid[p][q], mid[p][q + 1]), kj,
+                                             make_float2(acc[p][LBY - 1][q], acc[p][LBY - 1][q + 1]));
+                    fin[p][q] = t.x; fin[p][q + 1] = t.y;
+                }
+            } else {
 #pragma unroll
-                    for (int q = 0; q < PX; q += 2) {
-                        const float2 r = s2_fma2(make_float2(mid[p][q], mid[p][q + 1]), kj,
-                                                 make_float2(acc[p][slot][q], acc[p][slot][q + 1]));
-                        acc[p][slot][q] = r.x; acc[p][slot][q + 1] = r.y;
+                for (int q = 0; q < PX; ++q) fin[p][q] = mac<CT>(acc[p][LBY - 1][q], mid[p][q], kj);
+            }
+        }
+#pragma unroll
+        for (int j = LBY - 2; j >= 0; --j) {
+            if (LYT || j >= LBY - Ly) {
+#pragma unroll
+                for (int p = 0; p < NPL; ++p) {
+                    const CT kj = P.kyt[p][j];
+                    if constexpr (std::is_same<CT, float>::value) {
+#pragma unroll
+                        for (int q = 0; q < PX; q += 2) {
+                            const float2 t = s2_fma2(make_float2(mid[p][q], mid[p][q + 1]), kj,
+                                                     make_float2(acc[p][j][q], acc[p][j][q + 1]));
+                            acc[p][j + 1][q] = t.x; acc[p][j + 1][q + 1] = t.y;
+                        }
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < PX; ++q) acc[p][j + 1][q] = mac<CT>(acc[p][j][q], mid[p][q], kj);
                     }
-                } else {
-#pragma unroll
-                    for (int q = 0; q < PX; ++q) acc[p][slot][q] = mac<CT>(acc[p][slot][q], mid[p][q], kj);
                 }
             }
         }
+    } else {
+#pragma unroll
+        for (int p = 0; p < NPL; ++p)
+#pragma unroll
+            for (int q = 0; q < PX; ++q) fin[p][q] = mid[p][q];
     }
-    // output row o = rv-(ROT-1) is complete: emit it and recycle its slot
-    const int eslot = (u + 1) % ROT;
-    const int o = rv - (ROT - 1);
+    // output row o = r-(Ly-1) is complete: emit it
+    const int o = r - (Ly - 1);
     if (o >= 0 && o < th) {
         if (lane_full) {
 #pragma unroll
             for (int p = 0; p < NPL; ++p) {
                 V t;
 #pragma unroll
-                for (int q = 0; q < PX; ++q) ((CT *)&t)[q] = YS ? acc[p][eslot][q] : mid[p][q];
+                for (int q = 0; q < PX; ++q) ((CT *)&t)[q] = fin[p][q];
                 *reinterpret_cast<V *>(outp[p]) = t;
             }
         } else if (lane_live) {
@@ -221,15 +245,11 @@ __device__ __forceinline__ void s2_row(const int u, const int rv, const S2Params
             for (int p = 0; p < NPL; ++p)
 #pragma unroll
                 for (int q = 0; q < PX; ++q)
-                    if (lane * PX + q < tw) outp[p][q] = YS ? acc[p][eslot][q] : mid[p][q];
+                    if (lane * PX + q < tw) outp[p][q] = fin[p][q];
         }
 #pragma unroll
         for (int p = 0; p < NPL; ++p) outp[p] += P.out_pitch;
     }
-#pragma unroll
-    for (int p = 0; p < NPL; ++p)
-#pragma unroll
-        for (int q = 0; q < PX; ++q) acc[p][eslot][q] = (CT)0;
 }
 
 template <typename IT, typename CT, int LXT, int LYT, int LB, int NPL, int RB, int ROT, bool XS = true, bool YS = true>
@@ -238,8 +258,6 @@ __global__ void __launch_bounds__(S2_WARPS * 32) stream2d_kernel(const S2Params<
     constexpr int CW = 32 * PX;                              // strip width
     constexpr int LBX = XS ? (LXT ? LXT : LB) : 1;           // compile-time bound of the x taps (1: no x stage)
     constexpr int LBY = YS ? (LYT ? LYT : LB) : 1;
-    static_assert(YS || ROT == 1, "no y stage: the ring is a single pass-through slot");
-    constexpr int G = (ROT / s2_gcd(ROT, RB)) * RB;         // rows per unrolled group: lcm(ring size, prefetch block)
     constexpr int NCL = (CW + LBX - 1 + 31) / 32;            // loads per lane per input row
     constexpr int WIN = ((PX + LBX - 1 + PX - 1) / PX) * PX; // window registers (whole 128-bit granules)
     constexpr int PW = CW + WIN;                             // smem row pitch (elements), multiple of PX
@@ -286,20 +304,13 @@ __global__ void __launch_bounds__(S2_WARPS * 32) stream2d_kernel(const S2Params<
     const int ytop = y0 + (YS ? P.kloy : 0);              // buffer row of strip-local input row 0
     const bool y_interior = ytop >= 0 && ytop + in_rows <= P.H;
 
-    // Virtual row index rv = r + s0 with s0 = ROT - Ly: output row o = r-(Ly-1) = rv-(ROT-1) always sits in
-    // accumulator slot (rv+1) % ROT and row r feeds slot (rv+1+d) % ROT with tap ky[Ly-1-d] (= P.kyr[d]):
-    // every register index is a compile-time constant once the row loop is unrolled by ROT.
-    const int s0 = ROT - Ly;
-    const int vrows = in_rows + s0;
-
     IT stage[RB][NCL];
     unsigned rowfill = 0;       // bit rr: staged row rr lies in the Fill region
     auto fetch_block = [&](int blk) {
         rowfill = 0;
 #pragma unroll
         for (int rr = 0; rr < RB; ++rr) {
-            int r = blk * RB + rr - s0;
-            r = min(max(r, 0), in_rows - 1);              // rows outside the strip are never used: clamp the address
+            const int r = min(blk * RB + rr, in_rows - 1);   // rows past the strip are never used: clamp the address
             int gy = ytop + r;
             if (!y_interior && (unsigned)gy >= (unsigned)P.H) {
                 // outside this buffer: apply the border in GLOBAL row coordinates (slab form; y_first = 0, Hg = H otherwise)
@@ -324,11 +335,11 @@ __global__ void __launch_bounds__(S2_WARPS * 32) stream2d_kernel(const S2Params<
         }
     };
 
-    CT acc[NPL][ROT][PX];
+    CT acc[NPL][LBY][PX];       // acc[.][0] stays zero: the entry slot of a new output
 #pragma unroll
     for (int p = 0; p < NPL; ++p)
 #pragma unroll
-        for (int s = 0; s < ROT; ++s)
+        for (int s = 0; s < LBY; ++s)
 #pragma unroll
             for (int q = 0; q < PX; ++q) acc[p][s][q] = (CT)0;
 
@@ -345,22 +356,16 @@ __global__ void __launch_bounds__(S2_WARPS * 32) stream2d_kernel(const S2Params<
     park_block(0);
     __syncwarp();
 
-    // ---- main loop: groups of ROT rows (= ROT/RB prefetch blocks); the steady state runs without per-row checks ----
-    // Every group of G rows runs the same unchecked code: rows before the strip / past its end are clamped
-    // duplicates whose contributions only reach output rows that are never stored (o < 0 or o >= th).
-    for (int rbase = 0; rbase < vrows; rbase += G) {
-        const int blk0 = rbase / RB;
+    // ---- main loop: one prefetch block of RB rows per iteration, no per-row checks: rows past the end of the strip are
+    // clamped duplicates whose contributions only reach output rows that are never stored (o >= th)
+    for (int rbase = 0, blk = 0; rbase < in_rows; rbase += RB, ++blk) {
+        fetch_block(blk + 1);                                     // loads fly while this block is computed
 #pragma unroll
-        for (int u = 0; u < G; ++u) {
-            const int blk = blk0 + u / RB;
-            if (u % RB == 0) fetch_block(blk + 1);                // loads fly while this block is computed
+        for (int u = 0; u < RB; ++u)
             s2_row<CT, LXT, LYT, LB, NPL, RB, ROT, XS, YS>(u, rbase + u, P, Lx, Ly, th, sbuf + (blk & 1) * (RB * PW), lane, tw, lane_full,
-                                           lane_live, acc, outp);
-            if (u % RB == RB - 1) {
-                park_block(blk + 1);
-                __syncwarp();
-            }
-        }
+                                                           lane_live, acc, outp);
+        park_block(blk + 1);
+        __syncwarp();
     }
 }
 

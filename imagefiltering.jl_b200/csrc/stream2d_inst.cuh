@@ -12,10 +12,19 @@ static int s2_launch_one(const S2Params<CT, NPL> &P, cudaStream_t st) {
     constexpr int LBX = XS ? (LXT ? LXT : LB) : 1;
     constexpr int WIN = ((PX + LBX - 1 + PX - 1) / PX) * PX;
     constexpr int PW = 32 * PX + WIN;
+    constexpr int LBY = YS ? (LYT ? LYT : LB) : 1;
     const size_t smem = (size_t)S2_WARPS * 2 * RB * PW * sizeof(CT);
+    S2Params<CT, NPL> Q = P;                       // right-align the y taps in this instantiation's LBY slots
+    if (YS) {
+        if (P.Ly > LBY) return fail(B2F_ENOTSUP, "stream2d: more y taps than the instantiation holds");
+        for (int p = 0; p < NPL; ++p) {
+            for (int j = 0; j < S2_MAXTAPS; ++j) Q.kyt[p][j] = (CT)0;
+            for (int j = 0; j < P.Ly; ++j) Q.kyt[p][LBY - P.Ly + j] = P.ky[p][j];
+        }
+    }
     const long long blocks = (P.nstrips + S2_WARPS - 1) / S2_WARPS;
     if (blocks > 0x7fffffffLL) return fail(B2F_ENOTSUP, "stream2d grid too large");
-    stream2d_kernel<IT, CT, LXT, LYT, LB, NPL, RB, ROT, XS, YS><<<(unsigned)blocks, S2_WARPS * 32, smem, st>>>(P);
+    stream2d_kernel<IT, CT, LXT, LYT, LB, NPL, RB, ROT, XS, YS><<<(unsigned)blocks, S2_WARPS * 32, smem, st>>>(Q);
     count_launch();
     B2F_CUDA(cudaGetLastError());
     return 0;
