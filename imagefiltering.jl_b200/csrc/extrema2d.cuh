@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(S2_WARPS * 32) extrema2d_kernel(const E2Params
     constexpr int PW = CW + WIN;
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // shuffle: provably warp-uniform
     float *sbuf = reinterpret_cast<float *>(smem_raw) + (size_t)warp * (2 * RB * PW);
 
     const long long sid = (long long)blockIdx.x * S2_WARPS + warp;

@@ -253,7 +253,7 @@ __device__ __forceinline__ void s2_row(const int u, const int r, const S2Params<
 }
 
 template <typename IT, typename CT, int LXT, int LYT, int LB, int NPL, int RB, int ROT, bool XS = true, bool YS = true>
-__global__ void __launch_bounds__(S2_WARPS * 32) stream2d_kernel(const S2Params<CT, NPL> P) {
+__global__ void __launch_bounds__(S2_WARPS * 32) stream2d_kernel(const __grid_constant__ S2Params<CT, NPL> P) {
     constexpr int PX = S2Vec<CT>::PX;
     constexpr int CW = 32 * PX;                              // strip width
     constexpr int LBX = XS ? (LXT ? LXT : LB) : 1;           // compile-time bound of the x taps (1: no x stage)
@@ -265,7 +265,9 @@ __global__ void __launch_bounds__(S2_WARPS * 32) stream2d_kernel(const S2Params<
     static_assert(LBX <= S2_MAXTAPS && LBY <= S2_MAXTAPS, "too many taps");
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // the warp index through a shuffle: the compiler then knows it is warp-uniform, keeps the strip geometry and the taps
+    // in uniform registers and frees ~40 vector registers
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
     CT *sbuf = reinterpret_cast<CT *>(smem_raw) + (size_t)warp * (2 * RB * PW);
 
     const long long sid = (long long)blockIdx.x * S2_WARPS + warp;
