@@ -1,4 +1,5 @@
 // stream3d.cu — applicability, parameter set-up and launch of the fused 3-D separable kernel (stream3d.cuh)
+#include <algorithm>
 #include <cstdlib>
 
 #include "stream3d.cuh"
@@ -56,7 +57,7 @@ static bool s3_make_map(CUtensorMap *m, const void *base, int W, int H, long lon
 }
 
 template <int LXT, int LYT, int LZT>
-static int s3_launch_one(S3Params &P, const float *kz, long long nch, cudaStream_t st) {
+static int s3_launch_one(S3Params &P, const float *kz, cudaStream_t st) {
     long long nblocks;
     typedef S3C<LXT, LYT, LZT> C;
     const size_t smem = C::SMEM;
@@ -80,8 +81,13 @@ static int s3_launch_one(S3Params &P, const float *kz, long long nch, cudaStream
     // "illegal instruction" otherwise), so the tile grid is shifted left by xsh = klox mod 4 columns
     P.xsh = tma ? ((P.klox % 4) + 4) % 4 : 0;
     if (P.xsh & 1) P.vec_out = 0;
+    const int ntx0 = P.ntx;
     P.ntx = (P.W + P.xsh + S3_TX - 1) / S3_TX;
-    nblocks = (long long)P.ntx * P.nty * nch;
+    if (P.ntx != ntx0) {                              // the shift added a tile column: keep the split, as whole tile rows
+        const long long tiles = (long long)P.ntx * P.nty;
+        P.nfull = (int)std::min<long long>(tiles, (long long)P.nfull / ntx0 * P.ntx);
+    }
+    nblocks = P.nfull + ((long long)P.ntx * P.nty - P.nfull) * P.kch;
     kern<<<(unsigned)nblocks, S3_NT, smem, st>>>(P, m_own, m_lo, m_hi);
     count_launch();
     B2F_CUDA(cudaGetLastError());
@@ -114,26 +120,35 @@ int run_stream3d_slab(const Plan &Pl, const void *own, const void *lo, int64_t l
     P.vec_out = (P.W % 2 == 0) && reinterpret_cast<uintptr_t>(d_out) % 8 == 0;
     P.ntx = (P.W + S3_TX - 1) / S3_TX;
     P.nty = (P.H + S3_TY - 1) / S3_TY;
-    // z-chunks: every chunk re-runs Lz-1 planes of stages x and y, so take the split that minimises
-    // waves(tiles * nch) * (planes per chunk + Lz - 1) on the 148 SMs (1 CTA per SM)
+    // z-chunks.  One CTA per SM at a time, CTAs dispatched in blockIdx order.  A chunk re-runs Lz-1 planes of stages x and
+    // y, so long marches are cheapest, but whole waves of them quantise badly (512 tiles on 148 SMs: the 4th wave is
+    // 46% full).  So: the first `nfull` tiles (whole waves) march all planes, the remaining tiles are cut into `kch`
+    // chunks each, which fills the last wave evenly.  (nfull, kch) minimise the makespan of that list schedule.
     const long long tiles = (long long)P.ntx * P.nty;
-    long long best = 1;
-    double best_cost = 0;
-    for (long long nch = 1; nch <= 64 && nch <= own_n; ++nch) {
-        const long long zc = (own_n + nch - 1) / nch;
-        if (nch > 1 && zc < 16) break;
-        const long long waves = (tiles * ((own_n + zc - 1) / zc) + 147) / 148;
-        const double cost = (double)waves * (double)(zc + P.Lz - 1 + 3);
-        if (nch == 1 || cost < best_cost * 0.97) { best = nch; best_cost = cost; }
+    const int ov = P.Lz - 1 + 3, SMS = 148;
+    // closed form: w whole waves of full marches, then ceil(rest * k / SMS) waves of chunks
+    long long best_full = tiles, best_k = 1, best_cost = ((tiles + SMS - 1) / SMS) * (own_n + ov);
+    for (long long w = 0; w * SMS <= tiles; ++w) {
+        const long long rest = tiles - w * SMS;
+        if (rest == 0) break;
+        for (long long k = 1; k <= 16 && k <= own_n; ++k) {
+            const long long zc = (own_n + k - 1) / k;
+            if (k > 1 && zc < 8) break;
+            const long long c = w * (own_n + ov) + ((rest * k + SMS - 1) / SMS) * (zc + ov);
+            if (c < best_cost) { best_cost = c; best_full = w * SMS; best_k = k; }
+        }
     }
-    P.zchunk = (int)((own_n + best - 1) / best);
-    const long long nch = (own_n + P.zchunk - 1) / P.zchunk;
-    if ((tiles + P.nty) * nch > 0x7fffffffLL) return fail(B2F_ENOTSUP, "stream3d grid too large");
-    if (P.Lx == 17 && P.Ly == 17 && P.Lz == 17) return s3_launch_one<17, 17, 17>(P, kz, nch, st);
-    if (P.Lx == 9 && P.Ly == 9 && P.Lz == 9) return s3_launch_one<9, 9, 9>(P, kz, nch, st);
-    if (P.Lx == 5 && P.Ly == 5 && P.Lz == 5) return s3_launch_one<5, 5, 5>(P, kz, nch, st);
-    if (P.Lx == 3 && P.Ly == 3 && P.Lz == 3) return s3_launch_one<3, 3, 3>(P, kz, nch, st);
-    return s3_launch_one<0, 0, 0>(P, kz, nch, st);
+    P.nfull = (int)best_full;
+    P.kch = (int)best_k;
+    P.zchunk = (int)((own_n + best_k - 1) / best_k);
+    const long long nch = 0;
+    (void)nch;
+    if (best_full + (tiles - best_full) * best_k + (long long)P.nty * best_k > 0x7fffffffLL) return fail(B2F_ENOTSUP, "stream3d grid too large");
+    if (P.Lx == 17 && P.Ly == 17 && P.Lz == 17) return s3_launch_one<17, 17, 17>(P, kz, st);
+    if (P.Lx == 9 && P.Ly == 9 && P.Lz == 9) return s3_launch_one<9, 9, 9>(P, kz, st);
+    if (P.Lx == 5 && P.Ly == 5 && P.Lz == 5) return s3_launch_one<5, 5, 5>(P, kz, st);
+    if (P.Lx == 3 && P.Ly == 3 && P.Lz == 3) return s3_launch_one<3, 3, 3>(P, kz, st);
+    return s3_launch_one<0, 0, 0>(P, kz, st);
 }
 
 int run_stream3d(const Plan &P, const void *d_img, void *d_out, cudaStream_t st) {

@@ -58,6 +58,7 @@ struct S3Params {
     float fill;
     int Lx, Ly, Lz, klox, kloy, kloz;
     int zchunk, ntx, nty;          // output planes per z-chunk, tiles along x / y
+    int nfull, kch;                // the first nfull tiles march all planes in one CTA, the others are cut into kch chunks
     int vec_out;                   // 8-byte stores are aligned
     int xsh;                       // tiles start at x = 32*tx - xsh, so that the TMA box starts on a 16-byte boundary
     int use_tma;                   // the tensor maps are valid (else every cell comes through the gather loader)
@@ -252,11 +253,19 @@ stream3d_kernel(const __grid_constant__ S3Params P, const __grid_constant__ CUte
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int Lx = LXT ? LXT : P.Lx, Ly = LYT ? LYT : P.Ly, Lz = LZT ? LZT : P.Lz;
     const int bid = blockIdx.x;
-    const int tx = bid % P.ntx, ty = (bid / P.ntx) % P.nty, ch = bid / (P.ntx * P.nty);
+    int tile = bid, ch = 0, zc = P.own_n;
+    if (bid >= P.nfull) {
+        const int b2 = bid - P.nfull;
+        tile = P.nfull + b2 / P.kch;
+        ch = b2 - (tile - P.nfull) * P.kch;
+        zc = P.zchunk;
+    }
+    const int tx = tile % P.ntx, ty = tile / P.ntx;
     const int x0 = tx * TX - P.xsh, y0 = ty * TY;
     const int in_cols = TX + Lx - 1, in_rows = TY + Ly - 1;
-    const int zo0 = P.own_first + ch * P.zchunk;                         // first output plane of this chunk (global)
-    const int nout = min(P.zchunk, P.own_first + P.own_n - zo0);
+    const int zo0 = P.own_first + ch * zc;                               // first output plane of this chunk (global)
+    const int nout = min(zc, P.own_first + P.own_n - zo0);
+    if (nout <= 0) return;
     const int in_planes = nout + Lz - 1;
     const int zin0 = zo0 + P.kloz;                                       // global index of input plane p = 0
     const int xa = x0 + P.klox, ya = y0 + P.kloy;
