@@ -277,7 +277,7 @@ def ours_arm(args):
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get("fused2d_grad_bench_bytes_per_launch")
+                traffic = json.load(open(tp)).get("stream2d_grad_bench_bytes_per_launch")
             except Exception:
                 traffic = None
         cpu = None
