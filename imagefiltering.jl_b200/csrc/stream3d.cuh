@@ -98,26 +98,48 @@ __device__ __forceinline__ void s3_locate(const S3Params &P, int zi, int &which,
 }
 
 // ---- mbarrier / TMA primitives (sm_90+ PTX) ----------------------------------------------------------------------------
-__device__ __forceinline__ unsigned s3_sa(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void s3_mbar_init(uint64_t *b, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s3_sa(b)), "r"(count) : "memory");
+__device__ __forceinline__ unsigned s3_sa(const void *p) {
+    // through an opaque move: the compiler otherwise REMATERIALISES the address (S2R CgaCtaId + LEA) at every use
+    unsigned a;
+    asm volatile("mov.u32 %0, %1;" : "=r"(a) : "r"((unsigned)__cvta_generic_to_shared(p)));
+    return a;
 }
-__device__ __forceinline__ void s3_mbar_arrive(uint64_t *b) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s3_sa(b)) : "memory");
+// All of these take 32-bit shared-window addresses computed ONCE per CTA (s3_sa): converting a generic pointer costs an
+// S2R of the CTA-in-cluster id every time, seven special-register reads per plane in the first version of the loop.
+__device__ __forceinline__ void s3_mbar_init(unsigned b, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(b), "r"(count) : "memory");
 }
-__device__ __forceinline__ void s3_mbar_expect_tx(uint64_t *b, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s3_sa(b)), "r"(bytes) : "memory");
+__device__ __forceinline__ void s3_mbar_arrive(unsigned b) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(b) : "memory");
 }
-__device__ __forceinline__ void s3_mbar_wait(uint64_t *b, unsigned parity) {
+__device__ __forceinline__ void s3_mbar_expect_tx(unsigned b, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void s3_mbar_wait(unsigned b, unsigned parity) {
     unsigned ok;
     do {
         asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
-                     : "=r"(ok) : "r"(s3_sa(b)), "r"(parity) : "memory");
+                     : "=r"(ok) : "r"(b), "r"(parity) : "memory");
     } while (!ok);
 }
-__device__ __forceinline__ void s3_tma_load3d(float *dst, const void *tmap, uint64_t *bar, int c0, int c1, int c2) {
+__device__ __forceinline__ void s3_tma_load3d(unsigned dst, const void *tmap, unsigned bar, int c0, int c1, int c2) {
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-                 ::"r"(s3_sa(dst)), "l"(tmap), "r"(s3_sa(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+                 ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
+// shared-memory accesses of the hot stages by 32-bit shared address (same reason as above: no generic-pointer conversions)
+__device__ __forceinline__ float4 s3_lds128(unsigned a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ float2 s3_lds64(unsigned a) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void s3_sts128(unsigned a, float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
 // compile-time geometry
@@ -136,17 +158,17 @@ template <int LXT, int LYT, int LZT> struct S3C {
 
 // ---- stage x: one row group of 8 outputs per thread.  A quarter-warp covers two rows x 32 columns ----------------------
 template <int LXT, int LYT, int LZT>
-__device__ __forceinline__ void s3_x_task(const S3Params &P, const float *__restrict__ rb, float *__restrict__ xb,
+__device__ __forceinline__ void s3_x_task(const S3Params &P, const unsigned rb, const unsigned xb,
                                           const int in_rows, const int Lx, const int warp, const int lane) {
     typedef S3C<LXT, LYT, LZT> C;
     const int l8 = lane & 7, qw = lane >> 3;
     const int xg = l8 & 3, row = 8 * warp + 2 * qw + (l8 >> 2);
     if (row >= in_rows) return;
-    const float *src = rb + row * S3_RWP + 8 * xg;
+    const unsigned src = rb + (unsigned)(row * S3_RWP + 8 * xg) * 4u;
     float v[C::WINX];
 #pragma unroll
     for (int i = 0; i < C::WINX; i += 4) {
-        const float4 t = *reinterpret_cast<const float4 *>(src + i);
+        const float4 t = s3_lds128(src + i * 4);
         v[i] = t.x; v[i + 1] = t.y; v[i + 2] = t.z; v[i + 3] = t.w;
     }
     // input-major: window value v[i] feeds outputs (2c, 2c+1) with the tap pair (k[j], k[j-1]), j = i - 2c (one FFMA2
@@ -167,21 +189,21 @@ __device__ __forceinline__ void s3_x_task(const S3Params &P, const float *__rest
             }
         }
     }
-    float *d = xb + row * S3_XFP + 8 * xg;
-    *reinterpret_cast<float4 *>(d) = make_float4(a[0].x, a[0].y, a[1].x, a[1].y);
-    *reinterpret_cast<float4 *>(d + 4) = make_float4(a[2].x, a[2].y, a[3].x, a[3].y);
+    const unsigned d = xb + (unsigned)(row * S3_XFP + 8 * xg) * 4u;
+    s3_sts128(d, make_float4(a[0].x, a[0].y, a[1].x, a[1].y));
+    s3_sts128(d + 16, make_float4(a[2].x, a[2].y, a[3].x, a[3].y));
 }
 
 // ---- stage y: 2 columns x S3_R rows per thread; a half-warp covers the 32 columns of one row group -----------------------
 template <int LXT, int LYT, int LZT>
-__device__ __forceinline__ void s3_y_task(const S3Params &P, const float *__restrict__ xb, float2 (&m)[S3_R], const int Ly) {
+__device__ __forceinline__ void s3_y_task(const S3Params &P, const unsigned xb, float2 (&m)[S3_R], const int Ly) {
     typedef S3C<LXT, LYT, LZT> C;
 #pragma unroll
     for (int o = 0; o < S3_R; ++o) m[o] = make_float2(0.f, 0.f);
 #pragma unroll
     for (int i = 0; i < S3_R + C::LBY - 1; ++i) {
         if (LYT || i < S3_R + Ly - 1) {
-            const float2 s = *reinterpret_cast<const float2 *>(xb + i * S3_XFP);
+            const float2 s = s3_lds64(xb + i * (S3_XFP * 4));
 #pragma unroll
             for (int o = 0; o < S3_R; ++o) {
                 const int j = i - o;
@@ -247,8 +269,9 @@ stream3d_kernel(const __grid_constant__ S3Params P, const __grid_constant__ CUte
     unsigned short *cell_dst = reinterpret_cast<unsigned short *>(cell_src + C::NCELL);   // ... and raw-tile offset
     int *ptw = reinterpret_cast<int *>(cell_dst + C::NCELL);         // ring of plane sources: buffer (0 own, 1 lo, 2 hi, -1 Fill)
     int *ptz = ptw + S3_PT;                                           // ... and plane index inside it
-    uint64_t *full = reinterpret_cast<uint64_t *>(ptz + S3_PT);       // raw ring: TMA landed
-    uint64_t *xfull = full + N;                                       // xf ring: every warp is through stage x of the plane
+    // barriers, as 32-bit shared addresses: full + 8 b = TMA of raw buffer b landed; xfull + 8 s = every warp is through
+    // stage x of the plane in xf slot s
+    const unsigned full = s3_sa(ptz + S3_PT), xfull = full + 8 * N, raw_sa = s3_sa(raw), xf_sa = s3_sa(xf);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int Lx = LXT ? LXT : P.Lx, Ly = LYT ? LYT : P.Ly, Lz = LZT ? LZT : P.Lz;
@@ -296,8 +319,8 @@ stream3d_kernel(const __grid_constant__ S3Params P, const __grid_constant__ CUte
         cell_dst[idx] = (unsigned short)(r * S3_RWP + c);
     }
     if (tid == 0) {
-        for (int i = 0; i < N; ++i) s3_mbar_init(full + i, 1);
-        for (int i = 0; i < S3_NXF; ++i) s3_mbar_init(xfull + i, S3_NT / 32);
+        for (int i = 0; i < N; ++i) s3_mbar_init(full + 8 * i, 1);
+        for (int i = 0; i < S3_NXF; ++i) s3_mbar_init(xfull + 8 * i, S3_NT / 32);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
 
@@ -320,8 +343,8 @@ stream3d_kernel(const __grid_constant__ S3Params P, const __grid_constant__ CUte
         const int zc = which < 0 ? P.own_n : ptz[p & (S3_PT - 1)];         // Fill(0) plane: out of range reads zero
         const void *map = which == 1 ? (const void *)&m_lo : which == 2 ? (const void *)&m_hi : (const void *)&m_own;
         const int b = p & (N - 1);
-        s3_mbar_expect_tx(full + b, (unsigned)C::RAWBYTES);
-        s3_tma_load3d(raw + b * RAWSZ, map, full + b, xa, ya, zc);
+        s3_mbar_expect_tx(full + 8 * b, (unsigned)C::RAWBYTES);
+        s3_tma_load3d(raw_sa + b * (RAWSZ * 4), map, full + 8 * b, xa, ya, zc);
     };
     auto fixup = [&](int p) {                   // all threads: the gather list of input plane p
         const int which = ptw[p & (S3_PT - 1)];
@@ -379,29 +402,29 @@ stream3d_kernel(const __grid_constant__ S3Params P, const __grid_constant__ CUte
     int wb = 0, wph = 0, ab = 0;                // xf slot / phase of plane q, xf slot of plane q + 1
     for (int q = -2; q < in_planes; ++q) {
         if (((q + 2) & (S3_PTB - 1)) == 0) locate_block(q + S3_PTA, S3_PTB);   // read >= S3_PTA - S3_AHEAD - 2 intervals later
-        if (q >= 0) s3_mbar_wait(xfull + wb, wph);
+        if (q >= 0) s3_mbar_wait(xfull + 8 * wb, wph);
         if (tma && tid == 0 && q + 2 + S3_AHEAD < in_planes) issue(q + 2 + S3_AHEAD);
         if (fix && q + 2 < in_planes) {
             const int p = q + 2;
-            if (tma) s3_mbar_wait(full + (p & (N - 1)), (p / N) & 1);
+            if (tma) s3_mbar_wait(full + 8 * (p & (N - 1)), (p / N) & 1);
             fixup(p);
         }
         if (q + 1 < in_planes && q + 1 >= 0) {
             const int p = q + 1;
             const int xw = (p & 1) ? warp - XOFF : warp;
             if (xw >= 0) {
-                if (tma && !fix) s3_mbar_wait(full + (p & (N - 1)), (p / N) & 1);
-                s3_x_task<LXT, LYT, LZT>(P, raw + (p & (N - 1)) * RAWSZ, xf + ab * XFSZ, in_rows, Lx, xw, lane);
+                if (tma && !fix) s3_mbar_wait(full + 8 * (p & (N - 1)), (p / N) & 1);
+                s3_x_task<LXT, LYT, LZT>(P, raw_sa + (p & (N - 1)) * (RAWSZ * 4), xf_sa + ab * (XFSZ * 4), in_rows, Lx, xw, lane);
             }
             __syncwarp();
-            if (lane == 0) s3_mbar_arrive(xfull + ab);
+            if (lane == 0) s3_mbar_arrive(xfull + 8 * ab);
             ab = ab == S3_NXF - 1 ? 0 : ab + 1;
         }
         if (q < 0) {
             __syncthreads();                    // prologue: the gathers of planes 0 and 1 land before stage x reads them
         } else {
             float2 m[S3_R];
-            s3_y_task<LXT, LYT, LZT>(P, xf + wb * XFSZ + yoff, m, Ly);
+            s3_y_task<LXT, LYT, LZT>(P, xf_sa + (wb * XFSZ + yoff) * 4, m, Ly);
             s3_z_update<LXT, LYT, LZT>(P, acc, m, Lz, op, P.W, nrow, smode, q >= Lz - 1 && nrow > 0);
             if (wb == S3_NXF - 1) { wb = 0; wph ^= 1; } else ++wb;
         }
