@@ -14,6 +14,7 @@ from .border import Fill, Inner, NA, NoPad, Pad, borderinstance
 from .device import DeviceArray
 from .imfilter import factorkernel, filter_type, imfilter, imfilter_, imgradients, padarray
 from .kernel import reflect
+from .localextrema import BlobLoG, blob_LoG, findlocalmaxima, findlocalminima
 from .kernelfactors import ReshapedOneD, kernelfactors
 from .mapwindow import extrema, mapwindow, mapwindow_, maximum, minimum
 from .n0f8 import N0f8Array, n0f8
@@ -25,5 +26,5 @@ __all__ = [
     "imfilter_", "imgradients", "padarray", "mapwindow", "mapwindow_", "extrema", "minimum", "maximum", "centered",
     "OffsetArray", "reflect", "kernelfactors", "ReshapedOneD", "Algorithm", "CUDALibs", "CPU1",
     "CPUThreads", "DeviceArray", "n0f8", "N0f8Array", "filter_type", "factorkernel",
-    "DimensionMismatch", "ArgumentError", "InexactError", "NotSupportedError", "CudaError",
+    "findlocalmaxima", "findlocalminima", "blob_LoG", "BlobLoG", "DimensionMismatch", "ArgumentError", "InexactError", "NotSupportedError", "CudaError",
 ]

@@ -36,6 +36,7 @@ SYMBOLS = [
     "b2f_version", "b2f_last_error", "b2f_is_device_library", "b2f_set_device", "b2f_device_count",
     "b2f_malloc", "b2f_free", "b2f_host_alloc", "b2f_host_free", "b2f_memcpy_h2d", "b2f_memcpy_d2h",
     "b2f_sync", "b2f_ipc_export", "b2f_ipc_open", "b2f_ipc_close", "b2f_imfilter", "b2f_imgradients", "b2f_mapwindow_extrema", "b2f_imfilter_slab",
+    "b2f_findlocalextrema", "b2f_scale_into_slice", "b2f_maxabs", "b2f_gather",
     "b2f_launch_count", "b2f_reset_launch_count", "b2f_last_path",
 ]
 
@@ -183,6 +184,13 @@ class Library:
             C.POINTER(b2f_array), C.POINTER(b2f_array), C.POINTER(b2f_stage), C.c_int32,
             C.POINTER(b2f_border), C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]
 
+        d.b2f_findlocalextrema.argtypes = [
+            C.POINTER(b2f_array), C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.c_int64,
+            C.POINTER(C.c_int64), C.c_void_p]
+        d.b2f_scale_into_slice.argtypes = [C.POINTER(b2f_array), C.POINTER(b2f_array), C.c_int64, C.c_double, C.c_void_p]
+        d.b2f_maxabs.argtypes = [C.POINTER(b2f_array), C.POINTER(C.c_double), C.c_void_p]
+        d.b2f_gather.argtypes = [C.POINTER(b2f_array), C.POINTER(C.c_int64), C.c_int64, C.POINTER(C.c_double), C.c_void_p]
+
     # -- helpers ---------------------------------------------------------------------------
     def check(self, rc: int):
         if rc == OK:
@@ -255,3 +263,47 @@ class Library:
                                               C.byref(border), global_last_dim, slab_first,
                                               C.c_void_p(halo_lo or None), n_halo_lo,
                                               C.c_void_p(halo_hi or None), n_halo_hi, C.c_void_p(stream)))
+
+    # -- local extrema / blob_LoG plumbing -----------------------------------------------------
+    def findlocalextrema(self, img: b2f_array, minima: bool, window, edges, stream: int = 0) -> np.ndarray:
+        """-> 0-based column-major linear indices of the peaks, ascending (int64)."""
+        nd = img.ndim
+        win = (C.c_int64 * MAXDIM)(*list(window) + [1] * (MAXDIM - nd))
+        edg = (C.c_int32 * MAXDIM)(*[1 if e else 0 for e in edges] + [1] * (MAXDIM - nd))
+        n = 1
+        for d in range(nd):
+            n *= img.dims[d]
+        cap = max(1024, n // 64)
+        while True:
+            idx = np.empty(cap, dtype=np.int64)
+            cnt = C.c_int64()
+            self.check(self.dll.b2f_findlocalextrema(C.byref(img), 1 if minima else 0, win, edg,
+                                                     idx.ctypes.data_as(C.POINTER(C.c_int64)), cap, C.byref(cnt),
+                                                     C.c_void_p(stream)))
+            if cnt.value <= cap:
+                return idx[:cnt.value].copy()
+            cap = int(cnt.value)
+
+    def scale_into_slice(self, src: b2f_array, stack: b2f_array, slice_: int, scale: float, stream: int = 0):
+        self.check(self.dll.b2f_scale_into_slice(C.byref(src), C.byref(stack), slice_, scale, C.c_void_p(stream)))
+
+    def maxabs(self, img: b2f_array, stream: int = 0) -> float:
+        r = C.c_double()
+        self.check(self.dll.b2f_maxabs(C.byref(img), C.byref(r), C.c_void_p(stream)))
+        return float(r.value)
+
+    def gather(self, arr: b2f_array, idx: np.ndarray, stream: int = 0) -> np.ndarray:
+        idx = np.ascontiguousarray(idx, dtype=np.int64)
+        out = np.empty(idx.size, dtype=np.float64)
+        self.check(self.dll.b2f_gather(C.byref(arr), idx.ctypes.data_as(C.POINTER(C.c_int64)), idx.size,
+                                       out.ctypes.data_as(C.POINTER(C.c_double)), C.c_void_p(stream)))
+        return out
+
+    # -- raw device memory (arrays that never leave the GPU between calls) ------------------------
+    def malloc(self, nbytes: int) -> int:
+        p = C.c_void_p()
+        self.check(self.dll.b2f_malloc(C.byref(p), max(1, int(nbytes))))
+        return int(p.value)
+
+    def free(self, dptr: int):
+        self.check(self.dll.b2f_free(C.c_void_p(dptr)))

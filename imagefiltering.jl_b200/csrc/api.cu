@@ -181,7 +181,7 @@ struct Ctx {
 };
 static thread_local Ctx g_ctx;
 
-static int ensure_ctx() {
+int ensure_ctx() {
     int dev = 0;
     B2F_CUDA(cudaGetDevice(&dev));
     if (!g_ctx.pool_ready || g_ctx.device != dev) {
@@ -195,13 +195,7 @@ static int ensure_ctx() {
     return 0;
 }
 
-struct Staged {  // device view of one array of the call
-    void *dptr = nullptr;
-    bool owned = false;
-    size_t bytes = 0;
-};
-
-static int stage_in(const b2f_array *a, Staged &s, cudaStream_t st, bool copy) {
+int stage_in(const b2f_array *a, Staged &s, cudaStream_t st, bool copy) {
     int64_t n = 1;
     for (int d = 0; d < a->ndim; ++d) n *= a->dims[d] < 0 ? 0 : a->dims[d];
     s.bytes = (size_t)n * dtype_size(a->dtype);
@@ -213,7 +207,7 @@ static int stage_in(const b2f_array *a, Staged &s, cudaStream_t st, bool copy) {
     if (copy) B2F_CUDA(cudaMemcpyAsync(s.dptr, a->ptr, s.bytes, cudaMemcpyHostToDevice, st));
     return 0;
 }
-static void release(Staged &s, cudaStream_t st) {
+void release(Staged &s, cudaStream_t st) {
     if (s.owned && s.dptr) cudaFreeAsync(s.dptr, st);
     s.dptr = nullptr;
     s.owned = false;

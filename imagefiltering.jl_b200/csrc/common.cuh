@@ -210,6 +210,16 @@ template <typename CT> __device__ __forceinline__ CT mul_rn(CT a, CT b) { return
 template <> __device__ __forceinline__ double mul_rn<double>(double a, double b) { return __dmul_rn(a, b); }
 template <> __device__ __forceinline__ float mul_rn<float>(float a, float b) { return __fmul_rn(a, b); }
 
+// ---- host staging shared by the ABI files (api.cu, points.cu) -------------------------------------------
+struct Staged {  // device view of one array of the call
+    void *dptr = nullptr;
+    bool owned = false;
+    size_t bytes = 0;
+};
+int ensure_ctx();
+int stage_in(const b2f_array *a, Staged &s, cudaStream_t st, bool copy);   // host arrays: pool allocation (+ H2D copy)
+void release(Staged &s, cudaStream_t st);
+
 // ---- kernel-family entry points (host) ---------------------------------------------------------------
 struct DevArrays {        // device-resident views of the call's arrays
     const void *img; int img_dt;

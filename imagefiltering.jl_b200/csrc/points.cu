@@ -1,0 +1,304 @@
+// points.cu — the consumers of the LoG path that SURVEY §8(f) ranks next: local-extrema scan and the blob_LoG plumbing.
+//
+//   b2f_findlocalextrema   findlocalmaxima / findlocalminima      reference src/extrema.jl:107-164
+//   b2f_scale_into_slice   multiLoG's slice write and `.*= -σ`     reference src/extrema.jl:94-105
+//   b2f_maxabs             maximum(abs, img)                      reference src/extrema.jl:85
+//   b2f_gather             img_LoG[x] at the peaks                reference src/extrema.jl:86-90
+//
+// All of it is data-parallel compare / copy work: one thread per element, coalesced along the first axis, HBM-bound.
+// The peak list comes back in the reference's order (column-major ascending): per-block counts, one scan, an ordered
+// scatter (warp ballots give the rank of every peak inside its block).
+#include <cstring>
+
+#include "common.cuh"
+
+namespace b2f {
+
+struct PtGeom {
+    int ndim;
+    long long dims[B2F_MAXDIM];
+    int half[B2F_MAXDIM];      // window >> 1
+    int clip[B2F_MAXDIM];      // 1: first and last index along the axis are not eligible (edges[d] == false)
+    long long n;
+};
+
+constexpr int PT_BLOCK = 256;
+
+template <typename T> __device__ __forceinline__ T pt_load(const void *p, int dt, long long i);
+template <> __device__ __forceinline__ double pt_load<double>(const void *p, int dt, long long i) {
+    return dt == B2F_N0F8 ? (double)((const uint8_t *)p)[i] : load_elem<double>(p, dt, i);   // raw codes order like values
+}
+template <> __device__ __forceinline__ long long pt_load<long long>(const void *p, int, long long i) {
+    return ((const long long *)p)[i];
+}
+
+// isextrema of src/extrema.jl:137-160: strict comparison against every neighbour of the window that lies inside the
+// array; NaN compares false, so a NaN is never a peak and never lets a neighbour be one
+template <typename T>
+__device__ __forceinline__ bool pt_is_extremum(const void *img, int dt, const PtGeom &G, long long lin, bool minima) {
+    long long c[B2F_MAXDIM], r = lin;
+#pragma unroll
+    for (int d = 0; d < B2F_MAXDIM; ++d) {
+        c[d] = r % G.dims[d];
+        r /= G.dims[d];
+        if (G.clip[d] && (c[d] == 0 || c[d] == G.dims[d] - 1)) return false;
+    }
+    const T v = pt_load<T>(img, dt, lin);
+    long long stride[B2F_MAXDIM];
+    stride[0] = 1;
+#pragma unroll
+    for (int d = 1; d < B2F_MAXDIM; ++d) stride[d] = stride[d - 1] * G.dims[d - 1];
+    for (int j3 = -G.half[3]; j3 <= G.half[3]; ++j3) {
+        if ((unsigned long long)(c[3] + j3) >= (unsigned long long)G.dims[3]) continue;
+        for (int j2 = -G.half[2]; j2 <= G.half[2]; ++j2) {
+            if ((unsigned long long)(c[2] + j2) >= (unsigned long long)G.dims[2]) continue;
+            for (int j1 = -G.half[1]; j1 <= G.half[1]; ++j1) {
+                if ((unsigned long long)(c[1] + j1) >= (unsigned long long)G.dims[1]) continue;
+                const long long base = lin + j3 * stride[3] + j2 * stride[2] + j1 * stride[1];
+                for (int j0 = -G.half[0]; j0 <= G.half[0]; ++j0) {
+                    if ((unsigned long long)(c[0] + j0) >= (unsigned long long)G.dims[0]) continue;
+                    if (j0 == 0 && j1 == 0 && j2 == 0 && j3 == 0) continue;
+                    const T w = pt_load<T>(img, dt, base + j0);
+                    if (!(minima ? v < w : v > w)) return false;
+                }
+            }
+        }
+    }
+    return true;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(PT_BLOCK) pt_flag_kernel(const void *img, int dt, PtGeom G, int minima,
+                                                           unsigned char *flags, unsigned *block_counts) {
+    const long long lin = (long long)blockIdx.x * PT_BLOCK + threadIdx.x;
+    const bool f = lin < G.n && pt_is_extremum<T>(img, dt, G, lin, minima != 0);
+    if (lin < G.n) flags[lin] = f ? 1 : 0;
+    const int cnt = __syncthreads_count(f);
+    if (threadIdx.x == 0) block_counts[blockIdx.x] = (unsigned)cnt;
+}
+
+// exclusive scan of the per-block counts (one CTA; every thread owns a contiguous chunk); total -> *total
+__global__ void __launch_bounds__(1024) pt_scan_kernel(const unsigned *counts, long long *offsets, long long nblocks,
+                                                       long long *total) {
+    __shared__ long long part[1024];
+    const long long chunk = (nblocks + 1023) / 1024;
+    const long long b0 = min((long long)threadIdx.x * chunk, nblocks), b1 = min(b0 + chunk, nblocks);
+    long long s = 0;
+    for (long long b = b0; b < b1; ++b) s += counts[b];
+    part[threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        long long run = 0;
+        for (int t = 0; t < 1024; ++t) { const long long v = part[t]; part[t] = run; run += v; }
+        *total = run;
+    }
+    __syncthreads();
+    long long run = part[threadIdx.x];
+    for (long long b = b0; b < b1; ++b) { offsets[b] = run; run += counts[b]; }
+}
+
+__global__ void __launch_bounds__(PT_BLOCK) pt_scatter_kernel(const unsigned char *flags, const long long *offsets, long long n,
+                                                              long long *idx, long long cap) {
+    __shared__ unsigned wsum[PT_BLOCK / 32];
+    const long long lin = (long long)blockIdx.x * PT_BLOCK + threadIdx.x;
+    const bool f = lin < n && flags[lin];
+    const unsigned bal = __ballot_sync(0xffffffffu, f);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) wsum[warp] = __popc(bal);
+    __syncthreads();
+    unsigned before = 0;
+    for (int w = 0; w < warp; ++w) before += wsum[w];
+    if (f) {
+        const long long pos = offsets[blockIdx.x] + before + __popc(bal & ((1u << lane) - 1));
+        if (pos < cap) idx[pos] = lin;
+    }
+}
+
+__global__ void pt_scale_slice_kernel(const void *src, int sdt, void *stack, int odt, long long n, long long S, long long slice,
+                                      double scale) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const double v = load_elem<double>(src, sdt, i) * scale;      // slice .*= -σ: product in Float64, stored as eltype
+        if (odt == B2F_F32) ((float *)stack)[slice + S * i] = (float)v;
+        else ((double *)stack)[slice + S * i] = v;
+    }
+}
+
+__global__ void pt_maxabs_kernel(const void *img, int dt, long long n, unsigned long long *bits, int *nan_seen) {
+    double m = 0.0;
+    bool nan = false;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const double v = fabs(load_elem<double>(img, dt, i));
+        if (v != v) nan = true; else m = fmax(m, v);
+    }
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (__any_sync(0xffffffffu, nan) && (threadIdx.x & 31) == 0) atomicOr(nan_seen, 1);
+    if ((threadIdx.x & 31) == 0) atomicMax(bits, (unsigned long long)__double_as_longlong(m));   // m >= 0: bits order like values
+}
+
+__global__ void pt_gather_kernel(const void *arr, int dt, const long long *idx, long long n, double *out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = load_elem<double>(arr, dt, idx[i]);
+}
+
+static long long numel(const b2f_array *a) {
+    long long n = 1;
+    for (int d = 0; d < a->ndim; ++d) n *= a->dims[d] < 0 ? 0 : a->dims[d];
+    return n;
+}
+
+}  // namespace b2f
+
+using namespace b2f;
+
+extern "C" {
+
+int b2f_findlocalextrema(const b2f_array *img, int32_t minima, const int64_t *window, const int32_t *edges,
+                         int64_t *idx, int64_t cap, int64_t *count, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!img || !window || !edges || !count || (cap > 0 && !idx)) return fail(B2F_EARG, "NULL argument");
+    if (img->ndim < 1 || img->ndim > B2F_MAXDIM) return fail(B2F_ENOTSUP, "ndim %d not supported (1..%d)", img->ndim, B2F_MAXDIM);
+    if (img->dtype < B2F_U8 || img->dtype > B2F_U32) return fail(B2F_EARG, "unsupported image dtype %d", img->dtype);
+    PtGeom G;
+    memset(&G, 0, sizeof G);
+    G.ndim = img->ndim;
+    G.n = numel(img);
+    for (int d = 0; d < B2F_MAXDIM; ++d) {
+        G.dims[d] = d < img->ndim ? img->dims[d] : 1;
+        if (d < img->ndim) {
+            if (window[d] < 1) return fail(B2F_EARG, "window sizes must be positive");
+            G.half[d] = (int)(window[d] >> 1);
+            G.clip[d] = edges[d] ? 0 : 1;
+        }
+    }
+    *count = 0;
+    set_path("localextrema");
+    if (G.n == 0) return 0;
+    int rc = ensure_ctx();
+    if (rc) return rc;
+    Staged sin;
+    rc = stage_in(img, sin, st, true);
+    if (rc) return rc;
+    const long long nblocks = (G.n + PT_BLOCK - 1) / PT_BLOCK;
+    if (nblocks > 0x7fffffffLL) { release(sin, st); return fail(B2F_ENOTSUP, "array too large"); }
+    unsigned char *flags = nullptr;
+    unsigned *counts = nullptr;
+    long long *offsets = nullptr, *total = nullptr, *d_idx = nullptr;
+    cudaError_t e = cudaMallocAsync((void **)&flags, (size_t)G.n, st);
+    if (e == cudaSuccess) e = cudaMallocAsync((void **)&counts, (size_t)nblocks * sizeof(unsigned), st);
+    if (e == cudaSuccess) e = cudaMallocAsync((void **)&offsets, (size_t)(nblocks + 1) * sizeof(long long), st);
+    total = offsets ? offsets + nblocks : nullptr;
+    if (e == cudaSuccess && cap > 0) e = cudaMallocAsync((void **)&d_idx, (size_t)cap * sizeof(long long), st);
+    if (e == cudaSuccess) {
+        if (img->dtype == B2F_I64)
+            pt_flag_kernel<long long><<<(unsigned)nblocks, PT_BLOCK, 0, st>>>(sin.dptr, img->dtype, G, minima, flags, counts);
+        else
+            pt_flag_kernel<double><<<(unsigned)nblocks, PT_BLOCK, 0, st>>>(sin.dptr, img->dtype, G, minima, flags, counts);
+        pt_scan_kernel<<<1, 1024, 0, st>>>(counts, offsets, nblocks, total);
+        count_launch(2);
+        if (cap > 0) {
+            pt_scatter_kernel<<<(unsigned)nblocks, PT_BLOCK, 0, st>>>(flags, offsets, G.n, d_idx, cap);
+            count_launch();
+        }
+        e = cudaGetLastError();
+    }
+    long long h_total = 0;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&h_total, total, sizeof h_total, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess && cap > 0 && h_total > 0) {
+        const long long ncopy = h_total < cap ? h_total : cap;
+        e = cudaMemcpyAsync(idx, d_idx, (size_t)ncopy * sizeof(long long), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    }
+    if (flags) cudaFreeAsync(flags, st);
+    if (counts) cudaFreeAsync(counts, st);
+    if (offsets) cudaFreeAsync(offsets, st);
+    if (d_idx) cudaFreeAsync(d_idx, st);
+    release(sin, st);
+    if (e != cudaSuccess) return fail(B2F_ECUDA, "findlocalextrema failed: %s", cudaGetErrorString(e));
+    *count = h_total;
+    return 0;
+}
+
+int b2f_scale_into_slice(const b2f_array *src, const b2f_array *stack, int64_t slice, double scale, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!src || !stack) return fail(B2F_EARG, "NULL argument");
+    if (stack->ndim != src->ndim + 1 || stack->ndim > B2F_MAXDIM) return fail(B2F_EDIM, "stack must have one leading axis more than src");
+    for (int d = 0; d < src->ndim; ++d)
+        if (stack->dims[d + 1] != src->dims[d]) return fail(B2F_EDIM, "stack axes do not match src axes");
+    if (slice < 0 || slice >= stack->dims[0]) return fail(B2F_EDIM, "slice %lld outside the leading axis", (long long)slice);
+    if (stack->dtype != B2F_F32 && stack->dtype != B2F_F64) return fail(B2F_EARG, "stack must be Float32 or Float64");
+    if (src->mem != B2F_DEVICE || stack->mem != B2F_DEVICE) return fail(B2F_ENOTSUP, "scale_into_slice takes device arrays");
+    const long long n = numel(src);
+    set_path("scale_slice");
+    if (n == 0) return 0;
+    const long long blocks = (n + 255) / 256;
+    pt_scale_slice_kernel<<<(unsigned)(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, st>>>(src->ptr, src->dtype, stack->ptr, stack->dtype, n,
+                                                                                      stack->dims[0], slice, scale);
+    count_launch();
+    B2F_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int b2f_maxabs(const b2f_array *img, double *result, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!img || !result) return fail(B2F_EARG, "NULL argument");
+    const long long n = numel(img);
+    if (n == 0) return fail(B2F_EARG, "reducing over an empty collection is not allowed");
+    int rc = ensure_ctx();
+    if (rc) return rc;
+    Staged sin;
+    rc = stage_in(img, sin, st, true);
+    if (rc) return rc;
+    unsigned long long *acc = nullptr;
+    cudaError_t e = cudaMallocAsync((void **)&acc, 16, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(acc, 0, 16, st);
+    unsigned long long h[2] = {0, 0};
+    if (e == cudaSuccess) {
+        const long long blocks = (n + 255) / 256;
+        pt_maxabs_kernel<<<(unsigned)(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, st>>>(sin.dptr, img->dtype, n, acc, (int *)(acc + 1));
+        count_launch();
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h, acc, 16, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (acc) cudaFreeAsync(acc, st);
+    release(sin, st);
+    if (e != cudaSuccess) return fail(B2F_ECUDA, "maxabs failed: %s", cudaGetErrorString(e));
+    double m;
+    memcpy(&m, &h[0], sizeof m);
+    *result = (h[1] & 1ULL) ? __builtin_nan("") : m;
+    return 0;
+}
+
+int b2f_gather(const b2f_array *arr, const int64_t *idx, int64_t n, double *values, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!arr || (n > 0 && (!idx || !values))) return fail(B2F_EARG, "NULL argument");
+    if (n <= 0) return 0;
+    const long long total = numel(arr);
+    for (int64_t i = 0; i < n; ++i)
+        if (idx[i] < 0 || idx[i] >= total) return fail(B2F_EDIM, "index %lld outside the array", (long long)idx[i]);
+    int rc = ensure_ctx();
+    if (rc) return rc;
+    Staged sin;
+    rc = stage_in(arr, sin, st, true);
+    if (rc) return rc;
+    long long *d_idx = nullptr;
+    double *d_out = nullptr;
+    cudaError_t e = cudaMallocAsync((void **)&d_idx, (size_t)n * 8, st);
+    if (e == cudaSuccess) e = cudaMallocAsync((void **)&d_out, (size_t)n * 8, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_idx, idx, (size_t)n * 8, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) {
+        pt_gather_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(sin.dptr, arr->dtype, d_idx, n, d_out);
+        count_launch();
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(values, d_out, (size_t)n * 8, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (d_idx) cudaFreeAsync(d_idx, st);
+    if (d_out) cudaFreeAsync(d_out, st);
+    release(sin, st);
+    if (e != cudaSuccess) return fail(B2F_ECUDA, "gather failed: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+}  // extern "C"

@@ -198,6 +198,33 @@ int b2f_imfilter_slab(const b2f_array *img, const b2f_array *out,
                       const void *halo_hi, int64_t n_halo_hi,
                       void *stream);
 
+/* ---- consumers of the LoG path ------------------------------------------ */
+
+/* findlocalmaxima(img; window, edges) / findlocalminima  (src/extrema.jl:107-164, loop :125-162).
+ * `window[d]` >= 1 per axis (half-width window[d] >> 1), `edges[d]` == 0 excludes the first and last
+ * index along axis d.  An element is an extremum when it compares strictly greater (minima != 0:
+ * smaller) than every neighbour of the window that lies inside the array.  `idx` (HOST, capacity
+ * `cap`, may be NULL when cap == 0) receives the first `cap` peaks as 0-based column-major linear
+ * indices in ascending order — the order in which the reference pushes its CartesianIndex values;
+ * `*count` receives the total number of peaks (call again with cap >= count if it was larger).
+ * Synchronous. */
+int b2f_findlocalextrema(const b2f_array *img, int32_t minima, const int64_t *window, const int32_t *edges,
+                         int64_t *idx, int64_t cap, int64_t *count, void *stream);
+
+/* multiLoG (src/extrema.jl:94-105): `stack` has one LEADING axis more than `src` (dims (S, dims(src)...),
+ * Float32 or Float64); slice `slice` (0-based) of that axis receives src .* scale, the product taken in
+ * Float64 and stored as eltype(stack) — the reference's `imfilter!(view(img_LoG, isigma, :, ...), ...)`
+ * followed by `LoG_slice .*= -σ`, with src = the dense imfilter result.  Device arrays (the oracle
+ * library: host arrays); asynchronous on `stream`. */
+int b2f_scale_into_slice(const b2f_array *src, const b2f_array *stack, int64_t slice, double scale, void *stream);
+
+/* maximum(abs, img) (src/extrema.jl:85) -> *result (HOST).  NaN if any element is NaN.  Synchronous. */
+int b2f_maxabs(const b2f_array *img, double *result, void *stream);
+
+/* values[i] = arr[idx[i]] as Float64, idx = 0-based linear indices (HOST in, HOST out): the amplitudes
+ * img_LoG[x] of the peaks (src/extrema.jl:86-90).  Synchronous. */
+int b2f_gather(const b2f_array *arr, const int64_t *idx, int64_t n, double *values, void *stream);
+
 /* number of CUDA kernels launched by this library on the calling thread since the last reset
  * (the oracle library always reports 0) */
 int64_t b2f_launch_count(void);

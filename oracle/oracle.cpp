@@ -26,6 +26,7 @@
 //   tiled + threads   src/imfilter.jl:398-404,460-542,1298-1312 (b2f_oracle_imfilter_tiled)
 //   imgradients       src/specialty.jl:39-53
 //   mapwindow min/max src/mapwindow.jl:270-333 (generic, copy_win!), :388-481 (extrema_filter)
+//   local extrema     src/extrema.jl:125-164 (findlocalextrema), :94-105 (multiLoG slice), :85-90 (blob_LoG plumbing)
 //
 // Build: g++ -O3 -mavx2 -ffp-contract=off (NO -ffast-math, NO FMA contraction: Julia emits neither).
 
@@ -1028,3 +1029,129 @@ extern "C" int b2f_oracle_imfilter_tiled(const b2f_array *img, const b2f_array *
     if (out->dtype == B2F_F32) return tiled_typed<float>(img, out, P, border, tile, nthreads);
     return fail(B2F_ENOTSUP, "tiled oracle handles float outputs");
 }
+
+// ---- §8(f) rank 1: findlocalextrema / blob_LoG plumbing (reference src/extrema.jl:85-105, 125-164) ----------------
+namespace {
+double o_elem(const b2f_array *a, int64_t i) {          // element as Float64 (N0f8: the raw code, same order)
+    switch (a->dtype) {
+        case B2F_U8: case B2F_N0F8: return (double)((const uint8_t *)a->ptr)[i];
+        case B2F_I16: return (double)((const int16_t *)a->ptr)[i];
+        case B2F_U16: return (double)((const uint16_t *)a->ptr)[i];
+        case B2F_I32: return (double)((const int32_t *)a->ptr)[i];
+        case B2F_U32: return (double)((const uint32_t *)a->ptr)[i];
+        case B2F_I64: return (double)((const int64_t *)a->ptr)[i];
+        case B2F_F32: return (double)((const float *)a->ptr)[i];
+        default: return ((const double *)a->ptr)[i];
+    }
+}
+int64_t o_numel(const b2f_array *a) {
+    int64_t n = 1;
+    for (int d = 0; d < a->ndim; ++d) n *= a->dims[d] < 0 ? 0 : a->dims[d];
+    return n;
+}
+}  // namespace
+
+extern "C" {
+
+// src/extrema.jl:125-162: `for i in R` (column-major) over the edge-clipped indices; i is an extremum when f(img[i],
+// img[i+j]) holds for every window offset j != 0 whose target lies inside the array
+int b2f_findlocalextrema(const b2f_array *img, int32_t minima, const int64_t *window, const int32_t *edges,
+                         int64_t *idx, int64_t cap, int64_t *count, void *) {
+    if (!img || !window || !edges || !count || (cap > 0 && !idx)) return fail(B2F_EARG, "NULL argument");
+    if (img->ndim < 1 || img->ndim > B2F_MAXDIM) return fail(B2F_ENOTSUP, "ndim %d not supported", img->ndim);
+    int64_t dims[B2F_MAXDIM], half[B2F_MAXDIM], clip[B2F_MAXDIM], stride[B2F_MAXDIM];
+    for (int d = 0; d < B2F_MAXDIM; ++d) {
+        dims[d] = d < img->ndim ? img->dims[d] : 1;
+        half[d] = clip[d] = 0;
+        if (d < img->ndim) {
+            if (window[d] < 1) return fail(B2F_EARG, "window sizes must be positive");
+            half[d] = window[d] >> 1;
+            clip[d] = edges[d] ? 0 : 1;
+        }
+        stride[d] = d == 0 ? 1 : stride[d - 1] * dims[d - 1];
+    }
+    const int64_t n = o_numel(img);
+    const bool is_i64 = img->dtype == B2F_I64;
+    int64_t found = 0;
+    for (int64_t lin = 0; lin < n; ++lin) {
+        int64_t c[B2F_MAXDIM], r = lin;
+        bool ok = true;
+        for (int d = 0; d < B2F_MAXDIM; ++d) {
+            c[d] = r % dims[d];
+            r /= dims[d];
+            if (clip[d] && (c[d] == 0 || c[d] == dims[d] - 1)) ok = false;
+        }
+        if (!ok) continue;
+        const double v = o_elem(img, lin);
+        const int64_t vi = is_i64 ? ((const int64_t *)img->ptr)[lin] : 0;
+        for (int64_t j3 = -half[3]; j3 <= half[3] && ok; ++j3)
+            for (int64_t j2 = -half[2]; j2 <= half[2] && ok; ++j2)
+                for (int64_t j1 = -half[1]; j1 <= half[1] && ok; ++j1)
+                    for (int64_t j0 = -half[0]; j0 <= half[0] && ok; ++j0) {
+                        if (!j0 && !j1 && !j2 && !j3) continue;
+                        const int64_t q[4] = {c[0] + j0, c[1] + j1, c[2] + j2, c[3] + j3};
+                        bool inside = true;
+                        for (int d = 0; d < 4; ++d) inside = inside && q[d] >= 0 && q[d] < dims[d];
+                        if (!inside) continue;
+                        const int64_t t = lin + j0 * stride[0] + j1 * stride[1] + j2 * stride[2] + j3 * stride[3];
+                        if (is_i64) {
+                            const int64_t w = ((const int64_t *)img->ptr)[t];
+                            ok = minima ? vi < w : vi > w;
+                        } else {
+                            const double w = o_elem(img, t);
+                            ok = minima ? v < w : v > w;
+                        }
+                    }
+        if (ok) {
+            if (found < cap) idx[found] = lin;
+            ++found;
+        }
+    }
+    *count = found;
+    return 0;
+}
+
+// src/extrema.jl:99-103: the slice of the leading axis receives the filtered image, then `.*= -σ`
+int b2f_scale_into_slice(const b2f_array *src, const b2f_array *stack, int64_t slice, double scale, void *) {
+    if (!src || !stack) return fail(B2F_EARG, "NULL argument");
+    if (stack->ndim != src->ndim + 1 || stack->ndim > B2F_MAXDIM) return fail(B2F_EDIM, "stack must have one leading axis more than src");
+    for (int d = 0; d < src->ndim; ++d)
+        if (stack->dims[d + 1] != src->dims[d]) return fail(B2F_EDIM, "stack axes do not match src axes");
+    if (slice < 0 || slice >= stack->dims[0]) return fail(B2F_EDIM, "slice outside the leading axis");
+    if (stack->dtype != B2F_F32 && stack->dtype != B2F_F64) return fail(B2F_EARG, "stack must be Float32 or Float64");
+    const int64_t n = o_numel(src), S = stack->dims[0];
+    for (int64_t i = 0; i < n; ++i) {
+        const double v = o_elem(src, i) * scale;
+        if (stack->dtype == B2F_F32) ((float *)stack->ptr)[slice + S * i] = (float)v;
+        else ((double *)stack->ptr)[slice + S * i] = v;
+    }
+    return 0;
+}
+
+// src/extrema.jl:85: imgmax = maximum(abs, img)
+int b2f_maxabs(const b2f_array *img, double *result, void *) {
+    if (!img || !result) return fail(B2F_EARG, "NULL argument");
+    const int64_t n = o_numel(img);
+    if (n == 0) return fail(B2F_EARG, "reducing over an empty collection is not allowed");
+    double m = 0.0;
+    bool nan = false;
+    for (int64_t i = 0; i < n; ++i) {
+        const double v = std::fabs(o_elem(img, i));
+        if (v != v) nan = true; else if (v > m) m = v;
+    }
+    *result = nan ? std::numeric_limits<double>::quiet_NaN() : m;
+    return 0;
+}
+
+// src/extrema.jl:86-90: img_LoG[x] for every peak x
+int b2f_gather(const b2f_array *arr, const int64_t *idx, int64_t n, double *values, void *) {
+    if (!arr || (n > 0 && (!idx || !values))) return fail(B2F_EARG, "NULL argument");
+    const int64_t total = o_numel(arr);
+    for (int64_t i = 0; i < n; ++i) {
+        if (idx[i] < 0 || idx[i] >= total) return fail(B2F_EDIM, "index outside the array");
+        values[i] = o_elem(arr, idx[i]);
+    }
+    return 0;
+}
+
+}  // extern "C"

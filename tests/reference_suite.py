@@ -1,6 +1,6 @@
 """The reference's own tests for the FIR / min-max path, re-expressed against this package's API
 (reference test/border.jl, test/nd.jl, test/2d.jl, test/cascade.jl, test/gradient.jl,
-test/mapwindow.jl; citations at each check).  Every check takes `lib`:
+test/mapwindow.jl, test/extrema.jl; citations at each check).  Every check takes `lib`:
   * the CPU oracle Library  -> pins the oracle against the reference's goldens (CPU, `-m "not gpu"`)
   * None                    -> the product CUDA library through the same host code (`-m gpu`)
 """
@@ -469,6 +469,68 @@ def check_mapwindow_offsets(ifb, lib):
                             assert np.array_equal(p1, _naive_window(npf, a, wlo, whi, bname, fillv)), (fname, window, border)
 
 
-ALL_CHECKS = [check_padarray, check_1d, check_widening, check_prewitt_tiling, check_impulse_interior,
+def check_local_extrema(ifb, lib):
+    """reference test/extrema.jl:2-13 ("local extrema"): literal index lists, in the reference's order."""
+    A = np.zeros((9, 9), dtype=np.int64); A[[0, 1, 4], 4] = 1
+    assert ifb.findlocalmaxima(A, _library=lib) == [(5, 5)]
+    assert ifb.findlocalmaxima(A, window=(1, 3), _library=lib) == [(1, 5), (2, 5), (5, 5)]
+    assert ifb.findlocalmaxima(A, window=(1, 3), edges=False, _library=lib) == [(2, 5), (5, 5)]
+    A = np.zeros((9, 9, 9), dtype=np.int64); A[[0, 1, 4], 4, 4] = 1
+    assert ifb.findlocalmaxima(A, _library=lib) == [(5, 5, 5)]
+    assert ifb.findlocalmaxima(A, window=(1, 3, 1), _library=lib) == [(1, 5, 5), (2, 5, 5), (5, 5, 5)]
+    assert ifb.findlocalmaxima(A, window=(1, 3, 1), edges=False, _library=lib) == [(2, 5, 5), (5, 5, 5)]
+    A = np.zeros((9, 9), dtype=np.int64); A[[0, 1, 4], 4] = -1
+    assert ifb.findlocalminima(A, _library=lib) == [(5, 5)]
+
+
+def check_blob_log(ifb, lib):
+    """reference test/extrema.jl:15-60 ("blob_LoG"), incl. the 1/pi amplitude golden, and the docstring example
+    src/extrema.jl:47-56."""
+    A = np.zeros((9, 9), dtype=np.int64); A[4, 4] = 1
+    blobs = ifb.blob_LoG(A, 2.0 ** np.array([0.5, 0, 1]), _library=lib)
+    assert len(blobs) == 1
+    blob = blobs[0]
+    assert abs(blob.amplitude - 0.3183098861837907) <= 1.5e-8 * 0.3183098861837907
+    assert blob.σ == (1.0, 1.0) and blob.location == (5, 5)
+    assert ifb.blob_LoG(A, [1.0], _library=lib) == blobs
+    assert ifb.blob_LoG(A, [1.0], edges=(True, False, False), _library=lib) == blobs
+    assert ifb.blob_LoG(A, [1.0], edges=False, _library=lib) == []
+    A = np.zeros((9, 9), dtype=np.int64); A[0, 4] = 1
+    blobs = ifb.blob_LoG(A, 2.0 ** np.array([0.5, 0, 1]), _library=lib)
+    assert all(b.amplitude < 1e-16 for b in blobs)
+    blobs = [b for b in ifb.blob_LoG(A, 2.0 ** np.array([0.5, 0, 1]), edges=True, _library=lib) if b.amplitude > 0.1]
+    assert len(blobs) == 1 and blobs[0].location == (1, 5)
+    assert [b for b in ifb.blob_LoG(A, 2.0 ** np.array([0.5, 0, 1]), edges=(True, True, False), _library=lib)
+            if b.amplitude > 0.1] == blobs
+    assert ifb.blob_LoG(A, 2.0 ** np.array([0, 1]), edges=(False, True, False), _library=lib) == []
+    blobs = ifb.blob_LoG(A, 2.0 ** np.array([0, 0.5, 1]), edges=(True, False, True), _library=lib)
+    assert all(b.amplitude < 1e-16 for b in blobs)
+    A = np.zeros((9, 9, 9), dtype=np.int64); A[4, 4, 4] = 1
+    blobs = ifb.blob_LoG(A, 2.0 ** np.array([0.5, 0, 1]), _library=lib)
+    assert len(blobs) == 1 and blobs[0].location == (5, 5, 5)
+    A = np.zeros((9, 9, 9), dtype=np.int64); A[4, 3:6, 4] = 1          # "kinda anisotropic image"
+    blobs = ifb.blob_LoG(A, 2.0 ** np.array([1.0, 0, 0.5]), σshape=(1.0, 3.0, 1.0), _library=lib)
+    assert len(blobs) == 1 and blobs[0].location == (5, 5, 5)
+    A = np.zeros((9, 9, 9), dtype=np.int64); A[0, 0, 3:6] = 1
+    blobs = [b for b in ifb.blob_LoG(A, 2.0 ** np.array([0.5, 0, 1]), edges=True, σshape=(1.0, 1.0, 3.0), _library=lib)
+             if b.amplitude > 0.1]
+    assert len(blobs) == 1 and blobs[0].location == (1, 1, 5)
+    assert [b for b in ifb.blob_LoG(A, 2.0 ** np.array([0.5, 0, 1]), edges=(True, True, True, False),
+                                    σshape=(1.0, 1.0, 3.0), _library=lib) if b.amplitude > 0.1] == blobs
+    assert ifb.blob_LoG(A, 2.0 ** np.array([0, 1]), edges=(False, True, False, False), σshape=(1.0, 1.0, 3.0),
+                        _library=lib) == []
+    v = np.concatenate([np.zeros(10), [1.0, 0.0]])
+    assert len(ifb.blob_LoG(v, [4], edges=True, rthresh=0, _library=lib)) > len(ifb.blob_LoG(v, [4], edges=True, _library=lib))
+    # docstring example (two Gaussian bumps of width 4 and 8)
+    img = np.zeros(100)
+    img[19:30] = [np.exp(-x ** 2 / (2 * 4 ** 2)) for x in range(-5, 6)]
+    img[49:80] = [np.exp(-x ** 2 / (2 * 8 ** 2)) for x in range(-15, 16)]
+    blobs = ifb.blob_LoG(img, 2.0 ** np.arange(1, 7), edges=False, _library=lib)
+    assert [(b.location, b.σ) for b in blobs] == [((25,), (4.0,)), ((65,), (8.0,))]
+    assert abs(blobs[0].amplitude - 0.10453155018303673) < 1e-12 and abs(blobs[1].amplitude - 0.046175719034527364) < 1e-12
+
+
+
+ALL_CHECKS = [check_local_extrema, check_blob_log, check_padarray, check_1d, check_widening, check_prewitt_tiling, check_impulse_interior,
               check_impulse_corner, check_offset_axes, check_nonfinite, check_3d_box, check_cascade,
               check_gradients, check_laplacian, check_extrema_goldens, check_mapwindow_offsets]

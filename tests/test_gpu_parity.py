@@ -425,3 +425,48 @@ def test_stream3d_parity(ifb, oracle, device, border, monkeypatch):
     pa, pb = _both(ifb, oracle, np.float32, img, g((4, 4, 4)), b)
     assert device.last_path() == "sepnd"
     assert np.max(np.abs(pa.astype(np.float64) - pb.astype(np.float64))) <= _tol([k.data.parent for k in g((4, 4, 4))], img)
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64, np.uint8, np.int32, np.int64])
+def test_findlocalextrema_parity(ifb, oracle, device, dt):
+    """Strict-peak scan (src/extrema.jl:125-162): GPU index lists == oracle index lists (same order), for plateaus
+    (integer data with many ties), NaNs, even windows, per-axis edge flags, 1-D .. 4-D."""
+    rng = np.random.default_rng(int(np.dtype(dt).itemsize) * 7 + 1)
+    cases = [((1000,), (3,), (True,)), ((257, 130), (3, 3), (True, False)), ((64, 50, 33), (3, 3, 3), (False, True, True)),
+             ((40, 30, 20), (1, 5, 2), (True, True, False)), ((9, 8, 7, 6), (3, 3, 3, 3), (True, True, True, True)),
+             ((300, 300), (7, 1), (False, False)), ((2, 3), (3, 3), (False, True)), ((1, 5), (3, 3), (True, True))]
+    for shape, window, edges in cases:
+        if np.dtype(dt).kind == "f":
+            A = rng.random(shape).astype(dt)
+            if A.size > 50:
+                A.ravel()[rng.integers(0, A.size, 5)] = np.nan
+        else:
+            A = rng.integers(0, 6, size=shape).astype(dt)
+        A = np.asfortranarray(A)
+        for f in (ifb.findlocalmaxima, ifb.findlocalminima):
+            device.reset_launch_count()
+            got = f(A, window=window, edges=edges)
+            assert device.launch_count() > 0 and device.last_path() == "localextrema"
+            assert got == f(A, window=window, edges=edges, _library=oracle), (shape, window, edges, f.__name__)
+
+
+def test_blob_log_parity(ifb, oracle, device):
+    """blob_LoG on random blobs: same peaks and σ as the oracle, amplitudes bit-equal in Float64 and within the Float32
+    tolerance for Float32 images; the σ-stack stays on the GPU (multi-σ LoG + scan + gather)."""
+    rng = np.random.default_rng(11)
+    yy, xx = np.meshgrid(np.arange(96), np.arange(128))
+    img = np.zeros((128, 96))
+    for cx, cy, s in ((30, 20, 2.0), (80, 60, 4.0), (100, 30, 3.0)):
+        img += np.exp(-((xx - cx) ** 2 + (yy - cy) ** 2) / (2 * s * s))
+    img += 0.01 * rng.random(img.shape)
+    for T in (np.float64, np.float32):
+        A = np.asfortranarray(img.astype(T))
+        got = ifb.blob_LoG(A, [2.0, 3.0, 4.0, 6.0], rthresh=0.05)
+        ref = ifb.blob_LoG(A, [2.0, 3.0, 4.0, 6.0], rthresh=0.05, _library=oracle)
+        if T == np.float64:
+            assert got == ref and len(got) >= 3
+        else:       # Float32 LoG stack: peaks may only differ where the amplitudes tie within the tolerance
+            strong = lambda bl: sorted((b.location, b.σ) for b in bl if b.amplitude > 0.1)
+            assert strong(got) == strong(ref) and len(strong(got)) >= 3
+            amp = {b.location: b.amplitude for b in ref}
+            assert all(abs(b.amplitude - amp[b.location]) <= 1e-5 for b in got if b.location in amp)
