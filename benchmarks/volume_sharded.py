@@ -32,6 +32,7 @@ def main():
     lib = import_module("imagefiltering_jl_b200._lib").lib()
     ap = argparse.ArgumentParser()
     ap.add_argument("--n", type=int, default=1024)
+    ap.add_argument("--planes", type=int, default=0, help="planes along the sharded axis (default: n)")
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--mode", default="p2p", choices=["p2p", "sendrecv"])
@@ -70,7 +71,8 @@ def main():
 
     # ---- the timed volume ---------------------------------------------------------------------------------------------
     n = args.n
-    first, cnt = sh.slab_bounds(n, world, rank)
+    nz = args.planes or n
+    first, cnt = sh.slab_bounds(nz, world, rank)
     g.manual_seed(1000 + rank)
     slab = torch.rand((cnt, n, n), device=dev, generator=g)
     f = sh.ShardedImfilter(slab, kern, border, mode=args.mode)
@@ -99,11 +101,11 @@ def main():
     f.close()
     if rank == 0:
         hbm, which = peaks()
-        npx = n ** 3
+        npx = n * n * nz
         gbs = npx * 8 / (ms * 1e-3) / 1e9
         halo_mb = 2 * f.h_lo * n * n * 4 / 1e6 if world > 1 else 0.0
         print(json.dumps({
-            "workload": "c5-sharded", "desc": f"{n}^3 f32 gaussian((4,4,4)) Pad(:symmetric), {world} slab(s) along the last axis",
+            "workload": "c5-sharded", "desc": f"{n}x{n}x{nz} f32 gaussian((4,4,4)) Pad(:symmetric), {world} slab(s) along the last axis",
             "n_gpus": world, "mode": args.mode, "entry_barrier": not args.nosync, "ms": ms,
             "gpixel_per_s": npx / (ms * 1e-3) / 1e9, "achieved_gbs_total": gbs, "hbm_frac_per_gpu": gbs / world / hbm,
             "peak_source": "of " + which, "halo_mb_per_gpu_per_direction": halo_mb / 2, "path": path,

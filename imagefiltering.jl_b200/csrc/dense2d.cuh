@@ -93,7 +93,34 @@ __global__ void __launch_bounds__(D2_WARPS * 32) dense2d_kernel(const D2Params<C
         for (int t = threadIdx.x; t < P.Ky * KXP; t += blockDim.x) s_k[t] = P.taps[t];
     }
     __syncthreads();
-    {
+    // Interior tiles whose element type is already the compute type: 128-bit loads of the 16-byte aligned body of every
+    // row (all of a thread's loads in flight at once: one DRAM round trip instead of one per group of four), scalar head
+    // and tail.  The load phase is pure latency and co-resident CTAs run in lockstep, so it idles the FP32 pipe.
+    const int gx0 = x0 + P.klox, gy0 = y0 + P.kloy;
+    const bool fast = P.img_dt == (F32 ? B2F_F32 : B2F_F64) && gx0 >= 0 && gx0 + P.in_cols <= P.W && gy0 >= 0 &&
+                      gy0 + P.in_rows <= P.H && (P.W % R) == 0 && (reinterpret_cast<uintptr_t>(P.img) % 16) == 0 &&
+                      (P.img_plane % R) == 0;
+    if (fast) {
+        const CT *src = reinterpret_cast<const CT *>(P.img) + bz * P.img_plane + (long long)gy0 * P.W + gx0;
+        const int head = (R - (gx0 % R)) % R;                     // scalar elements before the aligned body
+        const int nvec = (P.in_cols - head) / R;                   // whole vectors per row
+        const int tail0 = head + nvec * R;
+        const int per_row = nvec + head + (P.in_cols - tail0);     // work items per row: vectors, then the scalars
+        for (int it = threadIdx.x; it < per_row * P.in_rows; it += blockDim.x) {
+            const int r = it / per_row, k = it - r * per_row;
+            const CT *srow = src + (long long)r * P.W;
+            CT *dst = s_in + (size_t)r * P.P1;
+            if (k < nvec) {
+                const int c = head + k * R;
+                const V t = __ldg(reinterpret_cast<const V *>(srow + c));
+#pragma unroll
+                for (int q = 0; q < R; ++q) dst[c + q] = ((const CT *)&t)[q];
+            } else {
+                const int e = k - nvec, c = e < head ? e : tail0 + (e - head);
+                dst[c] = __ldg(srow + c);
+            }
+        }
+    } else {
         const long long base = bz * P.img_plane;
         for (int r = warp; r < P.in_rows; r += D2_WARPS) {
             const int gy = s_iy[r];
