@@ -36,7 +36,8 @@ SYMBOLS = [
     "b2f_version", "b2f_last_error", "b2f_is_device_library", "b2f_set_device", "b2f_device_count",
     "b2f_malloc", "b2f_free", "b2f_host_alloc", "b2f_host_free", "b2f_memcpy_h2d", "b2f_memcpy_d2h",
     "b2f_sync", "b2f_ipc_export", "b2f_ipc_open", "b2f_ipc_close", "b2f_imfilter", "b2f_imgradients", "b2f_mapwindow_extrema", "b2f_imfilter_slab",
-    "b2f_findlocalextrema", "b2f_scale_into_slice", "b2f_maxabs", "b2f_gather",
+    "b2f_findlocalextrema", "b2f_scale_into_slice", "b2f_maxabs", "b2f_gather", "b2f_na_prepare", "b2f_divide",
+    "b2f_normalize_dims",
     "b2f_launch_count", "b2f_reset_launch_count", "b2f_last_path",
 ]
 
@@ -189,6 +190,10 @@ class Library:
             C.POINTER(C.c_int64), C.c_void_p]
         d.b2f_scale_into_slice.argtypes = [C.POINTER(b2f_array), C.POINTER(b2f_array), C.c_int64, C.c_double, C.c_void_p]
         d.b2f_maxabs.argtypes = [C.POINTER(b2f_array), C.POINTER(C.c_double), C.c_void_p]
+        d.b2f_na_prepare.argtypes = [C.POINTER(b2f_array), C.c_int32, C.POINTER(b2f_array), C.POINTER(b2f_array),
+                                     C.POINTER(C.c_int32), C.c_void_p]
+        d.b2f_divide.argtypes = [C.POINTER(b2f_array), C.POINTER(b2f_array), C.c_void_p]
+        d.b2f_normalize_dims.argtypes = [C.POINTER(b2f_array), C.POINTER(C.POINTER(C.c_double)), C.c_void_p]
         d.b2f_gather.argtypes = [C.POINTER(b2f_array), C.POINTER(C.c_int64), C.c_int64, C.POINTER(C.c_double), C.c_void_p]
 
     # -- helpers ---------------------------------------------------------------------------
@@ -298,6 +303,21 @@ class Library:
         self.check(self.dll.b2f_gather(C.byref(arr), idx.ctypes.data_as(C.POINTER(C.c_int64)), idx.size,
                                        out.ctypes.data_as(C.POINTER(C.c_double)), C.c_void_p(stream)))
         return out
+
+    # -- NA() border pieces --------------------------------------------------------------------
+    def na_prepare(self, img: b2f_array, na_mode: int, imgtmp=None, valid=None, stream: int = 0) -> bool:
+        h = C.c_int32()
+        self.check(self.dll.b2f_na_prepare(C.byref(img), na_mode, C.byref(imgtmp) if imgtmp is not None else None,
+                                           C.byref(valid) if valid is not None else None, C.byref(h), C.c_void_p(stream)))
+        return bool(h.value)
+
+    def divide(self, out: b2f_array, den: b2f_array, stream: int = 0):
+        self.check(self.dll.b2f_divide(C.byref(out), C.byref(den), C.c_void_p(stream)))
+
+    def normalize_dims(self, out: b2f_array, factors, stream: int = 0):
+        keep = [np.ascontiguousarray(f, dtype=np.float64) for f in factors]
+        arr = (C.POINTER(C.c_double) * len(keep))(*[k.ctypes.data_as(C.POINTER(C.c_double)) for k in keep])
+        self.check(self.dll.b2f_normalize_dims(C.byref(out), arr, C.c_void_p(stream)))
 
     # -- raw device memory (arrays that never leave the GPU between calls) ------------------------
     def malloc(self, nbytes: int) -> int:

@@ -99,10 +99,23 @@ class NoPad(AbstractBorder):
 
 
 class NA(AbstractBorder):
-    """NA() borders are two FIR calls and a divide (src/imfilter.jl:282-318); not accelerated yet."""
+    """NA(na=isnan): "Not Available" boundary conditions (src/border.jl:389-405): out-of-range and NA-flagged elements do
+    not contribute, the result is renormalised by the weight of the elements that did (src/imfilter.jl:282-318).
+    The predicate cannot cross the C ABI as a closure; the three predicates the reference exercises are modes:
+    NA() / NA("isnan"), NA("!isfinite"), NA("never") (= `x -> false`)."""
+    MODES = {"isnan": 0, "!isfinite": 1, "never": 2}
+
+    def __init__(self, na="isnan"):
+        if na not in self.MODES:
+            raise _abi.NotSupportedError(f"NA({na!r}): only {sorted(self.MODES)} are available on the device")
+        self.na = na
+        self.mode = self.MODES[na]
+
+    def __repr__(self):
+        return f"NA({self.na})"
 
     def to_abi(self, ndim):
-        raise _abi.NotSupportedError("NA() border is outside the accelerated path")
+        raise _abi.ArgumentError("NA() is resolved by imfilter itself (two Fill(0) passes and a division), not by the pad")
 
 
 def borderinstance(border):

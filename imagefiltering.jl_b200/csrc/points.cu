@@ -4,6 +4,8 @@
 //   b2f_scale_into_slice   multiLoG's slice write and `.*= -σ`     reference src/extrema.jl:94-105
 //   b2f_maxabs             maximum(abs, img)                      reference src/extrema.jl:85
 //   b2f_gather             img_LoG[x] at the peaks                reference src/extrema.jl:86-90
+//   b2f_na_prepare / b2f_divide / b2f_normalize_dims   the element-wise pieces of the NA() border (§8f rank 2)
+//                                                                 reference src/imfilter.jl:282-318, 1110-1127, 1234-1250
 //
 // All of it is data-parallel compare / copy work: one thread per element, coalesced along the first axis, HBM-bound.
 // The peak list comes back in the reference's order (column-major ascending): per-block counts, one scan, an ordered
@@ -138,6 +140,54 @@ __global__ void pt_maxabs_kernel(const void *img, int dt, long long n, unsigned 
 __global__ void pt_gather_kernel(const void *arr, int dt, const long long *idx, long long n, double *out) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = load_elem<double>(arr, dt, idx[i]);
+}
+
+// ---- NA() border (reference src/imfilter.jl:282-318, 1110-1127, 1234-1250): the element-wise pieces around the two FIR calls ----
+__device__ __forceinline__ bool pt_is_na(double v, int mode) {      // 0: isnan, 1: !isfinite, 2: never
+    return mode == 0 ? (v != v) : mode == 1 ? !(fabs(v) <= 1.79769313486231570815e308) : false;
+}
+__global__ void pt_na_prepare_kernel(const void *img, int dt, long long n, int mode, void *imgtmp, int tdt, void *valid, int vdt,
+                                     int *hasna) {
+    bool any = false;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const double v = load_elem<double>(img, dt, i);
+        const bool na = pt_is_na(v, mode);
+        any = any || na;
+        if (imgtmp) {                                   // imgtmp[naflag] .= zero(T)
+            if (tdt == B2F_F32) ((float *)imgtmp)[i] = na ? 0.f : (dt == B2F_N0F8 ? n0f8_to_f32(((const uint8_t *)img)[i]) : (float)v);
+            else ((double *)imgtmp)[i] = na ? 0.0 : v;
+        }
+        if (valid) {                                    // validpixels = !naflag
+            if (vdt == B2F_F32) ((float *)valid)[i] = na ? 0.f : 1.f;
+            else ((double *)valid)[i] = na ? 0.0 : 1.0;
+        }
+    }
+    if (__any_sync(0xffffffffu, any) && (threadIdx.x & 31) == 0) atomicOr(hasna, 1);
+}
+__global__ void pt_divide_kernel(void *out, int odt, const void *den, int ddt, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        if (odt == B2F_F32 && ddt == B2F_F32) ((float *)out)[i] = __fdiv_rn(((float *)out)[i], ((const float *)den)[i]);
+        else {                                          // promoted to Float64, stored as eltype(out)
+            const double q = __ddiv_rn(load_elem<double>(out, odt, i), load_elem<double>(den, ddt, i));
+            if (odt == B2F_F32) ((float *)out)[i] = (float)q; else ((double *)out)[i] = q;
+        }
+    }
+}
+struct PtFactors { const double *f[B2F_MAXDIM]; long long dims[B2F_MAXDIM]; int ndim; };
+__global__ void pt_normalize_dims_kernel(void *out, int odt, long long n, PtFactors F) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        long long r = i;
+        double t = load_elem<double>(out, odt, i);      // tmp = A[I] / f1[I1]; tmp /= f2[I2]; ...  (src/imfilter.jl:1241-1250)
+#pragma unroll
+        for (int d = 0; d < B2F_MAXDIM; ++d) {
+            if (d < F.ndim) {
+                const long long c = r % F.dims[d];
+                r /= F.dims[d];
+                t = __ddiv_rn(t, F.f[d][c]);
+            }
+        }
+        if (odt == B2F_F32) ((float *)out)[i] = (float)t; else ((double *)out)[i] = t;
+    }
 }
 
 static long long numel(const b2f_array *a) {
@@ -298,6 +348,122 @@ int b2f_gather(const b2f_array *arr, const int64_t *idx, int64_t n, double *valu
     if (d_out) cudaFreeAsync(d_out, st);
     release(sin, st);
     if (e != cudaSuccess) return fail(B2F_ECUDA, "gather failed: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+int b2f_na_prepare(const b2f_array *img, int32_t na_mode, const b2f_array *imgtmp, const b2f_array *valid, int32_t *hasna,
+                   void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!img || !hasna) return fail(B2F_EARG, "NULL argument");
+    if (na_mode < 0 || na_mode > 2) return fail(B2F_EARG, "na_mode must be 0 (isnan), 1 (!isfinite) or 2 (never)");
+    const long long n = numel(img);
+    for (const b2f_array *a : {imgtmp, valid}) {
+        if (!a) continue;
+        if (a->dtype != B2F_F32 && a->dtype != B2F_F64) return fail(B2F_EARG, "imgtmp / valid must be Float32 or Float64");
+        if (numel(a) != n) return fail(B2F_EDIM, "imgtmp / valid must have the axes of img");
+        if (a->mem != img->mem) return fail(B2F_ENOTSUP, "img, imgtmp and valid must live in the same memory space");
+    }
+    *hasna = 0;
+    set_path("na_prepare");
+    if (n == 0) return 0;
+    int rc = ensure_ctx();
+    if (rc) return rc;
+    Staged sin, st1, st2;
+    rc = stage_in(img, sin, st, true);
+    if (!rc && imgtmp) rc = stage_in(imgtmp, st1, st, false);
+    if (!rc && valid) rc = stage_in(valid, st2, st, false);
+    int *flag = nullptr;
+    cudaError_t e = rc ? cudaSuccess : cudaMallocAsync((void **)&flag, 4, st);
+    if (!rc && e == cudaSuccess) e = cudaMemsetAsync(flag, 0, 4, st);
+    if (!rc && e == cudaSuccess) {
+        const long long blocks = (n + 255) / 256;
+        pt_na_prepare_kernel<<<(unsigned)(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, st>>>(
+            sin.dptr, img->dtype, n, na_mode, imgtmp ? st1.dptr : nullptr, imgtmp ? imgtmp->dtype : 0, valid ? st2.dptr : nullptr,
+            valid ? valid->dtype : 0, flag);
+        count_launch();
+        e = cudaGetLastError();
+    }
+    int h = 0;
+    if (!rc && e == cudaSuccess) e = cudaMemcpyAsync(&h, flag, 4, cudaMemcpyDeviceToHost, st);
+    if (!rc && e == cudaSuccess && imgtmp && imgtmp->mem == B2F_HOST) e = cudaMemcpyAsync(imgtmp->ptr, st1.dptr, st1.bytes, cudaMemcpyDeviceToHost, st);
+    if (!rc && e == cudaSuccess && valid && valid->mem == B2F_HOST) e = cudaMemcpyAsync(valid->ptr, st2.dptr, st2.bytes, cudaMemcpyDeviceToHost, st);
+    if (!rc && e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (flag) cudaFreeAsync(flag, st);
+    release(sin, st); release(st1, st); release(st2, st);
+    if (rc) return rc;
+    if (e != cudaSuccess) return fail(B2F_ECUDA, "na_prepare failed: %s", cudaGetErrorString(e));
+    *hasna = h;
+    return 0;
+}
+
+int b2f_divide(const b2f_array *out, const b2f_array *den, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!out || !den) return fail(B2F_EARG, "NULL argument");
+    if ((out->dtype != B2F_F32 && out->dtype != B2F_F64) || (den->dtype != B2F_F32 && den->dtype != B2F_F64))
+        return fail(B2F_ENOTSUP, "divide takes Float32 / Float64 arrays");
+    const long long n = numel(out);
+    if (numel(den) != n) return fail(B2F_EDIM, "out and den must have the same axes");
+    set_path("divide");
+    if (n == 0) return 0;
+    int rc = ensure_ctx();
+    if (rc) return rc;
+    Staged so, sd;
+    rc = stage_in(out, so, st, true);
+    if (!rc) rc = stage_in(den, sd, st, true);
+    cudaError_t e = cudaSuccess;
+    if (!rc) {
+        const long long blocks = (n + 255) / 256;
+        pt_divide_kernel<<<(unsigned)(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, st>>>(so.dptr, out->dtype, sd.dptr, den->dtype, n);
+        count_launch();
+        e = cudaGetLastError();
+        if (e == cudaSuccess && out->mem == B2F_HOST) {
+            e = cudaMemcpyAsync(out->ptr, so.dptr, so.bytes, cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        }
+    }
+    release(so, st); release(sd, st);
+    if (rc) return rc;
+    if (e != cudaSuccess) return fail(B2F_ECUDA, "divide failed: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+int b2f_normalize_dims(const b2f_array *out, const double *const *factors, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!out || !factors) return fail(B2F_EARG, "NULL argument");
+    if (out->dtype != B2F_F32 && out->dtype != B2F_F64) return fail(B2F_ENOTSUP, "normalize_dims takes a Float32 / Float64 array");
+    if (out->ndim < 1 || out->ndim > B2F_MAXDIM) return fail(B2F_ENOTSUP, "ndim %d not supported", out->ndim);
+    const long long n = numel(out);
+    set_path("normalize_dims");
+    if (n == 0) return 0;
+    int rc = ensure_ctx();
+    if (rc) return rc;
+    Staged so;
+    rc = stage_in(out, so, st, true);
+    if (rc) return rc;
+    PtFactors F;
+    memset(&F, 0, sizeof F);
+    F.ndim = out->ndim;
+    long long total = 0;
+    for (int d = 0; d < out->ndim; ++d) { F.dims[d] = out->dims[d]; total += out->dims[d]; if (!factors[d]) { release(so, st); return fail(B2F_EARG, "NULL factor"); } }
+    double *d_f = nullptr;
+    cudaError_t e = cudaMallocAsync((void **)&d_f, (size_t)total * 8, st);
+    long long off = 0;
+    for (int d = 0; d < out->ndim && e == cudaSuccess; ++d) {
+        e = cudaMemcpyAsync(d_f + off, factors[d], (size_t)out->dims[d] * 8, cudaMemcpyHostToDevice, st);
+        F.f[d] = d_f + off;
+        off += out->dims[d];
+    }
+    if (e == cudaSuccess) {
+        const long long blocks = (n + 255) / 256;
+        pt_normalize_dims_kernel<<<(unsigned)(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, st>>>(so.dptr, out->dtype, n, F);
+        count_launch();
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess && out->mem == B2F_HOST) e = cudaMemcpyAsync(out->ptr, so.dptr, so.bytes, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);       // the factor vectors are host memory of the caller
+    if (d_f) cudaFreeAsync(d_f, st);
+    release(so, st);
+    if (e != cudaSuccess) return fail(B2F_ECUDA, "normalize_dims failed: %s", cudaGetErrorString(e));
     return 0;
 }
 

@@ -17,7 +17,7 @@ import numpy as np
 
 from . import _abi
 from ._abi import ArgumentError, DimensionMismatch, NotSupportedError
-from .border import AbstractBorder, Fill, Inner, NoPad, Pad, borderinstance
+from .border import AbstractBorder, Fill, Inner, NA, NoPad, Pad, borderinstance
 from .device import DeviceArray
 from .kernel import Laplacian
 from .kernelfactors import ReshapedOneD
@@ -139,7 +139,7 @@ def build_stages(kernel, ndim):
             ln[k.Npre] = k.data.shape[0]
             lo[k.Npre] = k.data.first[0]
             stages.append(dict(kind=_abi.STAGE_1D, axis=k.Npre, ndim=ndim, tap_dtype=_tap_dtype(k.dtype),
-                               len=ln, lo=lo, taps=k.data.parent))
+                               len=ln, lo=lo, taps=k.data.parent, reshaped=True))
             continue
         if isinstance(k, OffsetArray):
             p, first = k.parent, list(k.first)
@@ -328,8 +328,68 @@ def _run(r, out, img_desc, ndim, stages, border, roi, library):
     odesc, keep = _as_output(out)
     if odesc.ndim != ndim:
         raise DimensionMismatch(f"out has {odesc.ndim} dims, img has {ndim}")
+    if isinstance(border, NA):
+        if roi is not None:
+            raise NotSupportedError("NA() with inds is not available")
+        return _run_na(L, odesc, img_desc, ndim, stages, border)
     sl = _abi.StageList(stages)
     L.imfilter(img_desc, odesc, sl, border.to_abi(ndim), roi)
+
+
+def _run_na(L, odesc, img_desc, ndim, stages, border):
+    """imfilter!(r, out, img, kernel, NA(na))  (src/imfilter.jl:282-318): flags -> separable or inseparable NA filtering.
+    Every array operation is a call into the library; this function only sequences them."""
+    if odesc.dtype not in (_abi.F32, _abi.F64):
+        raise NotSupportedError("NA() needs a Float32 / Float64 output (the renormalising division)")
+    dims = [int(odesc.dims[d]) for d in range(ndim)]
+    if [int(img_desc.dims[d]) for d in range(ndim)] != dims:
+        raise DimensionMismatch("NA(): out must have the axes of img")
+    sl = _abi.StageList(stages)
+    fill0 = Fill(0).to_abi(ndim)
+    can_na = img_desc.dtype in (_abi.F32, _abi.F64)                 # Integer / fixed-point images cannot hold NaN
+    separable = all(st["kind"] == _abi.STAGE_1D and (st.get("reshaped") or sum(1 for n in st["len"] if n > 1) == 1)
+                    for st in stages)                               # isseparable, src/imfilter.jl:1219
+    hasna = L.na_prepare(img_desc, border.mode) if can_na else False
+    if separable and not hasna:                                     # imfilter_na_separable!, :1123-1127
+        if len(stages) != ndim:
+            raise TypeError("MethodError: no method matching normalize_separable! (one kernel factor per dimension)")
+        L.imfilter(img_desc, odesc, sl, fill0)
+        factors = []
+        for d in range(ndim):                                       # normalize_separable!, :1234-1239
+            st = stages[d]
+            ax = st["axis"]
+            ones, res = np.ones(dims[d]), np.empty(dims[d])
+            one_d = dict(kind=_abi.STAGE_1D, axis=0, ndim=1, tap_dtype=st["tap_dtype"], len=[st["len"][ax]],
+                         lo=[st["lo"][ax]], taps=st["taps"])
+            L.imfilter(_abi.numpy_array_desc(ones, (1,)), _abi.numpy_array_desc(res, (1,)), _abi.StageList([one_d]),
+                       Fill(0).to_abi(1))
+            factors.append(res)
+        L.normalize_dims(odesc, factors)
+        return
+    # imfilter_na_inseparable!, :1110-1121: temporaries live where img lives
+    n = int(np.prod(dims))
+    esz = _abi.DTYPE_SIZE[odesc.dtype]
+    origin = [int(img_desc.origin[d]) for d in range(ndim)]
+    owned, keep = [], []
+    try:
+        def temp():
+            if img_desc.mem == _abi.DEVICE:
+                p = L.malloc(n * esz)
+                owned.append(p)
+                return _abi.make_array(p, odesc.dtype, dims, origin, _abi.DEVICE)
+            a = np.empty(dims, dtype=_abi.DTYPE_TO_NP[odesc.dtype], order="F")
+            keep.append(a)
+            return _abi.numpy_array_desc(a, origin)
+        imgtmp, valid, vp = temp(), temp(), temp()
+        L.na_prepare(img_desc, border.mode if can_na else NA.MODES["never"], imgtmp, valid)
+        L.imfilter(imgtmp, odesc, sl, fill0)
+        L.imfilter(valid, vp, sl, fill0)
+        L.divide(odesc, vp)
+    finally:
+        if owned:
+            L.check(L.dll.b2f_sync())
+        for p in owned:
+            L.free(p)
 
 
 def imgradients(img, kernelfun, border="replicate", *, _library=None, T=None):

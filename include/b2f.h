@@ -225,6 +225,25 @@ int b2f_maxabs(const b2f_array *img, double *result, void *stream);
  * img_LoG[x] of the peaks (src/extrema.jl:86-90).  Synchronous. */
 int b2f_gather(const b2f_array *arr, const int64_t *idx, int64_t n, double *values, void *stream);
 
+/* ---- NA() border: the element-wise pieces around the two FIR calls -------------
+ * imfilter(img, kernel, NA(na)) (src/imfilter.jl:282-318) is: flag the NA elements; if the kernel is separable
+ * and nothing is flagged, filter with Fill(0) and divide by the per-axis responses to a vector of ones
+ * (imfilter_na_separable!, normalize_separable!/normalize_dims! :1123-1127,1234-1250); otherwise filter the image
+ * with the flagged elements zeroed and the validity mask, both with Fill(0), and divide (imfilter_na_inseparable!
+ * :1110-1121).  The FIR calls are b2f_imfilter; these three are the rest. */
+
+/* naflag = na.(img): na_mode 0 = isnan, 1 = !isfinite, 2 = never.  imgtmp (may be NULL) receives img with the
+ * flagged elements zeroed, converted to its eltype (F32/F64); valid (may be NULL) receives !naflag as 0/1 (F32/F64);
+ * *hasna = any(naflag).  Synchronous. */
+int b2f_na_prepare(const b2f_array *img, int32_t na_mode, const b2f_array *imgtmp, const b2f_array *valid, int32_t *hasna,
+                   void *stream);
+/* out[I] /= den[I] (src/imfilter.jl:1117-1119): Float32/Float32 divides in Float32, otherwise in Float64, stored as
+ * eltype(out). */
+int b2f_divide(const b2f_array *out, const b2f_array *den, void *stream);
+/* normalize_dims!(A, factors) (src/imfilter.jl:1241-1250): A[I] = (A[I] / f1[I1]) / f2[I2] ... with one HOST Float64
+ * vector of length dims[d] per axis.  Synchronous. */
+int b2f_normalize_dims(const b2f_array *out, const double *const *factors, void *stream);
+
 /* number of CUDA kernels launched by this library on the calling thread since the last reset
  * (the oracle library always reports 0) */
 int64_t b2f_launch_count(void);

@@ -1155,3 +1155,70 @@ int b2f_gather(const b2f_array *arr, const int64_t *idx, int64_t n, double *valu
 }
 
 }  // extern "C"
+
+// ---- NA() border pieces (reference src/imfilter.jl:282-318, 1110-1127, 1234-1250) ---------------------------------
+extern "C" {
+
+int b2f_na_prepare(const b2f_array *img, int32_t na_mode, const b2f_array *imgtmp, const b2f_array *valid, int32_t *hasna, void *) {
+    if (!img || !hasna) return fail(B2F_EARG, "NULL argument");
+    if (na_mode < 0 || na_mode > 2) return fail(B2F_EARG, "na_mode must be 0 (isnan), 1 (!isfinite) or 2 (never)");
+    const int64_t n = o_numel(img);
+    for (const b2f_array *a : {imgtmp, valid}) {
+        if (!a) continue;
+        if (a->dtype != B2F_F32 && a->dtype != B2F_F64) return fail(B2F_EARG, "imgtmp / valid must be Float32 or Float64");
+        if (o_numel(a) != n) return fail(B2F_EDIM, "imgtmp / valid must have the axes of img");
+    }
+    int any = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        const double v = o_elem(img, i);
+        const bool na = na_mode == 0 ? (v != v) : na_mode == 1 ? !std::isfinite(v) : false;
+        any |= na ? 1 : 0;
+        if (imgtmp) {
+            if (imgtmp->dtype == B2F_F32)
+                ((float *)imgtmp->ptr)[i] = na ? 0.f : (img->dtype == B2F_N0F8 ? (float)((const uint8_t *)img->ptr)[i] / 255.0f : (float)v);
+            else
+                ((double *)imgtmp->ptr)[i] = na ? 0.0 : (img->dtype == B2F_N0F8 ? v / 255.0 : v);
+        }
+        if (valid) {
+            if (valid->dtype == B2F_F32) ((float *)valid->ptr)[i] = na ? 0.f : 1.f;
+            else ((double *)valid->ptr)[i] = na ? 0.0 : 1.0;
+        }
+    }
+    *hasna = any;
+    return 0;
+}
+
+int b2f_divide(const b2f_array *out, const b2f_array *den, void *) {
+    if (!out || !den) return fail(B2F_EARG, "NULL argument");
+    if ((out->dtype != B2F_F32 && out->dtype != B2F_F64) || (den->dtype != B2F_F32 && den->dtype != B2F_F64))
+        return fail(B2F_ENOTSUP, "divide takes Float32 / Float64 arrays");
+    const int64_t n = o_numel(out);
+    if (o_numel(den) != n) return fail(B2F_EDIM, "out and den must have the same axes");
+    for (int64_t i = 0; i < n; ++i) {
+        if (out->dtype == B2F_F32 && den->dtype == B2F_F32) ((float *)out->ptr)[i] = ((float *)out->ptr)[i] / ((const float *)den->ptr)[i];
+        else {
+            const double q = o_elem(out, i) / o_elem(den, i);
+            if (out->dtype == B2F_F32) ((float *)out->ptr)[i] = (float)q; else ((double *)out->ptr)[i] = q;
+        }
+    }
+    return 0;
+}
+
+int b2f_normalize_dims(const b2f_array *out, const double *const *factors, void *) {
+    if (!out || !factors) return fail(B2F_EARG, "NULL argument");
+    if (out->dtype != B2F_F32 && out->dtype != B2F_F64) return fail(B2F_ENOTSUP, "normalize_dims takes a Float32 / Float64 array");
+    const int64_t n = o_numel(out);
+    for (int64_t i = 0; i < n; ++i) {
+        int64_t r = i;
+        double t = o_elem(out, i);
+        for (int d = 0; d < out->ndim; ++d) {
+            const int64_t c = r % out->dims[d];
+            r /= out->dims[d];
+            t = t / factors[d][c];
+        }
+        if (out->dtype == B2F_F32) ((float *)out->ptr)[i] = (float)t; else ((double *)out->ptr)[i] = t;
+    }
+    return 0;
+}
+
+}  // extern "C"

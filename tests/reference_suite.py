@@ -531,6 +531,35 @@ def check_blob_log(ifb, lib):
 
 
 
-ALL_CHECKS = [check_local_extrema, check_blob_log, check_padarray, check_1d, check_widening, check_prewitt_tiling, check_impulse_interior,
+def check_na_border(ifb, lib):
+    """reference test/border.jl:271-285 ("NA") and test/2d.jl:147-226 (NA targets of the corner impulse, dense and
+    factored kernels)."""
+    nan, inf = np.nan, np.inf
+    r = ifb.imfilter(np.arange(1, 11, dtype=np.float64), ifb.centered(np.array([1, 1, 1]) / 3), ifb.NA(), _library=lib)
+    assert approx(r, [1.5, 2, 3, 4, 5, 6, 7, 8, 9, 9.5])
+    x = np.array([1, nan, inf, 0, -inf, inf, nan, nan, 1.0])
+    k = ifb.OffsetArray.with_first(np.array([1, 1]), (0,))
+    same = lambda a, b: np.array_equal(np.asarray(a), np.asarray(b, dtype=np.float64), equal_nan=True)
+    assert same(ifb.imfilter(x, k, ifb.NA(), _library=lib), [1, inf, inf, -inf, nan, inf, nan, 1, 1])
+    assert same(ifb.imfilter(x, k, ifb.NA("!isfinite"), _library=lib), [1, nan, 0, 0, nan, nan, nan, 1, 1])
+    assert same(ifb.imfilter(x, k, ifb.NA("never"), _library=lib), [nan, nan, inf, -inf, nan, nan, nan, nan, 1])
+    assert same(ifb.imfilter(np.arange(1, 6, dtype=np.float64), ifb.centered(np.array([1])), ifb.NA(), _library=lib), [1, 2, 3, 4, 5])
+    kern = np.array([[0.1, 0.2], [0.4, 0.5]])
+    dense = ifb.OffsetArray.with_first(kern, (-1, 1))
+    factored = (ifb.OffsetArray.with_first(np.array([0.2, 0.8]), (-1,)), ifb.OffsetArray.with_first(np.array([[0.3, 0.6]]), (0, 1)))
+    for kernel, kk in ((dense, kern), (factored, np.outer([0.2, 0.8], [0.3, 0.6]))):
+        for img in (np.zeros((5, 7)), np.zeros((5, 7), dtype=np.int64)):
+            img[0, 1] = 1
+            target = np.zeros((5, 7))
+            target[0, 0] = kk[1, 0] / (kk[1, 0] + kk[1, 1])
+            target[1, 0] = kk[0, 0] / kk.sum()
+            for T in (None, np.float32):
+                r = ifb.imfilter(img, kernel, ifb.NA(), _library=lib) if T is None else ifb.imfilter(T, img, kernel, ifb.NA(), _library=lib)
+                assert np.all(np.isnan(r[:, -1]))          # the kernel lies entirely in the padding there
+                ok = approx if T is None else approx32
+                assert ok(r[:, :-1], target[:, :-1])
+
+
+ALL_CHECKS = [check_local_extrema, check_blob_log, check_na_border, check_padarray, check_1d, check_widening, check_prewitt_tiling, check_impulse_interior,
               check_impulse_corner, check_offset_axes, check_nonfinite, check_3d_box, check_cascade,
               check_gradients, check_laplacian, check_extrema_goldens, check_mapwindow_offsets]

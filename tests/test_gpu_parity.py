@@ -470,3 +470,34 @@ def test_blob_log_parity(ifb, oracle, device):
             assert strong(got) == strong(ref) and len(strong(got)) >= 3
             amp = {b.location: b.amplitude for b in ref}
             assert all(abs(b.amplitude - amp[b.location]) <= 1e-5 for b in got if b.location in amp)
+
+
+@pytest.mark.parametrize("T", [np.float64, np.float32])
+def test_na_border_parity(ifb, oracle, device, T):
+    """NA() border (src/imfilter.jl:282-318): separable path (no NA present: Fill(0) + normalize_dims), inseparable path
+    (NaNs present, or a dense kernel: two Fill(0) passes and the division), host and device-resident arrays."""
+    import torch
+    rng = np.random.default_rng(21)
+    img = np.asfortranarray(rng.random((150, 90)).astype(T))
+    holes = img.copy(order="F")
+    holes.ravel(order="K")[rng.integers(0, img.size, 200)] = np.nan
+    sep = ifb.KernelFactors.gaussian((2, 1.5))
+    dense = ifb.Kernel.DoG((1.5, 1.5)) if hasattr(ifb.Kernel, "DoG") else ifb.Kernel.LoG(1.5)
+    vol = np.asfortranarray(rng.random((40, 30, 20)).astype(T))
+    for A, kern in ((img, sep), (holes, sep), (img, dense), (holes, dense), (vol, ifb.KernelFactors.gaussian((1, 1, 1)))):
+        got = ifb.imfilter(A, kern, ifb.NA())
+        ref = ifb.imfilter(A, kern, ifb.NA(), _library=oracle)
+        assert got.dtype == ref.dtype
+        if got.dtype == np.float64:
+            assert np.array_equal(got, ref, equal_nan=True)
+        else:
+            assert np.array_equal(np.isnan(got), np.isnan(ref))
+            assert np.nanmax(np.abs(got.astype(np.float64) - ref.astype(np.float64))) <= 1e-5
+    # device-resident in and out
+    t_in = torch.from_numpy(np.ascontiguousarray(holes.T)).cuda()
+    t_out = torch.empty(t_in.shape, dtype=torch.float64 if T == np.float64 else torch.float32, device="cuda")
+    if T == np.float64:
+        ifb.imfilter_(ifb.DeviceArray.from_torch(t_out), ifb.DeviceArray.from_torch(t_in), sep, ifb.NA())
+        torch.cuda.synchronize()
+        ref = ifb.imfilter(holes, sep, ifb.NA(), _library=oracle)
+        assert np.array_equal(t_out.cpu().numpy().T, ref, equal_nan=True)
