@@ -11,6 +11,7 @@ module at the repository root.
 from . import _abi, kernel as Kernel, kernelfactors as KernelFactors
 from ._abi import (ArgumentError, CudaError, DimensionMismatch, InexactError, NotSupportedError)
 from .border import Fill, Inner, NA, NoPad, Pad, borderinstance
+from .color import ColorArray
 from .device import DeviceArray
 from .imfilter import factorkernel, filter_type, imfilter, imfilter_, imgradients, padarray
 from .kernel import reflect
@@ -26,5 +27,5 @@ __all__ = [
     "imfilter_", "imgradients", "padarray", "mapwindow", "mapwindow_", "extrema", "minimum", "maximum", "centered",
     "OffsetArray", "reflect", "kernelfactors", "ReshapedOneD", "Algorithm", "CUDALibs", "CPU1",
     "CPUThreads", "DeviceArray", "n0f8", "N0f8Array", "filter_type", "factorkernel",
-    "findlocalmaxima", "findlocalminima", "blob_LoG", "BlobLoG", "DimensionMismatch", "ArgumentError", "InexactError", "NotSupportedError", "CudaError",
+    "ColorArray", "findlocalmaxima", "findlocalminima", "blob_LoG", "BlobLoG", "DimensionMismatch", "ArgumentError", "InexactError", "NotSupportedError", "CudaError",
 ]

@@ -18,10 +18,11 @@ import numpy as np
 from . import _abi
 from ._abi import ArgumentError, DimensionMismatch, NotSupportedError
 from .border import AbstractBorder, Fill, Inner, NA, NoPad, Pad, borderinstance
+from .color import ColorArray, lift_kernel
 from .device import DeviceArray
 from .kernel import Laplacian
 from .kernelfactors import ReshapedOneD
-from .n0f8 import N0f8Array
+from .n0f8 import N0f8Array, n0f8
 from .offsetarrays import OffsetArray, centered
 from .resources import AbstractResource, Alg, CUDALibs, FIR, FIRTiled
 
@@ -270,6 +271,8 @@ def imfilter(*args, _library=None):
     if r is not None and alg is not None:
         raise TypeError("MethodError: a resource and an algorithm cannot both be given")
     r = _resolve_resource(r, alg)
+    if isinstance(img, ColorArray):
+        return _imfilter_color(r, T, img, kernel, border, _library)
     if T is None:
         T = filter_type(img, kernel)
     T = np.dtype(T)
@@ -284,6 +287,28 @@ def imfilter(*args, _library=None):
     out = allocate_output(T, first, shape, stages, border)
     _run(r, out, desc, ndim, stages, border, None, _library)
     return out
+
+
+def _imfilter_color(r, T, img, kernel, border, library):
+    """imfilter on a colour image (RGB{N0f8}, RGB{Float32}, ...): every channel with the same kernel (the reference's
+    eltype arithmetic, src/imfilter.jl:1131-1154) = the N+1-d path with the kernel lifted past the channel axis."""
+    raw = n0f8(img.data) if img.data.dtype == np.uint8 else img.data
+    if not isinstance(kernel, tuple):
+        kernel = factorkernel(kernel)
+    lifted = lift_kernel(kernel)
+    if T is None:
+        T = filter_type(raw, lifted)            # RGB{N0f8} * Float64 -> RGB{Float64}: the channel type follows the scalar rule
+    T = np.dtype(T)
+    if isinstance(border, (Pad, Fill, Inner)) and border.lo:
+        border = type(border)(*((border.value,) if isinstance(border, Fill) else (border.style,) if isinstance(border, Pad) else ()),
+                              (0,) + tuple(border.lo), (0,) + tuple(border.hi))
+    desc, ndim, first, shape, keep = _as_input(raw)
+    stages = build_stages(lifted, ndim)
+    out = allocate_output(T, first, shape, stages, border)
+    _run(r, out, desc, ndim, stages, border, None, library, nlead=1)
+    if isinstance(out, OffsetArray):            # Inner(): the spatial axes shrink; the channel axis keeps index 1
+        return out
+    return ColorArray(out)
 
 
 def _resolve_resource(r, alg):
@@ -322,7 +347,7 @@ def imfilter_(*args, _library=None):
     return out
 
 
-def _run(r, out, img_desc, ndim, stages, border, roi, library):
+def _run(r, out, img_desc, ndim, stages, border, roi, library, nlead=0):
     from ._lib import lib
     L = library if library is not None else lib()
     odesc, keep = _as_output(out)
@@ -331,12 +356,12 @@ def _run(r, out, img_desc, ndim, stages, border, roi, library):
     if isinstance(border, NA):
         if roi is not None:
             raise NotSupportedError("NA() with inds is not available")
-        return _run_na(L, odesc, img_desc, ndim, stages, border)
+        return _run_na(L, odesc, img_desc, ndim, stages, border, nlead)
     sl = _abi.StageList(stages)
     L.imfilter(img_desc, odesc, sl, border.to_abi(ndim), roi)
 
 
-def _run_na(L, odesc, img_desc, ndim, stages, border):
+def _run_na(L, odesc, img_desc, ndim, stages, border, nlead=0):
     """imfilter!(r, out, img, kernel, NA(na))  (src/imfilter.jl:282-318): flags -> separable or inseparable NA filtering.
     Every array operation is a call into the library; this function only sequences them."""
     if odesc.dtype not in (_abi.F32, _abi.F64):
@@ -351,12 +376,12 @@ def _run_na(L, odesc, img_desc, ndim, stages, border):
                     for st in stages)                               # isseparable, src/imfilter.jl:1219
     hasna = L.na_prepare(img_desc, border.mode) if can_na else False
     if separable and not hasna:                                     # imfilter_na_separable!, :1123-1127
-        if len(stages) != ndim:
+        if len(stages) != ndim - nlead:
             raise TypeError("MethodError: no method matching normalize_separable! (one kernel factor per dimension)")
         L.imfilter(img_desc, odesc, sl, fill0)
-        factors = []
-        for d in range(ndim):                                       # normalize_separable!, :1234-1239
-            st = stages[d]
+        factors = [np.ones(dims[d]) for d in range(nlead)]          # colour channels: nothing to normalise along them
+        for d in range(nlead, ndim):                                # normalize_separable!, :1234-1239
+            st = stages[d - nlead]
             ax = st["axis"]
             ones, res = np.ones(dims[d]), np.empty(dims[d])
             one_d = dict(kind=_abi.STAGE_1D, axis=0, ndim=1, tap_dtype=st["tap_dtype"], len=[st["len"][ax]],

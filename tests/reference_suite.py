@@ -560,6 +560,35 @@ def check_na_border(ifb, lib):
                 assert ok(r[:, :-1], target[:, :-1])
 
 
-ALL_CHECKS = [check_local_extrema, check_blob_log, check_na_border, check_padarray, check_1d, check_widening, check_prewitt_tiling, check_impulse_interior,
+def check_color_images(ifb, lib):
+    """reference test/2d.jl:49-86 and :147-226 for `imgc = fill(RGB(0,0,0), 5, 7); imgc[...] = RGB(1,0,0)`: the red
+    channel equals the Gray result, the others stay zero, for every border incl. Inner() and NA()."""
+    g = G["impulse"]
+    kern = np.array(g["kern"])
+    dense = ifb.OffsetArray.with_first(kern, (g["kern_axes"][0][0], g["kern_axes"][1][0]))
+    fk = g["factored"]
+    fact = (ifb.OffsetArray.with_first(np.array(fk["k1"]), (fk["k1_first"],)),
+            ifb.OffsetArray.with_first(np.array([fk["k2"]]), (0, fk["k2_first"])))
+    for pos in ((2, 3), (0, 1)):
+        raw = np.zeros((3, 5, 7), dtype=np.uint8); raw[(0,) + pos] = 255
+        gray = np.zeros((5, 7), dtype=np.uint8); gray[pos] = 255
+        for kernel in (dense, fact):
+            for border in BORDERS + (ifb.Fill(0), ifb.NA(), ifb.Inner()):
+                for T in (None, np.float32):
+                    a = (ifb.ColorArray(raw), kernel, border)
+                    b = (ifb.n0f8(gray), kernel, border)
+                    rc = ifb.imfilter(*a, _library=lib) if T is None else ifb.imfilter(T, *a, _library=lib)
+                    rg = ifb.imfilter(*b, _library=lib) if T is None else ifb.imfilter(T, *b, _library=lib)
+                    cd = rc.data if isinstance(rc, ifb.ColorArray) else rc.parent
+                    gd = rg.parent if isinstance(rg, ifb.OffsetArray) else rg
+                    assert cd.dtype == gd.dtype and cd.shape == (3,) + gd.shape
+                    assert np.array_equal(cd[0], gd, equal_nan=True), (pos, border)
+                    if isinstance(border, ifb.NA):      # 0/0 where the kernel sees padding only, in every channel
+                        assert np.array_equal(np.isnan(cd[1]), np.isnan(gd)) and np.all(np.nan_to_num(cd[1:]) == 0)
+                    else:
+                        assert np.all(cd[1:] == 0)
+
+
+ALL_CHECKS = [check_local_extrema, check_blob_log, check_na_border, check_color_images, check_padarray, check_1d, check_widening, check_prewitt_tiling, check_impulse_interior,
               check_impulse_corner, check_offset_axes, check_nonfinite, check_3d_box, check_cascade,
               check_gradients, check_laplacian, check_extrema_goldens, check_mapwindow_offsets]

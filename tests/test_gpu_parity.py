@@ -501,3 +501,22 @@ def test_na_border_parity(ifb, oracle, device, T):
         torch.cuda.synchronize()
         ref = ifb.imfilter(holes, sep, ifb.NA(), _library=oracle)
         assert np.array_equal(t_out.cpu().numpy().T, ref, equal_nan=True)
+
+
+def test_color_image_parity(ifb, oracle, device):
+    """RGB{N0f8} / RGB{Float32} images = a leading channel axis (src/imfilter.jl:1131-1154 eltype arithmetic): each
+    channel equals the scalar result of that channel, bit-exact in Float64."""
+    rng = np.random.default_rng(31)
+    raw = np.asfortranarray(rng.integers(0, 256, size=(3, 97, 61), dtype=np.uint8))
+    for kern, border in ((ifb.KernelFactors.gaussian((2, 2)), "reflect"), (ifb.Kernel.LoG(1.0), "circular"),
+                         (ifb.KernelFactors.sobel((True, True), 1), ifb.Fill(0)), (ifb.KernelFactors.gaussian((1, 2)), ifb.NA())):
+        got = ifb.imfilter(ifb.ColorArray(raw), kern, border)
+        ref = ifb.imfilter(ifb.ColorArray(raw), kern, border, _library=oracle)
+        assert got.data.dtype == np.float64 and np.array_equal(got.data, ref.data, equal_nan=True)
+        for c in range(3):
+            one = ifb.imfilter(ifb.n0f8(np.asfortranarray(raw[c])), kern, border)
+            assert np.array_equal(got.channel(c), one, equal_nan=True), (c, border)
+    f = ifb.ColorArray(np.asfortranarray(rng.random((3, 64, 50), dtype=np.float32)))
+    got = ifb.imfilter(np.float32, f, ifb.KernelFactors.gaussian((2, 2)), "symmetric")
+    ref = ifb.imfilter(np.float32, f, ifb.KernelFactors.gaussian((2, 2)), "symmetric", _library=oracle)
+    assert np.max(np.abs(got.data.astype(np.float64) - ref.data)) <= 1e-5
