@@ -150,6 +150,31 @@ def main():
         ms = timeit(filt(vol, out, kf, ifb.Pad("symmetric")), max(2, args.steps // 2))
         report("c5", "1024^3 f32, gaussian((4,4,4)) 17x3 taps, Pad(:symmetric) -> f32", ms, n ** 3, 8)
 
+    if not only or "f1" in only:   # strict-peak scan and the blob_LoG pipeline (synchronous calls: wall clock)
+        import time
+        img = torch.rand((8192, 8192), device=dev, generator=g)
+        A = DA.from_torch(img)
+        for _ in range(2):
+            pk = ifb.findlocalmaxima(A, as_array=True)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(5):
+            pk = ifb.findlocalmaxima(A, as_array=True)
+        ms = (time.perf_counter() - t0) / 5 * 1e3
+        report("f1-peaks", f"findlocalmaxima, 8192^2 f32, 3x3 window -> {len(pk)} peaks (flags + scan + ordered scatter + D2H of the list)",
+               ms, 8192 * 8192, 5)
+        del img, A
+        blob = torch.rand((2048, 2048), device=dev, generator=g)
+        B = DA.from_torch(blob)
+        for _ in range(2):
+            bl = ifb.blob_LoG(B, [1.0, 2.0, 3.0], rthresh=0.5)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            bl = ifb.blob_LoG(B, [1.0, 2.0, 3.0], rthresh=0.5)
+        ms = (time.perf_counter() - t0) / 3 * 1e3
+        report("f1-blob", f"blob_LoG, 2048^2 f32, 3 sigmas (9x9, 17x17, 27x27 dense LoG + scan) -> {len(bl)} blobs", ms, 2048 * 2048, 4 + 3 * 4)
+
 
 if __name__ == "__main__":
     main()

@@ -278,7 +278,7 @@ class Library:
         n = 1
         for d in range(nd):
             n *= img.dims[d]
-        cap = max(1024, n // 64)
+        cap = max(1024, n // 8)         # a retry recomputes the scan: start above any realistic peak density
         while True:
             idx = np.empty(cap, dtype=np.int64)
             cnt = C.c_int64()

@@ -38,19 +38,18 @@ def _lib(_library):
     return lib()                        # raises when the CUDA extension is missing: no CPU path
 
 
+def _unravel_array(lin, shape):
+    """0-based column-major linear indices -> (n, N) int64 array of 1-based indices (Julia CartesianIndex rows)."""
+    if len(lin) == 0:
+        return np.empty((0, len(shape)), dtype=np.int64)
+    return np.stack(np.unravel_index(lin, shape, order="F"), axis=1).astype(np.int64) + 1
+
+
 def _unravel(lin, shape):
-    """0-based column-major linear indices -> list of 1-based index tuples (Julia CartesianIndex)."""
-    out = []
-    for v in lin.tolist():
-        idx = []
-        for n in shape:
-            idx.append(v % n + 1)
-            v //= n
-        out.append(tuple(idx))
-    return out
+    return list(map(tuple, _unravel_array(lin, shape).tolist()))
 
 
-def _findlocalextrema(minima, img, window, edges, _library):
+def _findlocalextrema(minima, img, window, edges, _library, as_array=False):
     desc, ndim, _first, shape, keep = _as_input(img)
     if window is None:
         window = (3,) * ndim            # default_window: 3 on every spatial axis (src/extrema.jl:107)
@@ -59,18 +58,19 @@ def _findlocalextrema(minima, img, window, edges, _library):
     if len(window) != ndim or len(edges) != ndim:
         raise ArgumentError("window and edges need one entry per dimension of img")
     lin = _lib(_library).findlocalextrema(desc, minima, window, edges)
-    return _unravel(lin, shape)
+    return _unravel_array(lin, shape) if as_array else _unravel(lin, shape)
 
 
-def findlocalmaxima(img, *, window=None, edges=True, _library=None):
+def findlocalmaxima(img, *, window=None, edges=True, as_array=False, _library=None):
     """findlocalmaxima(img; window=default_window(img), edges=true) -> Vector{CartesianIndex}
-    (src/extrema.jl:107-119): the elements larger than all of their neighbours inside the window."""
-    return _findlocalextrema(False, img, window, edges, _library)
+    (src/extrema.jl:107-119): the elements larger than all of their neighbours inside the window, as a list of 1-based
+    index tuples in the reference's order (`as_array=True`: the same rows as an (n, N) int64 array, no Python objects)."""
+    return _findlocalextrema(False, img, window, edges, _library, as_array)
 
 
-def findlocalminima(img, *, window=None, edges=True, _library=None):
+def findlocalminima(img, *, window=None, edges=True, as_array=False, _library=None):
     """src/extrema.jl:121-127."""
-    return _findlocalextrema(True, img, window, edges, _library)
+    return _findlocalextrema(True, img, window, edges, _library, as_array)
 
 
 def blob_LoG(img, σscales, *, edges=None, σshape=None, rthresh=1e-3, _library=None):
@@ -98,16 +98,16 @@ def blob_LoG(img, σscales, *, edges=None, σshape=None, rthresh=1e-3, _library=
     device = lib.is_device_library()
     owned = []
     try:
-        if device:
+        if device:                                                          # ONE device allocation for all temporaries
+            in_bytes = numel * _abi.DTYPE_SIZE[in_dt] if desc.mem == _abi.HOST else 0
+            in_bytes = (in_bytes + 255) // 256 * 256
+            base = lib.malloc(in_bytes + (S + 1) * numel * esz)
+            owned.append(base)
             if desc.mem == _abi.HOST:                                       # upload once, filter S times
-                dimg = lib.malloc(numel * _abi.DTYPE_SIZE[in_dt])
-                owned.append(dimg)
-                lib.check(lib.dll.b2f_memcpy_h2d(dimg, desc.ptr, numel * _abi.DTYPE_SIZE[in_dt]))
-                desc = _abi.make_array(dimg, in_dt, shape, first, _abi.DEVICE)
-            tmp_ptr = lib.malloc(numel * esz)
-            owned.append(tmp_ptr)
-            stack_ptr = lib.malloc(S * numel * esz)
-            owned.append(stack_ptr)
+                lib.check(lib.dll.b2f_memcpy_h2d(base, desc.ptr, numel * _abi.DTYPE_SIZE[in_dt]))
+                desc = _abi.make_array(base, in_dt, shape, first, _abi.DEVICE)
+            tmp_ptr = base + in_bytes
+            stack_ptr = tmp_ptr + numel * esz
             mem = _abi.DEVICE
         else:                                                               # the oracle library works on host arrays
             tmp_np = np.empty(shape, dtype=F, order="F")
@@ -130,14 +130,15 @@ def blob_LoG(img, σscales, *, edges=None, σshape=None, rthresh=1e-3, _library=
             lib.check(lib.dll.b2f_sync())
         for p in owned:
             lib.free(p)
-    locs = _unravel(peaks, (S,) + tuple(shape))
+    # the reference's comprehension (src/extrema.jl:86-90), thresholded on arrays before any Python object is made
+    sidx = peaks % S                                                         # x[1] - 1: the σ index is the leading axis
+    sig = np.asarray(sigmas)
+    if rthresh != 0:
+        athresh = rthresh / (sig ** N * float(np.prod(σshape)))              # src/extrema.jl:84
+        keep_mask = amps > athresh[sidx] * imgmax
+        peaks, amps, sidx = peaks[keep_mask], amps[keep_mask], sidx[keep_mask]
+    locs = _unravel_array(peaks, (S,) + tuple(shape))[:, 1:] + (np.asarray(first, dtype=np.int64) - 1)
     blobs = []
-    for x, a in zip(locs, amps.tolist()):
-        s = x[0] - 1
-        if rthresh != 0:
-            athresh = rthresh / (sigmas[s] ** N * float(np.prod(σshape)))    # src/extrema.jl:84
-            if not a > athresh * imgmax:
-                continue
-        loc = tuple(i + f - 1 for i, f in zip(x[1:], first))
-        blobs.append(BlobLoG(loc, tuple(sigmas[s] * t for t in σshape), F(a).item() if F == np.float32 else a))
+    for loc, s, a in zip(locs.tolist(), sidx.tolist(), amps.tolist()):
+        blobs.append(BlobLoG(tuple(loc), tuple(sigmas[s] * t for t in σshape), F(a).item() if F == np.float32 else a))
     return blobs
