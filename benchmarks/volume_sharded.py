@@ -35,7 +35,7 @@ def main():
     ap.add_argument("--planes", type=int, default=0, help="planes along the sharded axis (default: n)")
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--mode", default="p2p", choices=["p2p", "sendrecv"])
+    ap.add_argument("--mode", default="p2p", choices=["p2p", "staged", "sendrecv"])
     ap.add_argument("--nosync", action="store_true", help="p2p: skip the per-step entry barrier (static inputs)")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -35,7 +35,8 @@ DTYPE_TO_NP[N0F8] = np.dtype(np.uint8)
 SYMBOLS = [
     "b2f_version", "b2f_last_error", "b2f_is_device_library", "b2f_set_device", "b2f_device_count",
     "b2f_malloc", "b2f_free", "b2f_host_alloc", "b2f_host_free", "b2f_memcpy_h2d", "b2f_memcpy_d2h",
-    "b2f_sync", "b2f_ipc_export", "b2f_ipc_open", "b2f_ipc_close", "b2f_imfilter", "b2f_imgradients", "b2f_mapwindow_extrema", "b2f_imfilter_slab",
+    "b2f_sync", "b2f_ipc_export", "b2f_ipc_open", "b2f_ipc_close", "b2f_imfilter", "b2f_imgradients", "b2f_mapwindow_extrema", "b2f_imfilter_slab", "b2f_imfilter_slab_staged", "b2f_memcpy_async", "b2f_memcpy2d_async",
+    "b2f_memset_async",
     "b2f_findlocalextrema", "b2f_scale_into_slice", "b2f_maxabs", "b2f_gather", "b2f_na_prepare", "b2f_divide",
     "b2f_normalize_dims",
     "b2f_launch_count", "b2f_reset_launch_count", "b2f_last_path",
@@ -185,6 +186,13 @@ class Library:
             C.POINTER(b2f_array), C.POINTER(b2f_array), C.POINTER(b2f_stage), C.c_int32,
             C.POINTER(b2f_border), C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]
 
+        d.b2f_imfilter_slab_staged.argtypes = [
+            C.POINTER(b2f_array), C.POINTER(b2f_array), C.POINTER(b2f_stage), C.c_int32,
+            C.POINTER(b2f_border), C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+            C.c_int32, C.c_int32, C.c_void_p]
+        d.b2f_memcpy2d_async.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p]
+        d.b2f_memcpy_async.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
+        d.b2f_memset_async.argtypes = [C.c_void_p, C.c_int32, C.c_uint64, C.c_void_p]
         d.b2f_findlocalextrema.argtypes = [
             C.POINTER(b2f_array), C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.c_int64,
             C.POINTER(C.c_int64), C.c_void_p]
@@ -268,6 +276,23 @@ class Library:
                                               C.byref(border), global_last_dim, slab_first,
                                               C.c_void_p(halo_lo or None), n_halo_lo,
                                               C.c_void_p(halo_hi or None), n_halo_hi, C.c_void_p(stream)))
+
+    def imfilter_slab_staged(self, img: b2f_array, out: b2f_array, stages: StageList, border: b2f_border,
+                             global_last_dim: int, slab_first: int, halo_lo: int, n_halo_lo: int, halo_hi: int,
+                             n_halo_hi: int, flag_lo: int, flag_hi: int, epoch: int, lo_early_rows: int = 0, stream: int = 0):
+        self.check(self.dll.b2f_imfilter_slab_staged(C.byref(img), C.byref(out), stages.arr, stages.n, C.byref(border),
+                                                     global_last_dim, slab_first, C.c_void_p(halo_lo or None), n_halo_lo,
+                                                     C.c_void_p(halo_hi or None), n_halo_hi, C.c_void_p(flag_lo or None),
+                                                     C.c_void_p(flag_hi or None), epoch, lo_early_rows, C.c_void_p(stream)))
+
+    def memcpy_async(self, dst: int, src: int, nbytes: int, stream: int = 0):
+        self.check(self.dll.b2f_memcpy_async(C.c_void_p(dst), C.c_void_p(src), nbytes, C.c_void_p(stream)))
+
+    def memcpy2d_async(self, dst: int, dpitch: int, src: int, spitch: int, width: int, height: int, stream: int = 0):
+        self.check(self.dll.b2f_memcpy2d_async(C.c_void_p(dst), dpitch, C.c_void_p(src), spitch, width, height, C.c_void_p(stream)))
+
+    def memset_async(self, dptr: int, byte: int, nbytes: int, stream: int = 0):
+        self.check(self.dll.b2f_memset_async(C.c_void_p(dptr), byte, nbytes, C.c_void_p(stream)))
 
     # -- local extrema / blob_LoG plumbing -----------------------------------------------------
     def findlocalextrema(self, img: b2f_array, minima: bool, window, edges, stream: int = 0) -> np.ndarray:

@@ -260,10 +260,10 @@ using namespace b2f;
 // planes [slab_first, slab_first + own_n); halo_lo / halo_hi hold n_halo_lo / n_halo_hi RAW input planes logically
 // below / above them (receive buffers, or the neighbour's memory mapped over NVLink).  Semantics = the owned planes of
 // b2f_imfilter on the whole array.
-extern "C" int b2f_imfilter_slab(const b2f_array *img, const b2f_array *out, const b2f_stage *stages, int32_t nstages,
-                                 const b2f_border *border, int64_t global_last_dim, int64_t slab_first,
-                                 const void *halo_lo, int64_t n_halo_lo, const void *halo_hi, int64_t n_halo_hi,
-                                 void *stream) {
+static int imfilter_slab_impl(const b2f_array *img, const b2f_array *out, const b2f_stage *stages, int32_t nstages,
+                              const b2f_border *border, int64_t global_last_dim, int64_t slab_first, const void *halo_lo,
+                              int64_t n_halo_lo, const void *halo_hi, int64_t n_halo_hi, const void *flag_lo,
+                              const void *flag_hi, int32_t epoch, int32_t lo_early_rows, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (!img || !out || !border || !stages) return fail(B2F_EARG, "NULL argument");
     if (img->mem != B2F_DEVICE || out->mem != B2F_DEVICE) return fail(B2F_EARG, "b2f_imfilter_slab works on device arrays");
@@ -304,7 +304,11 @@ extern "C" int b2f_imfilter_slab(const b2f_array *img, const b2f_array *out, con
     rc = 0;
     if (stream3d_applicable(P, img->dtype, out->dtype)) {
         set_path("stream3d_slab");
-        return run_stream3d_slab(P, img->ptr, halo_lo, n_halo_lo, halo_hi, n_halo_hi, slab_first, own_n, out->ptr, st);
+        return run_stream3d_slab(P, img->ptr, halo_lo, n_halo_lo, halo_hi, n_halo_hi, slab_first, own_n, out->ptr, st, flag_lo, flag_hi,
+                                 epoch, lo_early_rows);
+    }
+    if (flag_lo || flag_hi) {
+        return fail(B2F_ENOTSUP, "staged halos are available for the fused Float32 3-D kernel only");
     }
     // general separable cascade: gather [halo_lo; own; halo_hi] once, then one streamed pass per stage; the pass along
     // the sharded axis evaluates the border in GLOBAL plane coordinates and keeps only the owned planes
@@ -331,3 +335,43 @@ extern "C" int b2f_imfilter_slab(const b2f_array *img, const b2f_array *out, con
     if (ext) cudaFreeAsync(ext, st);
     return rc;
 }
+
+extern "C" {
+
+int b2f_imfilter_slab(const b2f_array *img, const b2f_array *out, const b2f_stage *stages, int32_t nstages,
+                      const b2f_border *border, int64_t global_last_dim, int64_t slab_first, const void *halo_lo,
+                      int64_t n_halo_lo, const void *halo_hi, int64_t n_halo_hi, void *stream) {
+    return imfilter_slab_impl(img, out, stages, nstages, border, global_last_dim, slab_first, halo_lo, n_halo_lo, halo_hi,
+                              n_halo_hi, nullptr, nullptr, 0, 0, stream);
+}
+
+// Staged form: halo_lo / halo_hi are LOCAL buffers that copy engines are still filling when the kernel starts (peer ->
+// local copies on another stream, each followed by a one-byte write of `epoch` to flag_lo / flag_hi).  The kernel
+// starts at once and only the CTA about to read a halo plane waits for its flag, so the NVLink transfer runs at copy
+// speed (no tile over-fetch) underneath the marches instead of stalling them in bursts.  The lower halo, which the first
+// wave of CTAs needs at once, comes in two parts: rows [0, lo_early_rows) of every plane first (flag_lo[0]), then the rest
+// (flag_lo[1]); a CTA waits for the part its tile rows lie in.
+int b2f_imfilter_slab_staged(const b2f_array *img, const b2f_array *out, const b2f_stage *stages, int32_t nstages,
+                             const b2f_border *border, int64_t global_last_dim, int64_t slab_first, const void *halo_lo,
+                             int64_t n_halo_lo, const void *halo_hi, int64_t n_halo_hi, const void *flag_lo,
+                             const void *flag_hi, int32_t epoch, int32_t lo_early_rows, void *stream) {
+    if ((n_halo_lo > 0 && !flag_lo) || (n_halo_hi > 0 && !flag_hi)) return fail(B2F_EARG, "NULL halo flag");
+    if (epoch < 1 || epoch > 255) return fail(B2F_EARG, "epoch must be 1..255");
+    return imfilter_slab_impl(img, out, stages, nstages, border, global_last_dim, slab_first, halo_lo, n_halo_lo, halo_hi,
+                              n_halo_hi, flag_lo, flag_hi, epoch, lo_early_rows, stream);
+}
+
+int b2f_memcpy_async(void *dst, const void *src, uint64_t bytes, void *stream) {
+    B2F_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, (cudaStream_t)stream));
+    return 0;
+}
+int b2f_memcpy2d_async(void *dst, uint64_t dpitch, const void *src, uint64_t spitch, uint64_t width, uint64_t height, void *stream) {
+    B2F_CUDA(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, height, cudaMemcpyDefault, (cudaStream_t)stream));
+    return 0;
+}
+int b2f_memset_async(void *dptr, int32_t byte, uint64_t bytes, void *stream) {
+    B2F_CUDA(cudaMemsetAsync(dptr, byte, bytes, (cudaStream_t)stream));
+    return 0;
+}
+
+}  // extern "C"

@@ -77,6 +77,8 @@ static int s3_launch_one(S3Params &P, const float *kz, cudaStream_t st) {
     if (tma && P.lo_n > 0) tma = s3_make_map(&m_lo, P.lo, P.W, P.H, P.lo_n, C::RH);
     if (tma && P.hi_n > 0) tma = s3_make_map(&m_hi, P.hi, P.W, P.H, P.hi_n, C::RH);
     P.use_tma = tma ? 1 : 0;
+    if (!tma && (P.flag_lo || P.flag_hi))
+        return fail(B2F_ENOTSUP, "staged halos need the TMA path (row length a multiple of 4, 16-byte aligned buffers)");
     // cp.async.bulk.tensor wants the box to start on a 16-byte boundary of the innermost axis (found the hard way:
     // "illegal instruction" otherwise), so the tile grid is shifted left by xsh = klox mod 4 columns
     P.xsh = tma ? ((P.klox % 4) + 4) % 4 : 0;
@@ -96,9 +98,14 @@ static int s3_launch_one(S3Params &P, const float *kz, cudaStream_t st) {
 
 // `own` holds planes [own_first, own_first+own_n) of a volume with Zg planes; lo/hi hold lo_n/hi_n planes below/above.
 int run_stream3d_slab(const Plan &Pl, const void *own, const void *lo, int64_t lo_n, const void *hi, int64_t hi_n,
-                      int64_t own_first, int64_t own_n, void *d_out, cudaStream_t st) {
+                      int64_t own_first, int64_t own_n, void *d_out, cudaStream_t st, const void *flag_lo, const void *flag_hi,
+                      int epoch, int lo_early_rows) {
     S3Params P;
     memset(&P, 0, sizeof P);
+    P.flag_lo = lo_n > 0 ? (const unsigned char *)flag_lo : nullptr;
+    P.flag_hi = hi_n > 0 ? (const unsigned char *)flag_hi : nullptr;
+    P.epoch = epoch;
+    P.lo_early_rows = lo_early_rows;
     P.own = (const float *)own; P.lo = (const float *)lo; P.hi = (const float *)hi;
     P.own_first = (int)own_first; P.own_n = (int)own_n; P.lo_n = (int)lo_n; P.hi_n = (int)hi_n;
     P.Zg = (int)Pl.img_ax.len(2);

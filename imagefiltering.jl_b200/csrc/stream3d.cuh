@@ -61,6 +61,10 @@ struct S3Params {
     int nfull, kch;                // the first nfull tiles march all planes in one CTA, the others are cut into kch chunks
     int vec_out;                   // 8-byte stores are aligned
     int xsh;                       // tiles start at x = 32*tx - xsh, so that the TMA box starts on a 16-byte boundary
+    // staged halos: lo / hi are LOCAL buffers being filled by copy engines while this kernel runs; *flag == epoch once the
+    // buffer is complete (NULL: the planes are there already)
+    const unsigned char *flag_lo, *flag_hi;   // flag_lo[0]: rows [0, lo_early_rows) of every lower halo plane, flag_lo[1]: the rest
+    int epoch, lo_early_rows;
     int use_tma;                   // the tensor maps are valid (else every cell comes through the gather loader)
     float kx[S3_MAXTAPS], ky[S3_MAXTAPS];
     float kzr[S3_MAXTAPS];         // z taps RIGHT-aligned in the instantiation's LBZ slots
@@ -338,8 +342,15 @@ stream3d_kernel(const __grid_constant__ S3Params P, const __grid_constant__ CUte
     locate_block(qb, S3_PTA);               // planes -2 .. PTA-3; the loop refills PTB planes at a time, PTA ahead
     __syncthreads();
 
+    bool lo_ready = P.flag_lo == nullptr, hi_ready = P.flag_hi == nullptr;     // thread 0 only
+    auto wait_flag = [&](const unsigned char *f) {
+        while (*reinterpret_cast<const volatile unsigned char *>(f) != (unsigned char)P.epoch) __nanosleep(64);
+        __threadfence_system();
+    };
     auto issue = [&](int p) {                   // one thread: TMA of input plane p into its ring buffer
         const int which = ptw[p & (S3_PT - 1)];
+        if (which == 1 && !lo_ready) { wait_flag(P.flag_lo + (ya + in_rows > P.lo_early_rows ? 1 : 0)); lo_ready = true; }
+        if (which == 2 && !hi_ready) { wait_flag(P.flag_hi); hi_ready = true; }
         const int zc = which < 0 ? P.own_n : ptz[p & (S3_PT - 1)];         // Fill(0) plane: out of range reads zero
         const void *map = which == 1 ? (const void *)&m_lo : which == 2 ? (const void *)&m_hi : (const void *)&m_own;
         const int b = p & (N - 1);

@@ -14,6 +14,10 @@ Two halo transports, same kernel entry (`b2f_imfilter_slab`, include/b2f.h):
               directly with peer loads while it streams its own planes — the exchange is fused into
               the compute kernel, no halo buffers, no copy kernels.  Per call only a stream-ordered
               barrier is needed (the neighbours' inputs must be complete before they are read).
+  "staged"    the neighbours' slabs are mapped as for "p2p", but the boundary planes are pulled into local halo buffers by
+              the COPY ENGINES on a side stream (dense copies at link speed, no tile over-fetch) while the filter kernel
+              is already marching; a CTA waits on a one-byte flag only when it is about to read its first halo plane
+              (`b2f_imfilter_slab_staged`).  Same barrier as "p2p".
   "sendrecv"  `dist.batch_isend_irecv` of the boundary planes into receive buffers (NCCL over NVLink;
               gloo on CPU tensors in the tests), then the same kernel with the buffers as halos.
 
@@ -125,7 +129,7 @@ class ShardedImfilter:
         self.plane_elems = int(np.prod(slab.shape[1:]))
         if mode == "auto":
             mode = "p2p" if (slab.is_cuda and self.world > 1) else "sendrecv"
-        if mode not in ("p2p", "sendrecv"):
+        if mode not in ("p2p", "staged", "sendrecv"):
             raise ArgumentError(f"unknown halo transport {mode!r}")
         self.mode = mode
         self._opened = []
@@ -133,9 +137,17 @@ class ShardedImfilter:
         self.recv_lo = self.recv_hi = None
         self._nccl = self.world > 1 and dist.get_backend(group) == "nccl"
         self._flag = torch.zeros(1, dtype=torch.int32, device=slab.device) if self._nccl else None
-        if self.world > 1 and (self.lower is not None or self.upper is not None or mode == "p2p"):
+        self._epoch = 0
+        if self.world > 1 and (self.lower is not None or self.upper is not None or mode in ("p2p", "staged")):
             if mode == "p2p":
                 self._setup_p2p()
+            elif mode == "staged":
+                self._setup_p2p()
+                self.peer_lo_ptr, self.peer_hi_ptr = self.halo_lo_ptr, self.halo_hi_ptr
+                self._setup_sendrecv()                 # local halo buffers; halo_*_ptr now point at them
+                self._flags = torch.zeros(4, dtype=torch.uint8, device=slab.device)    # lo early, lo rest, hi, (pad)
+                self._side = torch.cuda.Stream(device=slab.device)
+                self._ev_go, self._ev_done = torch.cuda.Event(), torch.cuda.Event()
             else:
                 self._setup_sendrecv()
 
@@ -226,6 +238,8 @@ class ShardedImfilter:
         (only valid when the neighbours' inputs are known to be complete and unchanged)."""
         t = self.torch
         stream = t.cuda.current_stream().cuda_stream if self.slab.is_cuda else 0
+        if self.world > 1 and self.mode == "staged":
+            return self._run_staged(sync, stream)
         if self.world > 1:
             if self.mode == "p2p":
                 if sync:
@@ -239,8 +253,63 @@ class ShardedImfilter:
             self.halo_hi_ptr, self.h_hi if self.upper is not None else 0, stream)
         return self.out
 
+    def _run_staged(self, sync, stream):
+        """barrier -> [side stream: peer -> local halo copies, each followed by its flag byte] || [main stream: the kernel,
+        whose CTAs wait for a flag only when they reach a halo plane] -> main stream joins the side stream."""
+        t = self.torch
+        if sync:
+            self.barrier()
+        self._epoch = self._epoch % 255 + 1
+        main = t.cuda.current_stream()
+        self._ev_go.record(main)
+        self._side.wait_event(self._ev_go)
+        side = self._side.cuda_stream
+        esz = self.slab.element_size()
+        flags = self._flags.data_ptr()
+        # copy order = the order of need: the rows of the lower halo that the first wave of tiles reads, then the upper halo
+        # (read when the first marches end), then the rest of the lower halo
+        row_bytes = int(self.slab.shape[-1]) * esz
+        nrows = self.plane_elems // int(self.slab.shape[-1])
+        plane_bytes = self.plane_elems * esz
+        early = 0
+        if self.lower is not None and self.ndim == 3:
+            tiles_x = -(-int(self.slab.shape[-1]) // 32)
+            early = min(nrows, (-(-148 // tiles_x) + 1) * 64)               # tile rows of the first wave (+1 for the halo rows)
+            if early >= nrows:
+                early = 0
+        if self.lower is not None:
+            if early:
+                self.lib.memcpy2d_async(self.halo_lo_ptr, plane_bytes, self.peer_lo_ptr, plane_bytes, early * row_bytes, self.h_lo, side)
+                self.lib.memset_async(flags, self._epoch, 1, side)
+        if self.upper is not None:
+            self.lib.memcpy_async(self.halo_hi_ptr, self.peer_hi_ptr, self.h_hi * plane_bytes, side)
+            self.lib.memset_async(flags + 2, self._epoch, 1, side)
+        if self.lower is not None:
+            if early:
+                self.lib.memcpy2d_async(self.halo_lo_ptr + early * row_bytes, plane_bytes, self.peer_lo_ptr + early * row_bytes,
+                                        plane_bytes, (nrows - early) * row_bytes, self.h_lo, side)
+            else:
+                self.lib.memcpy_async(self.halo_lo_ptr, self.peer_lo_ptr, self.h_lo * plane_bytes, side)
+            self.lib.memset_async(flags + 1, self._epoch, 1, side)
+        self._ev_done.record(self._side)
+        try:
+            self.lib.imfilter_slab_staged(
+                _desc(self.slab, self.n0f8), _desc(self.out), self.stages, self.border.to_abi(self.ndim),
+                self.global_planes, self.first,
+                self.halo_lo_ptr, self.h_lo if self.lower is not None else 0,
+                self.halo_hi_ptr, self.h_hi if self.upper is not None else 0,
+                flags, flags + 2, self._epoch, early, stream)
+            main.wait_event(self._ev_done)
+        except NotSupportedError:
+            # not the fused Float32 3-D kernel (or not TMA-capable): same result through direct peer reads from now on
+            main.wait_event(self._ev_done)
+            self.mode = "p2p"
+            self.halo_lo_ptr, self.halo_hi_ptr = self.peer_lo_ptr, self.peer_hi_ptr
+            return self.run(sync=False)
+        return self.out
+
     def close(self):
-        if self.world > 1 and self.mode == "p2p":
+        if self.world > 1 and self.mode in ("p2p", "staged"):
             self.barrier()                      # nobody may still be reading my planes
             if self.slab.is_cuda:
                 self.torch.cuda.synchronize()

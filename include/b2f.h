@@ -198,6 +198,28 @@ int b2f_imfilter_slab(const b2f_array *img, const b2f_array *out,
                       const void *halo_hi, int64_t n_halo_hi,
                       void *stream);
 
+/* Staged form of b2f_imfilter_slab: halo_lo / halo_hi are LOCAL buffers that are still being filled when the call is
+ * made — typically by b2f_memcpy_async from the neighbour's mapped memory on another stream, each copy followed by
+ * b2f_memset_async(flag, epoch, 1, that_stream).  The kernel starts immediately; a CTA waits for `*flag_lo == epoch`
+ * (`*flag_hi`) only when it is about to read the first plane of that halo, so the NVLink transfer proceeds at copy
+ * speed underneath the computation.  The lower halo is split: flag_lo[0] covers rows [0, lo_early_rows) of every
+ * plane (what the first wave of tiles reads; copy it first), flag_lo[1] the remaining rows; lo_early_rows = 0 puts
+ * everything under flag_lo[1].  epoch in 1..255, different from the value the flags hold from the previous call.
+ * Fused Float32 3-D path only (B2F_ENOTSUP otherwise: use b2f_imfilter_slab). */
+int b2f_imfilter_slab_staged(const b2f_array *img, const b2f_array *out,
+                             const b2f_stage *stages, int32_t nstages,
+                             const b2f_border *border,
+                             int64_t global_last_dim, int64_t slab_first,
+                             const void *halo_lo, int64_t n_halo_lo,
+                             const void *halo_hi, int64_t n_halo_hi,
+                             const void *flag_lo, const void *flag_hi, int32_t epoch, int32_t lo_early_rows,
+                             void *stream);
+/* stream-ordered device copies / byte fills (peer-mapped pointers allowed): the halo staging of the sharded path */
+int b2f_memcpy_async(void *dst, const void *src, uint64_t bytes, void *stream);
+int b2f_memcpy2d_async(void *dst, uint64_t dpitch, const void *src, uint64_t spitch, uint64_t width, uint64_t height,
+                       void *stream);
+int b2f_memset_async(void *dptr, int32_t byte, uint64_t bytes, void *stream);
+
 /* ---- consumers of the LoG path ------------------------------------------ */
 
 /* findlocalmaxima(img; window, edges) / findlocalminima  (src/extrema.jl:107-164, loop :125-162).

@@ -1222,3 +1222,14 @@ int b2f_normalize_dims(const b2f_array *out, const double *const *factors, void 
 }
 
 }  // extern "C"
+
+// staged slab form / stream-ordered copies: device-only features; the oracle exports the symbols and declines
+extern "C" {
+int b2f_imfilter_slab_staged(const b2f_array *, const b2f_array *, const b2f_stage *, int32_t, const b2f_border *, int64_t, int64_t,
+                             const void *, int64_t, const void *, int64_t, const void *, const void *, int32_t, int32_t, void *) {
+    return fail(B2F_ENOTSUP, "oracle library has no copy engines: use b2f_imfilter_slab");
+}
+int b2f_memcpy_async(void *, const void *, uint64_t, void *) { return fail(B2F_ENOTSUP, "oracle library has no device memory"); }
+int b2f_memcpy2d_async(void *, uint64_t, const void *, uint64_t, uint64_t, uint64_t, void *) { return fail(B2F_ENOTSUP, "oracle library has no device memory"); }
+int b2f_memset_async(void *, int32_t, uint64_t, void *) { return fail(B2F_ENOTSUP, "oracle library has no device memory"); }
+}

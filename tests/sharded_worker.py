@@ -25,6 +25,8 @@ def cases(ifb):
     out.append(("f64-3d-asym", np.float64, (24, 18, 21), (g((1, 1, 1))[0], g((1, 1, 1))[1],
                 ifb.ReshapedOneD(3, 2, ifb.OffsetArray.with_first(rng.random(4), (-1,)))), "symmetric", None))
     out.append(("f32-3d-17taps", np.float32, (70, 45, 40), g((4, 4, 4)), "symmetric", None))
+    out.append(("f32-3d-tma", np.float32, (64, 80, 37), g((2, 2, 2)), "reflect", None))        # wide enough for the TMA / staged path
+    out.append(("f32-3d-tma17", np.float32, (128, 96, 48), g((4, 4, 4)), "circular", None))
     out.append(("f32-2d", np.float32, (33, 29), g((1, 2)), "reflect", None))
     out.append(("f32-3d-uneven", np.float32, (20, 12, 31), g((1, 1, 2)), "circular", [20, 11]))
     out.append(("f64-3d-xy-only", np.float64, (20, 12, 16), (g((1, 1, 0))[0], g((1, 1, 0))[1]), "replicate", None))

@@ -3,7 +3,8 @@
 CPU suite (gloo, host tensors): the per-slab compute is the oracle library, so what is tested is sharded.py's host
 logic — partition, neighbours (incl. the circular wrap), message order, halo sizes, global-coordinate borders.
 GPU suite (-m gpu): the same worker with the product library on cuda:0, both halo transports ("p2p" = CUDA IPC peer
-pointers read by the fused kernel, "sendrecv" = exchanged halo buffers)."""
+pointers read by the fused kernel, "staged" = copy-engine staging overlapped with the kernel behind flag bytes, "sendrecv" =
+exchanged halo buffers)."""
 import pytest
 
 from sharded_worker import launch
@@ -35,4 +36,4 @@ def test_slab_bounds_and_halo_extent(ifb):
 @pytest.mark.gpu
 @pytest.mark.parametrize("world", [2, 3])
 def test_sharded_device_two_ranks_one_gpu(world):
-    _check(launch(world, use_device=True, modes=["p2p", "sendrecv"]), world)
+    _check(launch(world, use_device=True, modes=["p2p", "staged", "sendrecv"]), world)
