@@ -128,7 +128,7 @@ class ShardedImfilter:
         self.out = out
         self.plane_elems = int(np.prod(slab.shape[1:]))
         if mode == "auto":
-            mode = "p2p" if (slab.is_cuda and self.world > 1) else "sendrecv"
+            mode = "staged" if (slab.is_cuda and self.world > 1) else "sendrecv"   # falls back to "p2p" reads when unsupported
         if mode not in ("p2p", "staged", "sendrecv"):
             raise ArgumentError(f"unknown halo transport {mode!r}")
         self.mode = mode
