@@ -63,7 +63,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(self.index), "-lms", "20"], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -205,16 +205,22 @@ def ours_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # clocks / throttle reasons are sampled from before the warm-up to the end of the timed region (the timed region of a
+    # short run is only a few ms long: sampling it alone could return no sample at all)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.1)
     for _ in range(args.warmup):
         step()
     barrier()
     assert lib.last_path().endswith("_grad"), lib.last_path()
     kernel_path = lib.last_path()
-
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-        time.sleep(0.25)
+    t_load = time.time()
+    while time.time() - t_load < 0.3:       # untimed: keep the GPU under the same load until the sampler has readings
+        for _ in range(10):
+            step()
+        torch.cuda.synchronize()
     lib.reset_launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
@@ -316,7 +322,7 @@ def ours_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     args = ap.parse_args()
