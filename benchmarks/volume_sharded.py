@@ -36,6 +36,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--mode", default="p2p", choices=["p2p", "staged", "sendrecv"])
+    ap.add_argument("--allreduce-barrier", action="store_true", help="p2p/staged: all-reduce entry barrier instead of the neighbour hand-shake")
     ap.add_argument("--nosync", action="store_true", help="p2p: skip the per-step entry barrier (static inputs)")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -75,7 +76,7 @@ def main():
     first, cnt = sh.slab_bounds(nz, world, rank)
     g.manual_seed(1000 + rank)
     slab = torch.rand((cnt, n, n), device=dev, generator=g)
-    f = sh.ShardedImfilter(slab, kern, border, mode=args.mode)
+    f = sh.ShardedImfilter(slab, kern, border, mode=args.mode, handshake=not args.allreduce_barrier)
     stream = torch.cuda.current_stream()
 
     def barrier():

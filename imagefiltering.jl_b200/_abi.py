@@ -36,7 +36,7 @@ SYMBOLS = [
     "b2f_version", "b2f_last_error", "b2f_is_device_library", "b2f_set_device", "b2f_device_count",
     "b2f_malloc", "b2f_free", "b2f_host_alloc", "b2f_host_free", "b2f_memcpy_h2d", "b2f_memcpy_d2h",
     "b2f_sync", "b2f_ipc_export", "b2f_ipc_open", "b2f_ipc_close", "b2f_imfilter", "b2f_imgradients", "b2f_mapwindow_extrema", "b2f_imfilter_slab", "b2f_imfilter_slab_staged", "b2f_memcpy_async", "b2f_memcpy2d_async",
-    "b2f_memset_async",
+    "b2f_memset_async", "b2f_stream_write32", "b2f_stream_wait_geq32",
     "b2f_findlocalextrema", "b2f_scale_into_slice", "b2f_maxabs", "b2f_gather", "b2f_na_prepare", "b2f_divide",
     "b2f_normalize_dims",
     "b2f_launch_count", "b2f_reset_launch_count", "b2f_last_path",
@@ -193,6 +193,8 @@ class Library:
         d.b2f_memcpy2d_async.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p]
         d.b2f_memcpy_async.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
         d.b2f_memset_async.argtypes = [C.c_void_p, C.c_int32, C.c_uint64, C.c_void_p]
+        d.b2f_stream_write32.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
+        d.b2f_stream_wait_geq32.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
         d.b2f_findlocalextrema.argtypes = [
             C.POINTER(b2f_array), C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.c_int64,
             C.POINTER(C.c_int64), C.c_void_p]
@@ -290,6 +292,12 @@ class Library:
 
     def memcpy2d_async(self, dst: int, dpitch: int, src: int, spitch: int, width: int, height: int, stream: int = 0):
         self.check(self.dll.b2f_memcpy2d_async(C.c_void_p(dst), dpitch, C.c_void_p(src), spitch, width, height, C.c_void_p(stream)))
+
+    def stream_write32(self, dptr: int, value: int, stream: int = 0):
+        self.check(self.dll.b2f_stream_write32(C.c_void_p(dptr), value, C.c_void_p(stream)))
+
+    def stream_wait_geq32(self, dptr: int, value: int, stream: int = 0):
+        self.check(self.dll.b2f_stream_wait_geq32(C.c_void_p(dptr), value, C.c_void_p(stream)))
 
     def memset_async(self, dptr: int, byte: int, nbytes: int, stream: int = 0):
         self.check(self.dll.b2f_memset_async(C.c_void_p(dptr), byte, nbytes, C.c_void_p(stream)))

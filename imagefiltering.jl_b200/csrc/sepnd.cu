@@ -369,6 +369,28 @@ int b2f_memcpy2d_async(void *dst, uint64_t dpitch, const void *src, uint64_t spi
     B2F_CUDA(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, height, cudaMemcpyDefault, (cudaStream_t)stream));
     return 0;
 }
+// stream memory operations (cuStreamWriteValue32 / cuStreamWaitValue32, reached through the runtime): a rank signals its
+// neighbours by a 32-bit write into their (peer-mapped) flag words and waits on its own — no kernel, no collective
+typedef int (*s_memop_fn)(cudaStream_t, unsigned long long, unsigned int, unsigned int);
+static s_memop_fn s_memop(const char *name) {
+    void *f = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint(name, &f, cudaEnableDefault, &qr) != cudaSuccess || qr != cudaDriverEntryPointSuccess) f = nullptr;
+    return (s_memop_fn)f;
+}
+int b2f_stream_write32(void *dptr, uint32_t value, void *stream) {
+    static s_memop_fn fn = s_memop("cuStreamWriteValue32");
+    if (!fn) return fail(B2F_ENOTSUP, "cuStreamWriteValue32 is unavailable");
+    if (fn((cudaStream_t)stream, (unsigned long long)(uintptr_t)dptr, value, 0) != 0) return fail(B2F_ECUDA, "cuStreamWriteValue32 failed");
+    return 0;
+}
+int b2f_stream_wait_geq32(void *dptr, uint32_t value, void *stream) {
+    static s_memop_fn fn = s_memop("cuStreamWaitValue32");
+    if (!fn) return fail(B2F_ENOTSUP, "cuStreamWaitValue32 is unavailable");
+    if (fn((cudaStream_t)stream, (unsigned long long)(uintptr_t)dptr, value, 0 /* CU_STREAM_WAIT_VALUE_GEQ */) != 0)
+        return fail(B2F_ECUDA, "cuStreamWaitValue32 failed");
+    return 0;
+}
 int b2f_memset_async(void *dptr, int32_t byte, uint64_t bytes, void *stream) {
     B2F_CUDA(cudaMemsetAsync(dptr, byte, bytes, (cudaStream_t)stream));
     return 0;

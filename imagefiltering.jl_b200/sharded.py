@@ -74,11 +74,12 @@ class ShardedImfilter:
     """
 
     def __init__(self, slab, kernel, border="replicate", *, out=None, group=None, mode="auto",
-                 out_dtype=None, n0f8=False, _library=None):
+                 out_dtype=None, n0f8=False, handshake=True, _library=None):
         import torch
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
         self.group = group
+        self.handshake = handshake          # p2p / staged: neighbour flag words instead of an all-reduce as the entry barrier
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         if _library is not None:
@@ -156,18 +157,32 @@ class ShardedImfilter:
         if not self.slab.is_cuda:
             raise ArgumentError('halo transport "p2p" needs CUDA tensors')
         handle, offset = self.lib.ipc_export(self.slab.data_ptr())
+        # neighbour hand-shake words: [0] written by my lower neighbour, [1] by my upper neighbour (step counters)
+        # (their own cudaMalloc: an IPC handle names a whole allocation, and torch packs small tensors into shared blocks)
+        self._sync_ptr = self.lib.malloc(8)
+        self.lib.memset_async(self._sync_ptr, 0, 8, 0)
+        self.lib.check(self.lib.dll.b2f_sync())
+        self._step = 0
+        self._peer_sync = {}
+        sh, so = self.lib.ipc_export(self._sync_ptr)
         infos = [None] * self.world
-        self.dist.all_gather_object(infos, (handle, offset), group=self.group)
+        self.dist.all_gather_object(infos, (handle, offset, sh, so), group=self.group)
+        for nb in {self.lower, self.upper} - {None}:
+            base = self.lib.ipc_open(infos[nb][2], infos[nb][3])
+            self._opened.append((base, infos[nb][3]))
+            self._peer_sync[nb] = base
+        infos = [(h, o) for h, o, _, _ in infos]
         esz = self.slab.element_size()
+        lower_base = None
         if self.lower is not None:      # the last h_lo planes of the lower neighbour lie just below mine
             h, off = infos[self.lower]
-            base = self.lib.ipc_open(h, off)
+            base = lower_base = self.lib.ipc_open(h, off)
             self._opened.append((base, off))
             self.halo_lo_ptr = base + (self.counts[self.lower] - self.h_lo) * self.plane_elems * esz
         if self.upper is not None:      # the first h_hi planes of the upper neighbour lie just above mine
             h, off = infos[self.upper]
-            if self.upper == self.lower and self._opened:
-                base = self._opened[0][0]
+            if self.upper == self.lower and lower_base is not None:
+                base = lower_base
             else:
                 base = self.lib.ipc_open(h, off)
                 self._opened.append((base, off))
@@ -220,17 +235,34 @@ class ShardedImfilter:
     def _grank(self, r):
         return self.dist.get_global_rank(self.group, r) if self.group is not None else r
 
-    def barrier(self):
+    def barrier(self, full=False):
         """All ranks' inputs are complete / all ranks have finished reading: stream-ordered on NCCL (a
         4-byte all-reduce on the current stream), host-side otherwise."""
         if self.world == 1:
             return
+        if not full and self.mode in ("p2p", "staged") and getattr(self, "_peer_sync", None) is not None and self.handshake:
+            return self._neighbour_handshake()
         if self._nccl:
             self.dist.all_reduce(self._flag, group=self.group)
         else:
             if self.slab.is_cuda:
                 self.torch.cuda.synchronize()
             self.dist.barrier(group=self.group)
+
+    def _neighbour_handshake(self):
+        """Only the neighbours' data is read, so only they are synchronised: write my step counter into their flag words
+        (a 32-bit stream-ordered write over NVLink) and make the stream wait until mine have reached it.  No kernel, no
+        collective; before REFILLING a slab call `barrier(full=True)`."""
+        self._step += 1
+        stream = self.torch.cuda.current_stream().cuda_stream
+        if self.lower is not None:
+            self.lib.stream_write32(self._peer_sync[self.lower] + 4, self._step, stream)     # I am its upper neighbour
+        if self.upper is not None:
+            self.lib.stream_write32(self._peer_sync[self.upper], self._step, stream)         # I am its lower neighbour
+        if self.lower is not None:
+            self.lib.stream_wait_geq32(self._sync_ptr, self._step, stream)
+        if self.upper is not None:
+            self.lib.stream_wait_geq32(self._sync_ptr + 4, self._step, stream)
 
     # -- execution --------------------------------------------------------------------------------------
     def run(self, sync=True):
@@ -310,12 +342,15 @@ class ShardedImfilter:
 
     def close(self):
         if self.world > 1 and self.mode in ("p2p", "staged"):
-            self.barrier()                      # nobody may still be reading my planes
+            self.barrier(full=True)             # nobody may still be reading my planes
             if self.slab.is_cuda:
                 self.torch.cuda.synchronize()
         for base, off in self._opened:
             self.lib.ipc_close(base, off)
         self._opened = []
+        if getattr(self, "_sync_ptr", 0):
+            self.lib.free(self._sync_ptr)
+            self._sync_ptr = 0
 
 
 def imfilter_sharded(slab, kernel, border="replicate", *, out=None, group=None, mode="auto", out_dtype=None,

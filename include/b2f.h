@@ -219,6 +219,10 @@ int b2f_memcpy_async(void *dst, const void *src, uint64_t bytes, void *stream);
 int b2f_memcpy2d_async(void *dst, uint64_t dpitch, const void *src, uint64_t spitch, uint64_t width, uint64_t height,
                        void *stream);
 int b2f_memset_async(void *dptr, int32_t byte, uint64_t bytes, void *stream);
+/* stream-ordered 32-bit signal / wait on device memory (peer-mapped pointers allowed): the neighbour hand-shake of the
+ * sharded path (a rank writes its step counter into its neighbours' flag words and waits until its own are >= it) */
+int b2f_stream_write32(void *dptr, uint32_t value, void *stream);
+int b2f_stream_wait_geq32(void *dptr, uint32_t value, void *stream);
 
 /* ---- consumers of the LoG path ------------------------------------------ */
 

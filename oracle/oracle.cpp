@@ -1231,5 +1231,7 @@ int b2f_imfilter_slab_staged(const b2f_array *, const b2f_array *, const b2f_sta
 }
 int b2f_memcpy_async(void *, const void *, uint64_t, void *) { return fail(B2F_ENOTSUP, "oracle library has no device memory"); }
 int b2f_memcpy2d_async(void *, uint64_t, const void *, uint64_t, uint64_t, uint64_t, void *) { return fail(B2F_ENOTSUP, "oracle library has no device memory"); }
+int b2f_stream_write32(void *, uint32_t, void *) { return fail(B2F_ENOTSUP, "oracle library has no device memory"); }
+int b2f_stream_wait_geq32(void *, uint32_t, void *) { return fail(B2F_ENOTSUP, "oracle library has no device memory"); }
 int b2f_memset_async(void *, int32_t, uint64_t, void *) { return fail(B2F_ENOTSUP, "oracle library has no device memory"); }
 }
