@@ -35,7 +35,7 @@ DTYPE_TO_NP[N0F8] = np.dtype(np.uint8)
 SYMBOLS = [
     "b2f_version", "b2f_last_error", "b2f_is_device_library", "b2f_set_device", "b2f_device_count",
     "b2f_malloc", "b2f_free", "b2f_host_alloc", "b2f_host_free", "b2f_memcpy_h2d", "b2f_memcpy_d2h",
-    "b2f_sync", "b2f_ipc_export", "b2f_ipc_open", "b2f_ipc_close", "b2f_imfilter", "b2f_imgradients", "b2f_mapwindow_extrema", "b2f_imfilter_slab", "b2f_imfilter_slab_staged", "b2f_memcpy_async", "b2f_memcpy2d_async",
+    "b2f_sync", "b2f_ipc_export", "b2f_ipc_open", "b2f_ipc_close", "b2f_imfilter", "b2f_imgradients", "b2f_mapwindow_extrema", "b2f_mapwindow_median", "b2f_imfilter_slab", "b2f_imfilter_slab_staged", "b2f_memcpy_async", "b2f_memcpy2d_async",
     "b2f_memset_async", "b2f_stream_write32", "b2f_stream_wait_geq32",
     "b2f_findlocalextrema", "b2f_scale_into_slice", "b2f_maxabs", "b2f_gather", "b2f_na_prepare", "b2f_divide",
     "b2f_normalize_dims",
@@ -182,6 +182,8 @@ class Library:
         d.b2f_mapwindow_extrema.argtypes = [
             C.POINTER(b2f_array), C.POINTER(b2f_array), C.POINTER(b2f_array), C.c_int32,
             C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(b2f_border), C.c_void_p]
+        d.b2f_mapwindow_median.argtypes = [
+            C.POINTER(b2f_array), C.POINTER(b2f_array), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(b2f_border), C.c_void_p]
         d.b2f_imfilter_slab.argtypes = [
             C.POINTER(b2f_array), C.POINTER(b2f_array), C.POINTER(b2f_stage), C.c_int32,
             C.POINTER(b2f_border), C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]
@@ -269,6 +271,11 @@ class Library:
             C.byref(img), C.byref(out_min) if out_min is not None else None,
             C.byref(out_max) if out_max is not None else None, 1 if interleaved else 0, lo, hi,
             C.byref(border), C.c_void_p(stream)))
+
+    def mapwindow_median(self, img: b2f_array, out: b2f_array, win_lo, win_hi, border: b2f_border, stream: int = 0):
+        lo = (C.c_int64 * MAXDIM)(*list(win_lo) + [0] * (MAXDIM - len(win_lo)))
+        hi = (C.c_int64 * MAXDIM)(*list(win_hi) + [0] * (MAXDIM - len(win_hi)))
+        self.check(self.dll.b2f_mapwindow_median(C.byref(img), C.byref(out), lo, hi, C.byref(border), C.c_void_p(stream)))
 
     def imfilter_slab(self, img: b2f_array, out: b2f_array, stages: StageList, border: b2f_border,
                       global_last_dim: int, slab_first: int, halo_lo: int, n_halo_lo: int,

@@ -190,6 +190,85 @@ __global__ void pt_normalize_dims_kernel(void *out, int odt, long long n, PtFact
     }
 }
 
+// ---- mapwindow(median!, img, window) (reference src/mapwindow.jl:270-333 generic path with
+// f = median!, Statistics.median!: NaN if any NaN, middle of the sorted window, x/2 + y/2 for even lengths) ----------------
+constexpr int PT_MAXWIN = 128;
+struct PtWin {
+    int ndim;
+    long long dims[B2F_MAXDIM];       // image extent
+    long long odims[B2F_MAXDIM];      // output extent
+    long long ooff[B2F_MAXDIM];       // image coordinate (0-based) of output element 0
+    int wlo[B2F_MAXDIM], wn[B2F_MAXDIM];
+    int style;
+    double fill;
+    long long nout;
+    int wtotal;
+};
+
+// window position k (0-based image coordinate, possibly outside) along an axis of length n, for the window [a, b]:
+// copy_win! pads the window's in-image part `inner` = [max(a,0), min(b,n-1)] by padindex (src/mapwindow.jl:310-317,
+// src/border.jl:564-590): the border remap is taken relative to `inner`, not to the whole image.  -1: Fill value.
+__host__ __device__ inline long long pt_win_index(int style, long long k, long long a, long long b, long long n) {
+    if (style == B2F_FILL) return (k >= 0 && k < n) ? k : -1;
+    const long long lo = a > 0 ? a : 0, hi = b < n - 1 ? b : n - 1, len = hi - lo + 1;
+    if (len == 1) return lo;
+    return lo + remap_index(style, k - lo, len);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128) pt_median_kernel(const void *img, int dt, void *out, int odt, PtWin G) {
+    const long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= G.nout) return;
+    long long c[B2F_MAXDIM], r = o;
+#pragma unroll
+    for (int d = 0; d < B2F_MAXDIM; ++d) { c[d] = r % G.odims[d] + G.ooff[d]; r /= G.odims[d]; }
+    T buf[PT_MAXWIN];
+    bool nan = false;
+    int n = 0;
+    long long stride[B2F_MAXDIM];
+    stride[0] = 1;
+#pragma unroll
+    for (int d = 1; d < B2F_MAXDIM; ++d) stride[d] = stride[d - 1] * G.dims[d - 1];
+    for (int j3 = 0; j3 < G.wn[3]; ++j3) {
+        const long long i3 = pt_win_index(G.style, c[3] + G.wlo[3] + j3, c[3] + G.wlo[3], c[3] + G.wlo[3] + G.wn[3] - 1, G.dims[3]);
+        for (int j2 = 0; j2 < G.wn[2]; ++j2) {
+            const long long i2 = pt_win_index(G.style, c[2] + G.wlo[2] + j2, c[2] + G.wlo[2], c[2] + G.wlo[2] + G.wn[2] - 1, G.dims[2]);
+            for (int j1 = 0; j1 < G.wn[1]; ++j1) {
+                const long long i1 = pt_win_index(G.style, c[1] + G.wlo[1] + j1, c[1] + G.wlo[1], c[1] + G.wlo[1] + G.wn[1] - 1, G.dims[1]);
+                for (int j0 = 0; j0 < G.wn[0]; ++j0) {
+                    const long long i0 = pt_win_index(G.style, c[0] + G.wlo[0] + j0, c[0] + G.wlo[0], c[0] + G.wlo[0] + G.wn[0] - 1, G.dims[0]);
+                    T v;
+                    if (i0 < 0 || i1 < 0 || i2 < 0 || i3 < 0) v = (T)G.fill;
+                    else v = pt_load<T>(img, dt, i0 + i1 * stride[1] + i2 * stride[2] + i3 * stride[3]);
+                    nan = nan || (v != v);
+                    buf[n++] = v;
+                }
+            }
+        }
+    }
+    // partial selection sort up to the upper middle element (windows are small)
+    const int hiidx = n / 2;                      // 0-based: odd n -> the middle; even n -> the upper of the two
+    for (int i = 0; i <= hiidx; ++i) {
+        int m = i;
+        for (int j = i + 1; j < n; ++j)
+            if (buf[j] < buf[m]) m = j;
+        const T t = buf[i]; buf[i] = buf[m]; buf[m] = t;
+    }
+    if (odt == B2F_F32) {
+        float res;
+        if (nan) res = __int_as_float(0x7fc00000);
+        else if (n & 1) res = (float)buf[hiidx];
+        else res = __fadd_rn(__fmul_rn((float)buf[hiidx - 1], 0.5f), __fmul_rn((float)buf[hiidx], 0.5f));
+        ((float *)out)[o] = res;
+    } else {
+        double res;
+        if (nan) res = __longlong_as_double(0x7ff8000000000000LL);
+        else if (n & 1) res = (double)buf[hiidx];
+        else res = __dadd_rn(__dmul_rn((double)buf[hiidx - 1], 0.5), __dmul_rn((double)buf[hiidx], 0.5));
+        ((double *)out)[o] = res;
+    }
+}
+
 static long long numel(const b2f_array *a) {
     long long n = 1;
     for (int d = 0; d < a->ndim; ++d) n *= a->dims[d] < 0 ? 0 : a->dims[d];
@@ -464,6 +543,69 @@ int b2f_normalize_dims(const b2f_array *out, const double *const *factors, void 
     if (d_f) cudaFreeAsync(d_f, st);
     release(so, st);
     if (e != cudaSuccess) return fail(B2F_ECUDA, "normalize_dims failed: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+int b2f_mapwindow_median(const b2f_array *img, const b2f_array *out, const int64_t *win_lo, const int64_t *win_hi,
+                         const b2f_border *border, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!img || !out || !win_lo || !win_hi || !border) return fail(B2F_EARG, "NULL argument");
+    const int N = img->ndim;
+    if (N < 1 || N > B2F_MAXDIM || out->ndim != N) return fail(B2F_EDIM, "mapwindow needs 1..%d dims and equal rank", B2F_MAXDIM);
+    if (img->dtype == B2F_N0F8) return fail(B2F_ENOTSUP, "median of N0f8 images is not available");
+    const int want = img->dtype == B2F_F32 ? B2F_F32 : B2F_F64;       // median: Float32 stays, everything else -> Float64
+    if (out->dtype != want) return fail(B2F_EARG, "median output eltype must be %s", want == B2F_F32 ? "Float32" : "Float64");
+    if (border->style > B2F_INNER) return fail(B2F_ENOTSUP, "border style %d is not supported by mapwindow", border->style);
+    PtWin G;
+    memset(&G, 0, sizeof G);
+    G.ndim = N;
+    G.style = border->style == B2F_INNER ? B2F_REPLICATE : border->style;
+    G.fill = border->fill;
+    G.nout = 1;
+    G.wtotal = 1;
+    Box ia = axes_of(img), oa = axes_of(out);
+    for (int d = 0; d < B2F_MAXDIM; ++d) {
+        G.dims[d] = d < N ? img->dims[d] : 1;
+        G.odims[d] = d < N ? out->dims[d] : 1;
+        G.ooff[d] = d < N ? oa.lo[d] - ia.lo[d] : 0;
+        G.wlo[d] = d < N ? (int)win_lo[d] : 0;
+        G.wn[d] = d < N ? (int)(win_hi[d] - win_lo[d] + 1) : 1;
+        if (G.wn[d] < 1) return fail(B2F_EARG, "empty window");
+        G.wtotal *= G.wn[d];
+        G.nout *= G.odims[d] < 0 ? 0 : G.odims[d];
+        if (d < N) {
+            if (oa.lo[d] < ia.lo[d] || oa.hi[d] > ia.hi[d]) return fail(B2F_EDIM, "output axes exceed image axes");
+            if (border->style == B2F_INNER && (oa.lo[d] + win_lo[d] < ia.lo[d] || oa.hi[d] + win_hi[d] > ia.hi[d]))
+                return fail(B2F_EDIM, "output axes are not in the interior for Inner()");
+            if (border->style != B2F_FILL && (win_lo[d] > 0 || win_hi[d] < 0) && border->style != B2F_INNER)
+                return fail(B2F_ENOTSUP, "windows that do not contain their centre need Fill or Inner borders here");
+        }
+    }
+    if (G.wtotal > PT_MAXWIN) return fail(B2F_ENOTSUP, "median windows hold at most %d elements", PT_MAXWIN);
+    set_path("median");
+    if (G.nout == 0 || numel(img) == 0) return 0;
+    int rc = ensure_ctx();
+    if (rc) return rc;
+    Staged sin, so;
+    rc = stage_in(img, sin, st, true);
+    if (!rc) rc = stage_in(out, so, st, false);
+    cudaError_t e = cudaSuccess;
+    if (!rc) {
+        const long long blocks = (G.nout + 127) / 128;
+        if (img->dtype == B2F_I64) pt_median_kernel<long long><<<(unsigned)blocks, 128, 0, st>>>(sin.dptr, img->dtype, so.dptr, out->dtype, G);
+        else pt_median_kernel<double><<<(unsigned)blocks, 128, 0, st>>>(sin.dptr, img->dtype, so.dptr, out->dtype, G);
+        count_launch();
+        e = cudaGetLastError();
+        if (e == cudaSuccess && out->mem == B2F_HOST) {
+            e = cudaMemcpyAsync(out->ptr, so.dptr, so.bytes, cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        } else if (e == cudaSuccess && img->mem == B2F_HOST) {
+            e = cudaStreamSynchronize(st);
+        }
+    }
+    release(sin, st); release(so, st);
+    if (rc) return rc;
+    if (e != cudaSuccess) return fail(B2F_ECUDA, "mapwindow median failed: %s", cudaGetErrorString(e));
     return 0;
 }
 

@@ -1,5 +1,5 @@
 """mapwindow / mapwindow! for f in {extrema, minimum, maximum} (reference src/mapwindow.jl:75-121,
-337-481).  Arbitrary window functions are Julia closures and cannot cross a C ABI: they raise
+337-481) and f = median! (the generic window loop :270-333 with Statistics.median!).  Arbitrary window functions are Julia closures and cannot cross a C ABI: they raise
 NotSupportedError (there is no CPU fallback)."""
 from __future__ import annotations
 
@@ -29,6 +29,14 @@ def maximum(a):
     return np.asarray(a).max()
 
 
+def median(a):
+    """Marker mirroring Statistics.median / median! (mapwindow(median!, ...) is the reference's spelling)."""
+    return float(np.median(np.asarray(a)))
+
+
+median_ = median        # `median!`
+
+_MED = {median, np.median, "median", "median!"}
 _MIN = {minimum, builtins.min, np.min, np.amin, np.minimum.reduce, "minimum", "min"}
 _MAX = {maximum, builtins.max, np.max, np.amax, np.maximum.reduce, "maximum", "max"}
 _EXT = {extrema, "extrema"}
@@ -42,10 +50,12 @@ def _kind(f):
             return "min"
         if f in _MAX:
             return "max"
+        if f in _MED:
+            return "median"
     except TypeError:
         pass
     raise NotSupportedError(
-        "mapwindow on the device supports f in {extrema, minimum, maximum}; arbitrary window functions "
+        "mapwindow on the device supports f in {extrema, minimum, maximum, median}; arbitrary window functions "
         "cannot cross the C ABI and there is no CPU fallback")
 
 
@@ -109,6 +119,16 @@ def _mapwindow(f, out_spec, img, window, border, indices, library):
         lo, hi = list(first), [f0 + n - 1 for f0, n in zip(first, shape)]
     oshape = tuple(max(0, h - l + 1) for l, h in zip(lo, hi))
     base = _abi.DTYPE_TO_NP[desc.dtype]
+    if kind == "median":        # generic window path, src/mapwindow.jl:270-333 with f = median!
+        odt = _abi.F32 if desc.dtype == _abi.F32 else _abi.F64
+        if out_spec is not None:
+            odesc, okeep = _as_output(out_spec)
+            od = _abi.make_array(odesc.ptr, odesc.dtype, oshape, lo, odesc.mem)
+            L.mapwindow_median(desc, od, wlo, whi, b.to_abi(ndim))
+            return out_spec
+        res = np.empty(oshape, dtype=_abi.DTYPE_TO_NP[odt], order="F")
+        L.mapwindow_median(desc, _abi.make_array(res.ctypes.data, odt, oshape, lo, _abi.HOST), wlo, whi, b.to_abi(ndim))
+        return OffsetArray.with_first(res, lo) if any(l != 1 for l in lo) else res
 
     if out_spec is not None:  # mapwindow!
         out = out_spec

@@ -181,6 +181,15 @@ int b2f_mapwindow_extrema(const b2f_array *img, const b2f_array *out_min, const 
                           const int64_t *win_lo, const int64_t *win_hi,
                           const b2f_border *border, void *stream);
 
+/* mapwindow(median!, img, window; border)  (generic window loop src/mapwindow.jl:270-333 with
+ * f = Statistics.median!): NaN if the window holds a NaN, else the middle of the sorted window (x/2 + y/2 of the two
+ * middle elements for even lengths).  Output eltype: Float32 for Float32 images, Float64 otherwise.  Window [win_lo,
+ * win_hi] per axis, at most 128 elements.  Borders as in copy_win! (:310-333): Pad styles pad the window's in-image
+ * part by padindex (the remap is relative to that part, not to the whole image), Fill inserts the value, Inner
+ * restricts the outputs to out's axes. */
+int b2f_mapwindow_median(const b2f_array *img, const b2f_array *out, const int64_t *win_lo, const int64_t *win_hi,
+                         const b2f_border *border, void *stream);
+
 /* Slab form of a separable cascade, used by the sharded N-d path: the array's LAST axis is
  * partitioned across GPUs.  `img` and `out` hold this rank's owned planes [slab_first, slab_first + dims[ndim-1])
  * of an array whose last axis has `global_last_dim` planes.  `halo_lo` / `halo_hi` point to `n_halo_lo` /

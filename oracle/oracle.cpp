@@ -1235,3 +1235,104 @@ int b2f_stream_write32(void *, uint32_t, void *) { return fail(B2F_ENOTSUP, "ora
 int b2f_stream_wait_geq32(void *, uint32_t, void *) { return fail(B2F_ENOTSUP, "oracle library has no device memory"); }
 int b2f_memset_async(void *, int32_t, uint64_t, void *) { return fail(B2F_ENOTSUP, "oracle library has no device memory"); }
 }
+
+// ---- mapwindow(median!, ...) (reference src/mapwindow.jl:270-333 with f = median!; Statistics.median!) ------------------
+namespace {
+int64_t o_remap(int style, int64_t i, int64_t n) {        // src/border.jl:564-590 relative to a range of length n
+    if (i >= 0 && i < n) return i;
+    switch (style) {
+        case B2F_REPLICATE: return i < 0 ? 0 : n - 1;
+        case B2F_CIRCULAR: { int64_t m = i % n; return m < 0 ? m + n : m; }
+        case B2F_SYMMETRIC: { const int64_t p = 2 * n; int64_t m = i % p; if (m < 0) m += p; return m < n ? m : p - 1 - m; }
+        case B2F_REFLECT: { const int64_t p = 2 * n - 2; int64_t m = i % p; if (m < 0) m += p; return m < n ? m : p - m; }
+        default: return -1;
+    }
+}
+int64_t o_win_index(int style, int64_t k, int64_t a, int64_t b, int64_t n) {   // copy_win!: padindex on window ∩ image
+    if (style == B2F_FILL) return (k >= 0 && k < n) ? k : -1;
+    const int64_t lo = a > 0 ? a : 0, hi = b < n - 1 ? b : n - 1, len = hi - lo + 1;
+    if (len == 1) return lo;
+    return lo + o_remap(style, k - lo, len);
+}
+}  // namespace
+
+extern "C" int b2f_mapwindow_median(const b2f_array *img, const b2f_array *out, const int64_t *win_lo, const int64_t *win_hi,
+                                    const b2f_border *border, void *) {
+    if (!img || !out || !win_lo || !win_hi || !border) return fail(B2F_EARG, "NULL argument");
+    const int N = img->ndim;
+    if (N < 1 || N > B2F_MAXDIM || out->ndim != N) return fail(B2F_EDIM, "mapwindow needs 1..4 dims and equal rank");
+    if (img->dtype == B2F_N0F8) return fail(B2F_ENOTSUP, "median of N0f8 images is not available");
+    const int want = img->dtype == B2F_F32 ? B2F_F32 : B2F_F64;
+    if (out->dtype != want) return fail(B2F_EARG, "median output eltype must be %s", want == B2F_F32 ? "Float32" : "Float64");
+    if (border->style > B2F_INNER) return fail(B2F_ENOTSUP, "border style %d is not supported by mapwindow", border->style);
+    const int style = border->style == B2F_INNER ? B2F_REPLICATE : border->style;
+    int64_t dims[4], odims[4], ooff[4], wlo[4], wn[4], stride[4], nout = 1, wtotal = 1;
+    for (int d = 0; d < 4; ++d) {
+        dims[d] = d < N ? img->dims[d] : 1;
+        odims[d] = d < N ? out->dims[d] : 1;
+        ooff[d] = d < N ? out->origin[d] - img->origin[d] : 0;
+        wlo[d] = d < N ? win_lo[d] : 0;
+        wn[d] = d < N ? win_hi[d] - win_lo[d] + 1 : 1;
+        if (wn[d] < 1) return fail(B2F_EARG, "empty window");
+        wtotal *= wn[d];
+        nout *= odims[d] < 0 ? 0 : odims[d];
+        stride[d] = d == 0 ? 1 : stride[d - 1] * dims[d - 1];
+        if (d < N) {
+            if (ooff[d] < 0 || ooff[d] + odims[d] > dims[d]) return fail(B2F_EDIM, "output axes exceed image axes");
+            if (border->style == B2F_INNER && (ooff[d] + win_lo[d] < 0 || ooff[d] + odims[d] - 1 + win_hi[d] > dims[d] - 1))
+                return fail(B2F_EDIM, "output axes are not in the interior for Inner()");
+            if (border->style != B2F_FILL && (win_lo[d] > 0 || win_hi[d] < 0) && border->style != B2F_INNER)
+                return fail(B2F_ENOTSUP, "windows that do not contain their centre need Fill or Inner borders here");
+        }
+    }
+    if (wtotal > 128) return fail(B2F_ENOTSUP, "median windows hold at most 128 elements");
+    if (o_numel(img) == 0) return 0;
+    const bool is_i64 = img->dtype == B2F_I64;
+    std::vector<double> buf(wtotal);
+    std::vector<int64_t> ibuf(wtotal);
+    for (int64_t o = 0; o < nout; ++o) {
+        int64_t c[4], r = o;
+        for (int d = 0; d < 4; ++d) { c[d] = r % odims[d] + ooff[d]; r /= odims[d]; }
+        int n = 0;
+        bool nan = false;
+        for (int64_t j3 = 0; j3 < wn[3]; ++j3)
+            for (int64_t j2 = 0; j2 < wn[2]; ++j2)
+                for (int64_t j1 = 0; j1 < wn[1]; ++j1)
+                    for (int64_t j0 = 0; j0 < wn[0]; ++j0) {
+                        const int64_t j[4] = {j0, j1, j2, j3};
+                        int64_t lin = 0;
+                        bool fillv = false;
+                        for (int d = 0; d < 4; ++d) {
+                            const int64_t a = c[d] + wlo[d], i = o_win_index(style, a + j[d], a, a + wn[d] - 1, dims[d]);
+                            if (i < 0) fillv = true; else lin += i * stride[d];
+                        }
+                        if (is_i64) ibuf[n] = fillv ? (int64_t)border->fill : ((const int64_t *)img->ptr)[lin];
+                        const double v = fillv ? (img->dtype == B2F_F32 ? (double)(float)border->fill : border->fill) : o_elem(img, lin);
+                        nan = nan || (v != v);
+                        buf[n++] = v;
+                    }
+        double lo_v, hi_v;
+        const int mid = n / 2;
+        if (is_i64) {
+            std::sort(ibuf.begin(), ibuf.begin() + n);
+            hi_v = (double)ibuf[mid]; lo_v = (double)ibuf[mid > 0 ? mid - 1 : 0];
+        } else {
+            std::sort(buf.begin(), buf.begin() + n);
+            hi_v = buf[mid]; lo_v = buf[mid > 0 ? mid - 1 : 0];
+        }
+        if (out->dtype == B2F_F32) {
+            float res;
+            if (nan) res = std::numeric_limits<float>::quiet_NaN();
+            else if (n & 1) res = (float)hi_v;
+            else res = (float)lo_v / 2.0f + (float)hi_v / 2.0f;
+            ((float *)out->ptr)[o] = res;
+        } else {
+            double res;
+            if (nan) res = std::numeric_limits<double>::quiet_NaN();
+            else if (n & 1) res = hi_v;
+            else res = lo_v / 2.0 + hi_v / 2.0;
+            ((double *)out->ptr)[o] = res;
+        }
+    }
+    return 0;
+}

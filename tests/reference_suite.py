@@ -589,6 +589,29 @@ def check_color_images(ifb, lib):
                         assert np.all(cd[1:] == 0)
 
 
-ALL_CHECKS = [check_local_extrema, check_blob_log, check_na_border, check_color_images, check_padarray, check_1d, check_widening, check_prewitt_tiling, check_impulse_interior,
+def check_median_window(ifb, lib):
+    """reference test/mapwindow.jl:105-123 ("median"): literal goldens for median / median! in 1-D and 2-D."""
+    a = np.array([1, 1, 1, 2, 2, 2])
+    for f in (ifb.median, ifb.median_):
+        for w in (range(-1, 2), (range(-1, 2),), range(-2, 3), range(-3, 4)):
+            assert np.array_equal(ifb.mapwindow(f, a, w, _library=lib), a)
+        b = np.array([1, 100, 1, 2, -1000, 2])
+        assert np.array_equal(ifb.mapwindow(f, b, range(-1, 2), _library=lib), [1, 1, 2, 1, 2, 2])
+        assert np.array_equal(ifb.mapwindow(f, b, range(-2, 3), _library=lib), a)
+        A = np.array([[1, 5, -2, 3, 7], [2, 0, 3, 4, 4], [3, 3, 6, 2, 5], [1, -3, 5, 3, 0]])
+        assert np.array_equal(ifb.mapwindow(f, A, (3, 3), _library=lib),
+                              [[1, 1, 3, 3, 4], [2, 3, 3, 4, 4], [2, 3, 3, 4, 4], [1, 3, 3, 3, 2]])
+    # mapwindow! into a preallocated Float64 array, and the interior (Inner) equals numpy's median of the windows
+    rng = np.random.default_rng(5)
+    x = rng.random((12, 9))
+    out = np.empty((12, 9), order="F")
+    ifb.mapwindow_(ifb.median_, out, x, (3, 5), _library=lib)
+    inner = ifb.mapwindow(ifb.median, x, (3, 5), ifb.Inner(), _library=lib)
+    want = np.array([[np.median(x[i - 1:i + 2, j - 2:j + 3]) for j in range(2, 7)] for i in range(1, 11)])
+    assert np.array_equal(inner.parent, want) and inner.first == (2, 3)
+    assert np.array_equal(out[1:11, 2:7], want)
+
+
+ALL_CHECKS = [check_median_window, check_local_extrema, check_blob_log, check_na_border, check_color_images, check_padarray, check_1d, check_widening, check_prewitt_tiling, check_impulse_interior,
               check_impulse_corner, check_offset_axes, check_nonfinite, check_3d_box, check_cascade,
               check_gradients, check_laplacian, check_extrema_goldens, check_mapwindow_offsets]

@@ -520,3 +520,32 @@ def test_color_image_parity(ifb, oracle, device):
     got = ifb.imfilter(np.float32, f, ifb.KernelFactors.gaussian((2, 2)), "symmetric")
     ref = ifb.imfilter(np.float32, f, ifb.KernelFactors.gaussian((2, 2)), "symmetric", _library=oracle)
     assert np.max(np.abs(got.data.astype(np.float64) - ref.data)) <= 1e-5
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64, np.int32, np.uint8, np.int64])
+def test_median_window_parity(ifb, oracle, device, dt):
+    """mapwindow(median!, ...) (src/mapwindow.jl:270-333 + Statistics.median!): bit-equal to the oracle for odd and even
+    windows, asymmetric ranges, every border (the Pad styles pad the window's in-image part), NaNs, 1-D .. 3-D."""
+    rng = np.random.default_rng(int(np.dtype(dt).itemsize) + 40)
+    cases = [((200,), (5,)), ((64, 50), (3, 3)), ((64, 50), (range(-2, 2), range(0, 3))), ((33, 20, 11), (3, 1, 5)),
+             ((40, 30), (7, 7)), ((5, 4), (7, 9))]
+    borders = ["replicate", "circular", "symmetric", "reflect", ifb.Fill(2), ifb.Inner()]
+    for shape, window in cases:
+        if np.dtype(dt).kind == "f":
+            A = rng.random(shape).astype(dt)
+            if A.size > 100:
+                A.ravel()[rng.integers(0, A.size, 4)] = np.nan
+        else:
+            A = rng.integers(0, 50, size=shape).astype(dt)
+        A = np.asfortranarray(A)
+        for border in borders:
+            if isinstance(border, ifb.Inner) and shape == (5, 4):
+                continue
+            device.reset_launch_count()
+            got = ifb.mapwindow(ifb.median, A, window, border)
+            assert device.launch_count() > 0 and device.last_path() == "median"
+            ref = ifb.mapwindow(ifb.median, A, window, border, _library=oracle)
+            g = got.parent if isinstance(got, ifb.OffsetArray) else got
+            r = ref.parent if isinstance(ref, ifb.OffsetArray) else ref
+            assert g.dtype == r.dtype == (np.float32 if dt == np.float32 else np.float64)
+            assert np.array_equal(g, r, equal_nan=True), (shape, window, border)
