@@ -344,7 +344,14 @@ stream3d_kernel(const __grid_constant__ S3Params P, const __grid_constant__ CUte
 
     bool lo_ready = P.flag_lo == nullptr, hi_ready = P.flag_hi == nullptr;     // thread 0 only
     auto wait_flag = [&](const unsigned char *f) {
-        while (*reinterpret_cast<const volatile unsigned char *>(f) != (unsigned char)P.epoch) __nanosleep(64);
+        // bounded: a copy that never arrives (a failed transfer on the side stream) must become an error, not a hung GPU
+        unsigned long long t0 = 0, t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        while (*reinterpret_cast<const volatile unsigned char *>(f) != (unsigned char)P.epoch) {
+            __nanosleep(64);
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            if (t - t0 > 5000000000ULL) asm volatile("trap;");          // 5 s
+        }
         __threadfence_system();
     };
     auto issue = [&](int p) {                   // one thread: TMA of input plane p into its ring buffer
