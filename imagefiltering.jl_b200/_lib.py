@@ -7,7 +7,7 @@ import os
 from . import _abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb2f.so")
+LIB_PATH = os.environ.get("B2F_LIB_PATH") or os.path.join(_HERE, "libb2f.so")     # env: A/B testing of kernel builds
 _lib = None
 
 

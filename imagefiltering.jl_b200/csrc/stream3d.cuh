@@ -119,11 +119,13 @@ __device__ __forceinline__ void s3_mbar_arrive(unsigned b) {
 __device__ __forceinline__ void s3_mbar_expect_tx(unsigned b, unsigned bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
 }
+// try_wait with a suspend-time hint: the hardware parks the warp until the phase completes (or the hint expires) instead of
+// having it re-poll — in the first version the polling loop was 6 % of all issued instructions
 __device__ __forceinline__ void s3_mbar_wait(unsigned b, unsigned parity) {
     unsigned ok;
     do {
-        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
-                     : "=r"(ok) : "r"(b), "r"(parity) : "memory");
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(b), "r"(parity), "r"(200000u) : "memory");
     } while (!ok);
 }
 __device__ __forceinline__ void s3_tma_load3d(unsigned dst, const void *tmap, unsigned bar, int c0, int c1, int c2) {
@@ -277,7 +279,11 @@ stream3d_kernel(const __grid_constant__ S3Params P, const __grid_constant__ CUte
     // stage x of the plane in xf slot s
     const unsigned full = s3_sa(ptz + S3_PT), xfull = full + 8 * N, raw_sa = s3_sa(raw), xf_sa = s3_sa(xf);
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // the thread index through an opaque move: the compiler otherwise re-reads the special register (S2R, ~20 cycles on the
+    // critical path) four times per plane instead of keeping it in a register
+    int tid;
+    asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
+    const int warp = tid >> 5, lane = tid & 31;
     const int Lx = LXT ? LXT : P.Lx, Ly = LYT ? LYT : P.Ly, Lz = LZT ? LZT : P.Lz;
     const int bid = blockIdx.x;
     int tile = bid, ch = 0, zc = P.own_n;
