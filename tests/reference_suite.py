@@ -612,6 +612,44 @@ def check_median_window(ifb, lib):
     assert np.array_equal(out[1:11, 2:7], want)
 
 
-ALL_CHECKS = [check_median_window, check_local_extrema, check_blob_log, check_na_border, check_color_images, check_padarray, check_1d, check_widening, check_prewitt_tiling, check_impulse_interior,
+def check_golden_fixtures_f(ifb, lib):
+    """The §8f goldens as stored in tests/golden/reference_goldens.json (transcribed by transcribe_goldens.py from
+    test/extrema.jl, test/border.jl, test/mapwindow.jl and the blob_LoG docstring): the same facts as the literal checks
+    below, read from the committed fixture."""
+    num = lambda v: float(v.replace("Inf", "inf").replace("NaN", "nan")) if isinstance(v, str) else float(v)
+    for c in G["local_extrema"]["cases"]:
+        A = np.zeros(c["shape"], dtype=np.int64)
+        for pos in c["ones"]:
+            A[tuple(i - 1 for i in pos)] = c["value"]
+        f = ifb.findlocalminima if c["minima"] else ifb.findlocalmaxima
+        kw = {} if c["window"] is None else {"window": tuple(c["window"])}
+        assert f(A, edges=c["edges"], _library=lib, **kw) == [tuple(t) for t in c["out"]], c
+    g = G["blob_log"]["impulse_9x9"]
+    A = np.zeros((9, 9), dtype=np.int64); A[tuple(i - 1 for i in g["at"])] = 1
+    (blob,) = ifb.blob_LoG(A, 2.0 ** np.array(g["sigmas_log2"]), _library=lib)
+    assert approx(blob.amplitude, g["amplitude"]) and blob.σ == tuple(g["sigma"]) and blob.location == tuple(g["at"])
+    d = G["blob_log"]["docstring"]
+    img = np.zeros(d["n"])
+    for b in d["bumps"]:
+        img[b["lo"] - 1:b["hi"]] = [np.exp(-x ** 2 / (2 * b["sigma"] ** 2)) for x in range(-b["half"], b["half"] + 1)]
+    blobs = ifb.blob_LoG(img, 2.0 ** np.array(d["sigmas_log2"], dtype=np.float64), edges=False, _library=lib)
+    assert [(list(b.location), list(b.σ)) for b in blobs] == [(e["location"], e["sigma"]) for e in d["blobs"]]
+    assert all(abs(b.amplitude - e["amplitude"]) < 1e-12 for b, e in zip(blobs, d["blobs"]))
+    n = G["na_border"]
+    assert approx(ifb.imfilter(np.arange(1, 11, dtype=np.float64), ifb.centered(np.array([1, 1, 1]) / 3), ifb.NA(), _library=lib), n["box_1_10"])
+    x = np.array([num(v) for v in n["x"]])
+    k = ifb.OffsetArray.with_first(np.array(n["k"]), (n["k_first"],))
+    for mode in ("isnan", "!isfinite", "never"):
+        want = np.array([num(v) for v in n[mode]])
+        assert np.array_equal(ifb.imfilter(x, k, ifb.NA(mode), _library=lib), want, equal_nan=True), mode
+    m = G["median"]
+    for lo, hi in m["a_windows"]:
+        assert np.array_equal(ifb.mapwindow(ifb.median, np.array(m["a"]), range(lo, hi + 1), _library=lib), m["a"])
+    assert np.array_equal(ifb.mapwindow(ifb.median, np.array(m["b"]), range(-1, 2), _library=lib), m["b_w1"])
+    assert np.array_equal(ifb.mapwindow(ifb.median, np.array(m["b"]), range(-2, 3), _library=lib), m["a"])
+    assert np.array_equal(ifb.mapwindow(ifb.median, np.array(m["A"]), (3, 3), _library=lib), m["A_3x3"])
+
+
+ALL_CHECKS = [check_golden_fixtures_f, check_median_window, check_local_extrema, check_blob_log, check_na_border, check_color_images, check_padarray, check_1d, check_widening, check_prewitt_tiling, check_impulse_interior,
               check_impulse_corner, check_offset_axes, check_nonfinite, check_3d_box, check_cascade,
               check_gradients, check_laplacian, check_extrema_goldens, check_mapwindow_offsets]
