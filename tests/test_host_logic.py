@@ -145,3 +145,58 @@ def test_resolve_window(ifb):
     assert mw.resolve_window((2, 4), 2, allow_even=True) == ([-1, -2], [0, 1])
     with pytest.raises(ifb.ArgumentError):
         mw.resolve_window((), 0)
+
+
+def test_color_kernel_lifting(ifb):
+    """ColorArray: the kernel factors move one axis up, dense blocks get a leading axis of length 1 (color.py)."""
+    from importlib import import_module
+    col = import_module("imagefiltering_jl_b200.color")
+    k1, k2 = ifb.KernelFactors.gaussian((1, 2))
+    l1, l2 = col.lift_kernel((k1, k2))
+    assert (l1.N, l1.Npre, l2.N, l2.Npre) == (3, 1, 3, 2) and l1.data is k1.data
+    dense = ifb.OffsetArray.with_first(np.arange(6.0).reshape(2, 3), (-1, 0))
+    (ld,) = col.lift_kernel((dense,))
+    assert ld.parent.shape == (1, 2, 3) and tuple(ld.first) == (0, -1, 0) and np.array_equal(ld.parent[0], dense.parent)
+    (ll,) = col.lift_kernel((ifb.Kernel.Laplacian((True, False)),))
+    assert tuple(ll.flags) == (False, True, False)
+    c = ifb.ColorArray(np.zeros((3, 5, 7), dtype=np.uint8))
+    assert (c.nchannels, c.shape, c.ndim) == (3, (5, 7), 2) and c.data.flags.f_contiguous
+    with pytest.raises(TypeError):
+        ifb.ColorArray(np.zeros(3))
+
+
+def test_na_border_modes(ifb):
+    """NA(na): the three predicates the reference exercises are modes; anything else is refused, not emulated."""
+    assert (ifb.NA().mode, ifb.NA("!isfinite").mode, ifb.NA("never").mode) == (0, 1, 2)
+    with pytest.raises(ifb.NotSupportedError):
+        ifb.NA("x -> x > 3")
+    with pytest.raises(ifb.ArgumentError):
+        ifb.NA().to_abi(2)            # NA is resolved by imfilter itself, never by the pad
+
+
+def test_local_extrema_argument_checks(ifb, oracle):
+    A = np.zeros((4, 5))
+    with pytest.raises(ifb.ArgumentError):
+        ifb.findlocalmaxima(A, window=(3,), _library=oracle)
+    with pytest.raises(ifb.ArgumentError):
+        ifb.findlocalmaxima(A, edges=(True,), _library=oracle)
+    with pytest.raises(ifb.ArgumentError):
+        ifb.blob_LoG(A, [1.0], edges=(True, False), _library=oracle)
+    assert ifb.findlocalmaxima(np.zeros((0, 3)), _library=oracle) == []
+    rows = ifb.findlocalmaxima(np.eye(5), as_array=True, _library=oracle)
+    assert rows.dtype == np.int64 and rows.shape[1] == 2
+    b = ifb.BlobLoG((5, 5), (1.0, 1.0), 0.25)
+    assert "CartesianIndex(5, 5)" in repr(b) and b == ifb.BlobLoG((5, 5), (1.0, 1.0), 0.25)
+
+
+def test_median_window_resolution(ifb, oracle):
+    """mapwindow(median!, ...): odd Dims or ranges; even Dims are an ArgumentError like the reference's resolve_window."""
+    x = np.arange(10.0)
+    with pytest.raises(ifb.ArgumentError):
+        ifb.mapwindow(ifb.median, x, (4,), _library=oracle)
+    even = ifb.mapwindow(ifb.median, x, range(0, 2), ifb.Fill(0), _library=oracle)      # window i:i+1 -> mean of two neighbours
+    assert np.array_equal(even[:-1], x[:-1] / 2 + x[1:] / 2) and even[-1] == 4.5
+    with pytest.raises(ifb.NotSupportedError):
+        ifb.mapwindow(ifb.median, x, range(1, 3), "replicate", _library=oracle)       # window without its centre: Fill / Inner only
+    f32 = ifb.mapwindow(ifb.median, x.astype(np.float32), (3,), _library=oracle)
+    assert f32.dtype == np.float32 and ifb.mapwindow(ifb.median, x.astype(np.int32), (3,), _library=oracle).dtype == np.float64
