@@ -33,7 +33,7 @@ DTYPE_TO_NP[N0F8] = np.dtype(np.uint8)
 
 # every symbol include/b2f.h declares (tests check the built library exports all of them)
 SYMBOLS = [
-    "b2f_version", "b2f_last_error", "b2f_is_device_library", "b2f_set_device", "b2f_device_count",
+    "b2f_version", "b2f_last_error", "b2f_is_device_library", "b2f_set_device", "b2f_device_count", "b2f_sm_count",
     "b2f_malloc", "b2f_free", "b2f_host_alloc", "b2f_host_free", "b2f_memcpy_h2d", "b2f_memcpy_d2h",
     "b2f_sync", "b2f_ipc_export", "b2f_ipc_open", "b2f_ipc_close", "b2f_imfilter", "b2f_imgradients", "b2f_mapwindow_extrema", "b2f_mapwindow_median", "b2f_imfilter_slab", "b2f_imfilter_slab_staged", "b2f_memcpy_async", "b2f_memcpy2d_async",
     "b2f_memset_async", "b2f_stream_write32", "b2f_stream_wait_geq32",
@@ -109,6 +109,8 @@ def numpy_array_desc(x: np.ndarray, origin=None, dtype=None) -> b2f_array:
         raise ValueError("array must be Fortran-contiguous (Julia memory order)")
     if x.ndim == 1 and not x.flags.c_contiguous:
         raise ValueError("vector must be contiguous")
+    if dtype is None and x.dtype not in NP_TO_DTYPE:
+        raise NotSupportedError(f"element type {x.dtype} has no counterpart in the C ABI (include/b2f.h dtypes)")
     dt = NP_TO_DTYPE[x.dtype] if dtype is None else dtype
     return make_array(x.ctypes.data, dt, x.shape, origin, HOST)
 
@@ -170,6 +172,7 @@ class Library:
         d.b2f_memcpy_d2h.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
         d.b2f_set_device.argtypes = [C.c_int]
         d.b2f_device_count.argtypes = [C.POINTER(C.c_int)]
+        d.b2f_sm_count.argtypes = [C.POINTER(C.c_int)]
         d.b2f_ipc_export.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
         d.b2f_ipc_open.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]
         d.b2f_ipc_close.argtypes = [C.c_void_p, C.c_uint64]
@@ -220,6 +223,11 @@ class Library:
 
     def is_device_library(self) -> bool:
         return bool(self.dll.b2f_is_device_library())
+
+    def sm_count(self) -> int:
+        n = C.c_int()
+        self.check(self.dll.b2f_sm_count(C.byref(n)))
+        return int(n.value)
 
     def last_path(self) -> str:
         return self.dll.b2f_last_path().decode()

@@ -26,8 +26,8 @@ class Pad(AbstractBorder):
         self.style = style
         if len(args) == 0:
             self.lo, self.hi = (), ()
-        elif len(args) == 1:
-            both = tuple(int(v) for v in args[0])
+        elif len(args) == 1:      # Pad(style, (m, n, …)) or, for vectors, Pad(style, m)  (src/border.jl:43-45)
+            both = (int(args[0]),) if isinstance(args[0], (int,)) else tuple(int(v) for v in args[0])
             self.lo, self.hi = both, both
         elif len(args) == 2 and all(isinstance(a, (tuple, list)) for a in args):
             lo, hi = tuple(int(v) for v in args[0]), tuple(int(v) for v in args[1])
@@ -56,8 +56,8 @@ class Fill(AbstractBorder):
 
     def __init__(self, value, lo=(), hi=None):
         self.value = value
-        lo = tuple(int(v) for v in lo)
-        hi = lo if hi is None else tuple(int(v) for v in hi)
+        lo = (int(lo),) if isinstance(lo, int) else tuple(int(v) for v in lo)
+        hi = lo if hi is None else ((int(hi),) if isinstance(hi, int) else tuple(int(v) for v in hi))
         self.lo, self.hi = lo, hi
 
     def __repr__(self):
@@ -73,8 +73,8 @@ class Inner(AbstractBorder):
     """Inner() | Inner(lo, hi) | Inner(both).  src/border.jl:442-560."""
 
     def __init__(self, lo=(), hi=None):
-        lo = tuple(int(v) for v in lo)
-        hi = lo if hi is None else tuple(int(v) for v in hi)
+        lo = (int(lo),) if isinstance(lo, int) else tuple(int(v) for v in lo)
+        hi = lo if hi is None else ((int(hi),) if isinstance(hi, int) else tuple(int(v) for v in hi))
         self.lo, self.hi = lo, hi
 
     def __repr__(self):

@@ -34,6 +34,19 @@ int fail(int code, const char *fmt, ...) {
 void set_path(const char *name) { g_path = name; }
 void count_launch(int n) { g_launches += n; }
 
+int sm_count() {
+    static thread_local int cached_dev = -1, cached = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (dev != cached_dev) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1) n = 148;
+        cached = n;
+        cached_dev = dev;
+    }
+    return cached;
+}
+
 static int analyse_stage(const b2f_stage *s, int ndim, StageInfo &si) {
     si.s = s;
     for (int d = 0; d < B2F_MAXDIM; ++d) si.lo[d] = si.hi[d] = 0;
@@ -230,6 +243,11 @@ int b2f_set_device(int device) { B2F_CUDA(cudaSetDevice(device)); return 0; }
 int b2f_device_count(int *count) {
     if (!count) return fail(B2F_EARG, "NULL argument");
     B2F_CUDA(cudaGetDeviceCount(count));
+    return 0;
+}
+int b2f_sm_count(int *count) {
+    if (!count) return fail(B2F_EARG, "NULL argument");
+    *count = sm_count();
     return 0;
 }
 int b2f_malloc(void **dptr, uint64_t bytes) { B2F_CUDA(cudaMalloc(dptr, bytes)); return 0; }

@@ -13,6 +13,8 @@ namespace b2f {
 
 // ---- host-side status plumbing ---------------------------------------------------------------
 int fail(int code, const char *fmt, ...);
+// multiprocessor count of the current device (cudaDevAttrMultiProcessorCount, cached per device; 148 on a B200)
+int sm_count();
 void set_path(const char *name);
 void count_launch(int n = 1);
 #define B2F_CUDA(expr)                                                                         \
@@ -21,6 +23,20 @@ void count_launch(int n = 1);
         if (e__ != cudaSuccess)                                                                \
             return ::b2f::fail(B2F_ECUDA, "%s failed: %s", #expr, cudaGetErrorString(e__));    \
     } while (0)
+
+// stream-ordered frees on scope exit: an early error return (B2F_CUDA) releases what was allocated so far
+struct AsyncFrees {
+    cudaStream_t st;
+    std::vector<void *> v;
+    explicit AsyncFrees(cudaStream_t s) : st(s) {}
+    AsyncFrees(const AsyncFrees &) = delete;
+    AsyncFrees &operator=(const AsyncFrees &) = delete;
+    void push_back(void *p) { v.push_back(p); }
+    ~AsyncFrees() {
+        for (void *p : v)
+            if (p) cudaFreeAsync(p, st);
+    }
+};
 
 // ---- geometry ------------------------------------------------------------------------------------
 struct Box {  // inclusive index ranges; axes >= ndim are 0:0

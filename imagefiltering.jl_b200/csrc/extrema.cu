@@ -53,7 +53,7 @@ int run_extrema(const b2f_array *img, const void *d_img, void *d_min, void *d_ma
     P.vec_ok = aligned;
     const long long nbatch = ia.len(2) * ia.len(3);
     P.nsx = (P.rw + 127) / 128;
-    const long long want = 148LL * 16 * 6;
+    const long long want = (long long)sm_count() * 16 * 6;
     int SH = 256;
     while (SH > 32 && (long long)P.nsx * ((P.rh + SH - 1) / SH) * nbatch < want) SH >>= 1;
     P.SH = SH;

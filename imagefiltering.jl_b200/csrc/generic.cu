@@ -103,15 +103,12 @@ static int run_generic_typed(const Plan &P, const void *d_img, int img_dt, void 
     int64_t rlo = 0, rhi = 0;
     const bool int_out = int_range(out_dt, rlo, rhi);
     int *d_flag = nullptr;
+    AsyncFrees to_free(st);                  // released on every exit, error returns included
     if (int_out) {
         B2F_CUDA(cudaMallocAsync((void **)&d_flag, sizeof(int), st));
+        to_free.push_back(d_flag);
         B2F_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), st));
     }
-    std::vector<void *> to_free;
-    auto cleanup = [&]() {
-        for (void *p : to_free) cudaFreeAsync(p, st);
-        if (d_flag) cudaFreeAsync(d_flag, st);
-    };
     const void *src = d_img;
     int src_dt = img_dt;
     Box src_ax = P.img_ax;
@@ -164,7 +161,7 @@ static int run_generic_typed(const Plan &P, const void *d_img, int img_dt, void 
         g.dst = dst;
         for (int d = 0; d < B2F_MAXDIM; ++d) { g.dst_lo[d] = dst_ax.lo[d]; g.dst_len[d] = dst_ax.len(d); }
         const int64_t total = reg.count();
-        int blocks = (int)std::min<int64_t>((total + 255) / 256, 148 * 16);
+        int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)sm_count() * 16);
         if (blocks < 1) blocks = 1;
         generic_stage_kernel<CT><<<blocks, 256, 0, st>>>(g);
         count_launch();
@@ -179,7 +176,6 @@ static int run_generic_typed(const Plan &P, const void *d_img, int img_dt, void 
         if (e != cudaSuccess) rc = fail(B2F_ECUDA, "flag readback failed: %s", cudaGetErrorString(e));
         else if (flag) rc = fail(B2F_EINEXACT, "result not representable in eltype(out) (InexactError)");
     }
-    cleanup();
     return rc;
 }
 
@@ -255,7 +251,7 @@ static int run_extrema_generic_typed(const b2f_array *img, const void *d_img, vo
     g.fill_on = style == B2F_FILL;
     g.fill = (T)fill;
     const int64_t total = out_ax.count();
-    int blocks = (int)std::min<int64_t>((total + 255) / 256, 148 * 16);
+    int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)sm_count() * 16);
     generic_extrema_kernel<T><<<blocks < 1 ? 1 : blocks, 256, 0, st>>>(g);
     count_launch();
     B2F_CUDA(cudaGetLastError());

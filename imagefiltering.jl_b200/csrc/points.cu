@@ -361,7 +361,7 @@ int b2f_scale_into_slice(const b2f_array *src, const b2f_array *stack, int64_t s
     set_path("scale_slice");
     if (n == 0) return 0;
     const long long blocks = (n + 255) / 256;
-    pt_scale_slice_kernel<<<(unsigned)(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, st>>>(src->ptr, src->dtype, stack->ptr, stack->dtype, n,
+    pt_scale_slice_kernel<<<(unsigned)(blocks < sm_count() * 16 ? blocks : sm_count() * 16), 256, 0, st>>>(src->ptr, src->dtype, stack->ptr, stack->dtype, n,
                                                                                       stack->dims[0], slice, scale);
     count_launch();
     B2F_CUDA(cudaGetLastError());
@@ -384,7 +384,7 @@ int b2f_maxabs(const b2f_array *img, double *result, void *stream) {
     unsigned long long h[2] = {0, 0};
     if (e == cudaSuccess) {
         const long long blocks = (n + 255) / 256;
-        pt_maxabs_kernel<<<(unsigned)(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, st>>>(sin.dptr, img->dtype, n, acc, (int *)(acc + 1));
+        pt_maxabs_kernel<<<(unsigned)(blocks < sm_count() * 16 ? blocks : sm_count() * 16), 256, 0, st>>>(sin.dptr, img->dtype, n, acc, (int *)(acc + 1));
         count_launch();
         e = cudaGetLastError();
     }
@@ -456,7 +456,7 @@ int b2f_na_prepare(const b2f_array *img, int32_t na_mode, const b2f_array *imgtm
     if (!rc && e == cudaSuccess) e = cudaMemsetAsync(flag, 0, 4, st);
     if (!rc && e == cudaSuccess) {
         const long long blocks = (n + 255) / 256;
-        pt_na_prepare_kernel<<<(unsigned)(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, st>>>(
+        pt_na_prepare_kernel<<<(unsigned)(blocks < sm_count() * 16 ? blocks : sm_count() * 16), 256, 0, st>>>(
             sin.dptr, img->dtype, n, na_mode, imgtmp ? st1.dptr : nullptr, imgtmp ? imgtmp->dtype : 0, valid ? st2.dptr : nullptr,
             valid ? valid->dtype : 0, flag);
         count_launch();
@@ -492,7 +492,7 @@ int b2f_divide(const b2f_array *out, const b2f_array *den, void *stream) {
     cudaError_t e = cudaSuccess;
     if (!rc) {
         const long long blocks = (n + 255) / 256;
-        pt_divide_kernel<<<(unsigned)(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, st>>>(so.dptr, out->dtype, sd.dptr, den->dtype, n);
+        pt_divide_kernel<<<(unsigned)(blocks < sm_count() * 16 ? blocks : sm_count() * 16), 256, 0, st>>>(so.dptr, out->dtype, sd.dptr, den->dtype, n);
         count_launch();
         e = cudaGetLastError();
         if (e == cudaSuccess && out->mem == B2F_HOST) {
@@ -534,7 +534,7 @@ int b2f_normalize_dims(const b2f_array *out, const double *const *factors, void 
     }
     if (e == cudaSuccess) {
         const long long blocks = (n + 255) / 256;
-        pt_normalize_dims_kernel<<<(unsigned)(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, st>>>(so.dptr, out->dtype, n, F);
+        pt_normalize_dims_kernel<<<(unsigned)(blocks < sm_count() * 16 ? blocks : sm_count() * 16), 256, 0, st>>>(so.dptr, out->dtype, n, F);
         count_launch();
         e = cudaGetLastError();
     }

@@ -71,7 +71,7 @@ static void strip_geometry(S2Params<CT, 1> &P, long long nbatch) {
     constexpr int PX = S2Vec<CT>::PX;
     constexpr int CW = 32 * PX;
     P.nsx = (P.rw + CW - 1) / CW;
-    const long long want = 148LL * 16 * 6;
+    const long long want = (long long)sm_count() * 16 * 6;
     int SH = 256;
     while (SH > 32 && (long long)P.nsx * ((P.rh + SH - 1) / SH) * nbatch < want) SH >>= 1;
     P.SH = SH;
@@ -319,9 +319,11 @@ static int imfilter_slab_impl(const b2f_array *img, const b2f_array *out, const 
     if (zlo == 0 && zhi == 0) n_halo_lo = n_halo_hi = 0;   // nothing acts along the sharded axis: halos are not read
     int64_t nplanes = n_halo_lo + own_n + n_halo_hi;
     void *ext = nullptr;
+    AsyncFrees ext_guard(st);                // released on every exit, error returns included
     const void *src = img->ptr;
     if (n_halo_lo + n_halo_hi > 0) {
         B2F_CUDA(cudaMallocAsync(&ext, (size_t)(plane * nplanes) * esz, st));
+        ext_guard.push_back(ext);
         char *e = (char *)ext;
         if (n_halo_lo) B2F_CUDA(cudaMemcpyAsync(e, halo_lo, (size_t)(plane * n_halo_lo) * esz, cudaMemcpyDefault, st));
         B2F_CUDA(cudaMemcpyAsync(e + (size_t)(plane * n_halo_lo) * esz, img->ptr, (size_t)(plane * own_n) * esz, cudaMemcpyDefault, st));
@@ -332,7 +334,6 @@ static int imfilter_slab_impl(const b2f_array *img, const b2f_array *out, const 
     rc = out->dtype == B2F_F32
              ? run_slab_typed<float>(P, last, src, img->dtype, out->ptr, nplanes, n_halo_lo, own_n, global_last_dim, slab_first, st)
              : run_slab_typed<double>(P, last, src, img->dtype, out->ptr, nplanes, n_halo_lo, own_n, global_last_dim, slab_first, st);
-    if (ext) cudaFreeAsync(ext, st);
     return rc;
 }
 

@@ -63,7 +63,7 @@ static int run_typed(const Plan *plans, const void *d_img, int img_dt, void *con
     const long long nbatch = P0.img_ax.len(2) * P0.img_ax.len(3);
     P.nsx = (P.rw + CW - 1) / CW;
     // strip height: as tall as possible (less y-halo re-read) while still filling the machine with warps
-    const long long want = 148LL * 16 * 6;
+    const long long want = (long long)sm_count() * 16 * 6;
     int SH = 256;
     while (SH > 32 && (long long)P.nsx * ((P.rh + SH - 1) / SH) * nbatch < want) SH >>= 1;
     P.SH = SH;

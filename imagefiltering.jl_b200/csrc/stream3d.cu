@@ -132,7 +132,7 @@ int run_stream3d_slab(const Plan &Pl, const void *own, const void *lo, int64_t l
     // 46% full).  So: the first `nfull` tiles (whole waves) march all planes, the remaining tiles are cut into `kch`
     // chunks each, which fills the last wave evenly.  (nfull, kch) minimise the makespan of that list schedule.
     const long long tiles = (long long)P.ntx * P.nty;
-    const int ov = P.Lz - 1 + 3, SMS = 148;
+    const int ov = P.Lz - 1 + 3, SMS = sm_count();
     // closed form: w whole waves of full marches, then ceil(rest * k / SMS) waves of chunks
     long long best_full = tiles, best_k = 1, best_cost = ((tiles + SMS - 1) / SMS) * (own_n + ov);
     for (long long w = 0; w * SMS <= tiles; ++w) {

@@ -270,6 +270,7 @@ def imfilter(*args, _library=None):
     border, alg = _split_tail(args[2:])
     if r is not None and alg is not None:
         raise TypeError("MethodError: a resource and an algorithm cannot both be given")
+    r_given = r is not None
     r = _resolve_resource(r, alg)
     if isinstance(img, ColorArray):
         return _imfilter_color(r, T, img, kernel, border, _library)
@@ -279,9 +280,14 @@ def imfilter(*args, _library=None):
     S = _img_eltype(img)
     if not isinstance(kernel, tuple):
         kd = _kernel_dtype(kernel)
-        int_path = (T.kind in "iu" and not isinstance(S, str) and np.dtype(S).kind in "iub"
+        int_path = (T.kind in "iub" and not isinstance(S, str) and np.dtype(S).kind in "iub"
                     and kd is not None and np.dtype(kd).kind in "iub")
-        kernel = factorkernel(kernel, int_path)
+        if int_path and not r_given and not isinstance(kernel, Laplacian):
+            # src/imfilter.jl:10-12: T, TI, TK <: Integer (no resource given) wraps the kernel as `(kernel,)` WITHOUT
+            # kernelshift — a plain array keeps its axes 1:n (out[i] = sum_j A[i+j] k[j], j = 1..n), an OffsetArray its own
+            kernel = (kernel,)
+        else:
+            kernel = factorkernel(kernel, int_path)
     desc, ndim, first, shape, keep = _as_input(img)
     stages = build_stages(kernel, ndim)
     out = allocate_output(T, first, shape, stages, border)

@@ -38,19 +38,21 @@ def _lib(_library):
     return lib()                        # raises when the CUDA extension is missing: no CPU path
 
 
-def _unravel_array(lin, shape):
-    """0-based column-major linear indices -> (n, N) int64 array of 1-based indices (Julia CartesianIndex rows)."""
+def _unravel_array(lin, shape, first=None):
+    """0-based column-major linear indices -> (n, N) int64 array of indices along the array's own axes (Julia
+    CartesianIndex rows: 1-based for a plain Array, offset by `first` for an OffsetArray)."""
     if len(lin) == 0:
         return np.empty((0, len(shape)), dtype=np.int64)
-    return np.stack(np.unravel_index(lin, shape, order="F"), axis=1).astype(np.int64) + 1
+    base = np.asarray(first if first is not None else (1,) * len(shape), dtype=np.int64)
+    return np.stack(np.unravel_index(lin, shape, order="F"), axis=1).astype(np.int64) + base
 
 
-def _unravel(lin, shape):
-    return list(map(tuple, _unravel_array(lin, shape).tolist()))
+def _unravel(lin, shape, first=None):
+    return list(map(tuple, _unravel_array(lin, shape, first).tolist()))
 
 
 def _findlocalextrema(minima, img, window, edges, _library, as_array=False):
-    desc, ndim, _first, shape, keep = _as_input(img)
+    desc, ndim, first, shape, keep = _as_input(img)
     if window is None:
         window = (3,) * ndim            # default_window: 3 on every spatial axis (src/extrema.jl:107)
     if isinstance(edges, bool):
@@ -58,7 +60,8 @@ def _findlocalextrema(minima, img, window, edges, _library, as_array=False):
     if len(window) != ndim or len(edges) != ndim:
         raise ArgumentError("window and edges need one entry per dimension of img")
     lin = _lib(_library).findlocalextrema(desc, minima, window, edges)
-    return _unravel_array(lin, shape) if as_array else _unravel(lin, shape)
+    # CartesianIndices(img) carry the array's own axes (src/extrema.jl:125-162): an OffsetArray reports offset indices
+    return _unravel_array(lin, shape, first) if as_array else _unravel(lin, shape, first)
 
 
 def findlocalmaxima(img, *, window=None, edges=True, as_array=False, _library=None):

@@ -306,7 +306,7 @@ class ShardedImfilter:
         early = 0
         if self.lower is not None and self.ndim == 3:
             tiles_x = -(-int(self.slab.shape[-1]) // 32)
-            early = min(nrows, (-(-148 // tiles_x) + 1) * 64)               # tile rows of the first wave (+1 for the halo rows)
+            early = min(nrows, (-(-self.lib.sm_count() // tiles_x) + 1) * 64)               # tile rows of the first wave (+1 for the halo rows)
             if early >= nrows:
                 early = 0
         if self.lower is not None:

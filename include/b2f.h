@@ -125,6 +125,8 @@ int b2f_is_device_library(void);
 /* ---- device memory helpers (so the Julia side needs no CUDA.jl) --------------------------- */
 int b2f_set_device(int device);
 int b2f_device_count(int *count);
+/* multiprocessors of the current device (grid sizing of the sharded driver; 148 on a B200) */
+int b2f_sm_count(int *count);
 int b2f_malloc(void **dptr, uint64_t bytes);
 int b2f_free(void *dptr);
 int b2f_host_alloc(void **hptr, uint64_t bytes);   /* pinned */

@@ -135,6 +135,16 @@ def check_widening(ifb, lib):
         raise AssertionError("expected InexactError")
     ret = ifb.imfilter(np.int32, img, kern, _library=lib)
     assert ret.dtype == np.int32 and np.all(ret == G["widen_i16"]["value"])
+    # src/imfilter.jl:10-12: Int image x Int kernel x Int T (no resource) wraps the kernel as `(kernel,)` WITHOUT
+    # kernelshift: a plain vector keeps its axes 1:n, out[i] = sum_j A[i+j] k[j].  Derived from the method itself
+    # (the reference has no literal golden for it); a centred kernel or a resource argument takes the usual route.
+    a = np.arange(1, 8)
+    assert np.array_equal(ifb.imfilter(a, np.array([1, 0, 0]), _library=lib), [2, 3, 4, 5, 6, 7, 7])
+    assert np.array_equal(ifb.imfilter(a, ifb.centered(np.array([1, 0, 0])), _library=lib), [1, 1, 2, 3, 4, 5, 6])
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", DeprecationWarning)
+        r = ifb.imfilter(ifb.CUDALibs(ifb.Algorithm.FIR()), a, np.array([1, 0, 0]), _library=lib)
+    assert np.array_equal(r, [1, 1, 2, 3, 4, 5, 6])
 
 
 # ---- test/2d.jl:7-37 ------------------------------------------------------------------------------
