@@ -2,7 +2,7 @@
 #include <algorithm>
 #include <cstdlib>
 
-#include "stream3d.cuh"
+#include "stream3d_v3.cuh"
 
 namespace b2f {
 
@@ -60,12 +60,32 @@ template <int LXT, int LYT, int LZT>
 static int s3_launch_one(S3Params &P, const float *kz, cudaStream_t st) {
     long long nblocks;
     typedef S3C<LXT, LYT, LZT> C;
-    const size_t smem = C::SMEM;
-    auto kern = stream3d_kernel<LXT, LYT, LZT>;
+    // debugging knobs: B2F_S3_V=1 / 2 run the round-1 kernel / its one-plane-per-step successor (A/B on the same box),
+    // B2F_S3_CS=0 plain instead of streaming stores
+    static const int ver = getenv("B2F_S3_V") ? atoi(getenv("B2F_S3_V")) : 3;
+    static const bool cs = getenv("B2F_S3_CS") ? atoi(getenv("B2F_S3_CS")) != 0 : true;
+    typedef S3VC<LXT, LYT, LZT> C3;
+    const size_t smem = ver == 3 ? C3::SMEM : C::SMEM;
+    void (*kern)(const S3Params, const CUtensorMap, const CUtensorMap, const CUtensorMap) =
+        ver == 1 ? stream3d_kernel<LXT, LYT, LZT>
+                 : (cs ? stream3d_kernel2<LXT, LYT, LZT, true> : stream3d_kernel2<LXT, LYT, LZT, false>);
+    void (*kern3)(const S3Params, const S3VTaps, const CUtensorMap, const CUtensorMap, const CUtensorMap) =
+        cs ? stream3d_kernel3<LXT, LYT, LZT, true> : stream3d_kernel3<LXT, LYT, LZT, false>;
     static thread_local bool configured = false;
     if (!configured) {
-        B2F_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (ver == 3) B2F_CUDA(cudaFuncSetAttribute(kern3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        else B2F_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
+    }
+    S3VTaps TZ;
+    memset(&TZ, 0, sizeof TZ);
+    {   // z taps right-aligned in K (odd) slots, as the pairs of the paired z stage
+        float kk[S3_MAXTAPS + 3] = {0};                      // kk[1 + j], j = -1 .. K
+        for (int j = 0; j < P.Lz; ++j) kk[1 + C3::K - P.Lz + j] = kz[j];
+        for (int i = 0; i <= C3::NP; ++i) {
+            TZ.p0[i] = make_float2(kk[1 + 2 * i - 1], kk[1 + 2 * i]);
+            TZ.p1[i] = make_float2(kk[1 + 2 * i], kk[1 + 2 * i + 1]);
+        }
     }
     for (int j = 0; j < S3_MAXTAPS; ++j) P.kzr[j] = 0.f;
     for (int j = 0; j < P.Lz; ++j) P.kzr[C::LBZ - P.Lz + j] = kz[j];      // right-aligned in the LBZ slots
@@ -90,7 +110,8 @@ static int s3_launch_one(S3Params &P, const float *kz, cudaStream_t st) {
         P.nfull = (int)std::min<long long>(tiles, (long long)P.nfull / ntx0 * P.ntx);
     }
     nblocks = P.nfull + ((long long)P.ntx * P.nty - P.nfull) * P.kch;
-    kern<<<(unsigned)nblocks, S3_NT, smem, st>>>(P, m_own, m_lo, m_hi);
+    if (ver == 3) kern3<<<(unsigned)nblocks, S3_NT, smem, st>>>(P, TZ, m_own, m_lo, m_hi);
+    else kern<<<(unsigned)nblocks, S3_NT, smem, st>>>(P, m_own, m_lo, m_hi);
     count_launch();
     B2F_CUDA(cudaGetLastError());
     return 0;
@@ -121,6 +142,7 @@ int run_stream3d_slab(const Plan &Pl, const void *own, const void *lo, int64_t l
     for (int j = 0; j < P.Lx; ++j) P.kx[j] = (float)sx.s->taps[j];
     for (int j = 1; j < P.Lx; ++j) P.kxp[j] = make_float2(P.kx[j], P.kx[j - 1]);
     for (int j = 0; j < P.Ly; ++j) P.ky[j] = (float)sy.s->taps[j];
+    for (int j = 1; j < P.Ly; ++j) P.kyp[j] = make_float2(P.ky[j], P.ky[j - 1]);
     for (int j = 0; j < P.Lz; ++j) kz[j] = (float)sz.s->taps[j];
     auto al16 = [](const void *p) { return reinterpret_cast<uintptr_t>(p) % 16 == 0; };
     P.use_tma = (P.W % 4 == 0) && al16(own) && (lo_n == 0 || al16(lo)) && (hi_n == 0 || al16(hi));

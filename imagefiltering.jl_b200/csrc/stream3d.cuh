@@ -33,6 +33,8 @@
 
 #include <cuda.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace b2f {
@@ -69,6 +71,7 @@ struct S3Params {
     float kx[S3_MAXTAPS], ky[S3_MAXTAPS];
     float kzr[S3_MAXTAPS];         // z taps RIGHT-aligned in the instantiation's LBZ slots
     float2 kxp[S3_MAXTAPS];        // kxp[j] = (kx[j], kx[j-1]): the taps one input value carries to two adjacent outputs
+    float2 kyp[S3_MAXTAPS];        // the same pairs of the y taps (v2: a thread owns 4 consecutive rows of one column)
 };
 
 __device__ __forceinline__ float2 s3_fma2(float2 a, float k, float2 c) {
@@ -142,6 +145,11 @@ __device__ __forceinline__ float4 s3_lds128(unsigned a) {
 __device__ __forceinline__ float2 s3_lds64(unsigned a) {
     float2 v;
     asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ float s3_lds32(unsigned a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
     return v;
 }
 __device__ __forceinline__ void s3_sts128(unsigned a, float4 v) {
@@ -454,6 +462,292 @@ stream3d_kernel(const __grid_constant__ S3Params P, const __grid_constant__ CUte
         }
         op += P.plane;
     }
+}
+
+// =====================================================================================================================
+// v2 of the marching kernel (round 2).  Same tile, rings, barriers and stage x as above; what changed:
+//   * stages y / z: a thread owns ONE column x FOUR consecutive rows (warp w = rows 4w..4w+3, lane = column).  Stage y
+//     reads 4 + Ly - 1 single floats of its column (LDS.32, one wavefront per warp and row: 20 B per voxel instead of
+//     the 36 B of the 2 x 2 mapping — shared-memory bandwidth was the tightest floor of v1) and feeds two row pairs in
+//     the value-broadcast x tap-pair form of stage x; stage z keeps the pairs (rows 0,1) and (rows 2,3) as float2
+//     partial sums; a finished plane leaves as four 128-byte row segments per warp;
+//   * the plane loop is split into ramp-up, STEADY STATE and drain: the steady-state body has no per-plane predicates
+//     (every sub-step is active, border patching is a compile-time flag), which removes the ~25 branches, the ISETPs and
+//     the BSSY/BSYNC pairs v1 executed per warp and plane.
+// =====================================================================================================================
+template <int LXT, int LYT, int LZT>
+__device__ __forceinline__ void s3_y_task4(const S3Params &P, const unsigned xb, float2 (&m)[2], const int Ly) {
+    typedef S3C<LXT, LYT, LZT> C;
+    m[0] = make_float2(0.f, 0.f);
+    m[1] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < 4 + C::LBY - 1; ++i) {
+        if (LYT || i < 4 + Ly - 1) {
+            const float s = s3_lds32(xb + i * (S3_XFP * 4));
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int j = i - 2 * h;            // row pair h = outputs (2h, 2h+1): taps (j, j-1) of input row i
+                if (j >= 0 && j <= C::LBY && (LYT || j <= Ly)) {
+                    if (j == 0) m[h].x = fmaf(s, P.ky[0], m[h].x);
+                    else if (j < C::LBY && (LYT || j < Ly)) m[h] = s3_fma2b(s, P.kyp[j], m[h]);
+                    else if (LYT || j == Ly) m[h].y = fmaf(s, P.ky[j - 1], m[h].y);
+                }
+            }
+        }
+    }
+}
+
+template <int LXT, int LYT, int LZT, bool CS>
+__device__ __forceinline__ void s3_z_update4(const S3Params &P, float2 (&acc)[2][S3C<LXT, LYT, LZT>::LBZ], const float2 (&m)[2],
+                                             const int Lz, float *__restrict__ op, const int W, const int nrow, const bool emit) {
+    typedef S3C<LXT, LYT, LZT> C;
+    float2 fin[2];
+    // the two 64-bit register operands of an FFMA2 must come from different register banks (bank = bit 1 of the register
+    // number); consecutive partial sums alternate banks, so the new value is kept in both: without the explicit second copy
+    // ptxas re-copies it for every other tap (~16 MOVs per plane in v1)
+    float2 mb[2];
+#pragma unroll
+    for (int o = 0; o < 2; ++o) {
+        asm volatile("mov.b32 %0, %1;" : "=f"(mb[o].x) : "f"(m[o].x));
+        asm volatile("mov.b32 %0, %1;" : "=f"(mb[o].y) : "f"(m[o].y));
+    }
+    {
+        const float k = P.kzr[C::LBZ - 1];
+#pragma unroll
+        for (int o = 0; o < 2; ++o) fin[o] = s3_fma2(((C::LBZ - 1) & 1) ? mb[o] : m[o], k, acc[o][C::LBZ - 1]);
+    }
+#pragma unroll
+    for (int j = C::LBZ - 2; j >= 0; --j) {
+        if (LZT || j >= C::LBZ - Lz) {
+            const float k = P.kzr[j];
+#pragma unroll
+            for (int o = 0; o < 2; ++o) acc[o][j + 1] = s3_fma2((j & 1) ? mb[o] : m[o], k, acc[o][j]);
+        }
+    }
+    if (emit) {
+        const float v[4] = {fin[0].x, fin[0].y, fin[1].x, fin[1].y};
+#pragma unroll
+        for (int o = 0; o < 4; ++o)
+            if (o < nrow) {
+                if (CS) __stcs(op + (long long)o * W, v[o]); else op[(long long)o * W] = v[o];
+            }
+    }
+}
+
+template <int LXT, int LYT, int LZT, bool CS>
+__global__ void __launch_bounds__(S3_NT, 1)
+stream3d_kernel2(const __grid_constant__ S3Params P, const __grid_constant__ CUtensorMap m_own,
+                 const __grid_constant__ CUtensorMap m_lo, const __grid_constant__ CUtensorMap m_hi) {
+    typedef S3C<LXT, LYT, LZT> C;
+    constexpr int TX = S3_TX, TY = S3_TY, RAWSZ = C::RAWSZ, XFSZ = C::XFSZ, LBZ = C::LBZ, N = S3_NRAW;
+
+    extern __shared__ __align__(1024) float s3_smem[];
+    float *raw = s3_smem;                       // N x RAWSZ
+    float *xf = raw + N * RAWSZ;                // S3_NXF x XFSZ
+    int *cell_src = reinterpret_cast<int *>(xf + S3_NXF * XFSZ);
+    unsigned short *cell_dst = reinterpret_cast<unsigned short *>(cell_src + C::NCELL);
+    int *ptw = reinterpret_cast<int *>(cell_dst + C::NCELL);
+    int *ptz = ptw + S3_PT;
+    const unsigned full = s3_sa(ptz + S3_PT), xfull = full + 8 * N, raw_sa = s3_sa(raw), xf_sa = s3_sa(xf);
+
+    int tid;
+    asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
+    const int warp = tid >> 5, lane = tid & 31;
+    const int Lx = LXT ? LXT : P.Lx, Ly = LYT ? LYT : P.Ly, Lz = LZT ? LZT : P.Lz;
+    const int bid = blockIdx.x;
+    int tile = bid, ch = 0, zc = P.own_n;
+    if (bid >= P.nfull) {
+        const int b2 = bid - P.nfull;
+        tile = P.nfull + b2 / P.kch;
+        ch = b2 - (tile - P.nfull) * P.kch;
+        zc = P.zchunk;
+    }
+    const int tx = tile % P.ntx, ty = tile / P.ntx;
+    const int x0 = tx * TX - P.xsh, y0 = ty * TY;
+    const int in_cols = TX + Lx - 1, in_rows = TY + Ly - 1;
+    const int zo0 = P.own_first + ch * zc;
+    const int nout = min(zc, P.own_first + P.own_n - zo0);
+    if (nout <= 0) return;
+    const int in_planes = nout + Lz - 1;
+    const int zin0 = zo0 + P.kloz;
+    const int xa = x0 + P.klox, ya = y0 + P.kloy;
+    const bool tma = P.use_tma != 0;
+
+    int cl = min(max(-xa, 0), in_cols), cr = min(max(P.W - xa, 0), in_cols);
+    const int rt = tma ? min(max(-ya, 0), in_rows) : 0, rb = tma ? min(max(P.H - ya, 0), in_rows) : in_rows;
+    if (!tma) cl = cr = in_cols;
+    const bool fix = !tma || (P.style != B2F_FILL && (cl > 0 || cr < in_cols || rt > 0 || rb < in_rows));
+    const int ncs = cl + (in_cols - cr), n1 = ncs * in_rows, wc = cr - cl, ncell = fix ? n1 + (rt + (in_rows - rb)) * wc : 0;
+    for (int idx = tid; idx < ncell; idx += S3_NT) {
+        int r, c;
+        if (idx < n1) {
+            r = idx / ncs;
+            const int k = idx - r * ncs;
+            c = k < cl ? k : cr + (k - cl);
+        } else {
+            const int i2 = idx - n1;
+            const int rr = i2 / wc;
+            c = cl + (i2 - rr * wc);
+            r = rr < rt ? rr : rb + (rr - rt);
+        }
+        const int sx = (int)remap_index(P.style, (int64_t)xa + c, (int64_t)P.W);
+        const int sy = (int)remap_index(P.style, (int64_t)ya + r, (int64_t)P.H);
+        cell_src[idx] = (sx < 0 || sy < 0) ? -1 : sy * P.W + sx;
+        cell_dst[idx] = (unsigned short)(r * S3_RWP + c);
+    }
+    if (tid == 0) {
+        for (int i = 0; i < N; ++i) s3_mbar_init(full + 8 * i, 1);
+        for (int i = 0; i < S3_NXF; ++i) s3_mbar_init(xfull + 8 * i, S3_NT / 32);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+
+    const int qb = -2;
+    auto locate_block = [&](int p0, int n) {
+        if (tid < n) {
+            const int p = p0 + tid;
+            int which = -1, zc = 0;
+            if (p >= 0 && p < in_planes) s3_locate(P, zin0 + p, which, zc);
+            ptw[p & (S3_PT - 1)] = which;
+            ptz[p & (S3_PT - 1)] = zc;
+        }
+    };
+    locate_block(qb, S3_PTA);
+    __syncthreads();
+
+    bool lo_ready = P.flag_lo == nullptr, hi_ready = P.flag_hi == nullptr;     // thread 0 only
+    auto wait_flag = [&](const unsigned char *f) {
+        unsigned long long t0 = 0, t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        while (*reinterpret_cast<const volatile unsigned char *>(f) != (unsigned char)P.epoch) {
+            __nanosleep(64);
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            if (t - t0 > 5000000000ULL) asm volatile("trap;");          // 5 s: a copy that never arrives is an error, not a hang
+        }
+        __threadfence_system();
+    };
+    auto issue = [&](int p) {                   // one thread: TMA of input plane p into its ring buffer
+        const int which = ptw[p & (S3_PT - 1)];
+        if (which == 1 && !lo_ready) { wait_flag(P.flag_lo + (ya + in_rows > P.lo_early_rows ? 1 : 0)); lo_ready = true; }
+        if (which == 2 && !hi_ready) { wait_flag(P.flag_hi); hi_ready = true; }
+        const int zc = which < 0 ? P.own_n : ptz[p & (S3_PT - 1)];
+        const void *map = which == 1 ? (const void *)&m_lo : which == 2 ? (const void *)&m_hi : (const void *)&m_own;
+        const int b = p & (N - 1);
+        s3_mbar_expect_tx(full + 8 * b, (unsigned)C::RAWBYTES);
+        s3_tma_load3d(raw_sa + b * (RAWSZ * 4), map, full + 8 * b, xa, ya, zc);
+    };
+    auto fixup = [&](int p) {                   // all threads: the gather list of input plane p
+        const int which = ptw[p & (S3_PT - 1)];
+        const float *src = which < 0 ? nullptr
+                                     : (which == 1 ? P.lo : which == 2 ? P.hi : P.own) + (long long)ptz[p & (S3_PT - 1)] * P.plane;
+        float *dst = raw + (p & (N - 1)) * RAWSZ;
+        for (int base = tid; base < ncell; base += 4 * S3_NT) {
+            float v[4];
+            int d[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int idx = base + k * S3_NT;
+                d[k] = -1;
+                if (idx < ncell) {
+                    const int so = cell_src[idx];
+                    d[k] = cell_dst[idx];
+                    v[k] = (src != nullptr && so >= 0) ? __ldg(src + so) : P.fill;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (d[k] >= 0) dst[d[k]] = v[k];
+        }
+        if (tma) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    };
+
+    if (tma && tid == 0)
+        for (int p = 0; p < min(S3_AHEAD, in_planes); ++p) issue(p);
+
+    // this thread's column and 4 rows in stages y / z
+    const int gx = x0 + lane, gy = y0 + 4 * warp;
+    const int nrow = (gx >= 0 && gx < P.W) ? min(4, P.H - gy) : 0;                  // <= 0: nothing to store
+    float *op = P.out + ((long long)(zo0 - P.own_first) + (qb - (Lz - 1))) * P.plane + (long long)gy * P.W + gx;
+    const int yoff = (4 * warp) * S3_XFP + lane;
+
+    float2 acc[2][LBZ];
+#pragma unroll
+    for (int o = 0; o < 2; ++o)
+#pragma unroll
+        for (int j = 0; j < LBZ; ++j) acc[o][j] = make_float2(0.f, 0.f);
+
+    constexpr int NW = S3_NT / 32, XW = (C::RH + 7) / 8, XOFF = NW > XW ? NW - XW : 0;
+    int wb = 0, wph = 0, ab = 0;                // xf slot / phase of plane q, xf slot of plane q + 1
+
+    // ---- general interval (ramp-up, drain, volumes without TMA): every sub-step behind its run-time predicate -------------
+    auto slow_interval = [&](const int q) {
+        if (((q + 2) & (S3_PTB - 1)) == 0) locate_block(q + S3_PTA, S3_PTB);
+        if (q >= 0) s3_mbar_wait(xfull + 8 * wb, wph);
+        if (tma && tid == 0 && q + 2 + S3_AHEAD < in_planes) issue(q + 2 + S3_AHEAD);
+        if (fix && q + 2 < in_planes) {
+            const int p = q + 2;
+            if (tma) s3_mbar_wait(full + 8 * (p & (N - 1)), (p / N) & 1);
+            fixup(p);
+        }
+        if (q + 1 < in_planes && q + 1 >= 0) {
+            const int p = q + 1;
+            const int xw = (p & 1) ? warp - XOFF : warp;
+            if (xw >= 0 && xw < XW) {
+                if (tma && !fix) s3_mbar_wait(full + 8 * (p & (N - 1)), (p / N) & 1);
+                s3_x_task<LXT, LYT, LZT>(P, raw_sa + (p & (N - 1)) * (RAWSZ * 4), xf_sa + ab * (XFSZ * 4), in_rows, Lx, xw, lane);
+            }
+            __syncwarp();
+            if (lane == 0) s3_mbar_arrive(xfull + 8 * ab);
+            ab = ab == S3_NXF - 1 ? 0 : ab + 1;
+        }
+        if (q < 0) {
+            __syncthreads();                    // prologue: the gathers of planes 0 and 1 land before stage x reads them
+        } else {
+            float2 m[2];
+            s3_y_task4<LXT, LYT, LZT>(P, xf_sa + (wb * XFSZ + yoff) * 4, m, Ly);
+            s3_z_update4<LXT, LYT, LZT, CS>(P, acc, m, Lz, op, P.W, nrow, q >= Lz - 1 && nrow > 0);
+            if (wb == S3_NXF - 1) { wb = 0; wph ^= 1; } else ++wb;
+        }
+        op += P.plane;
+    };
+    // ---- steady state: TMA issue, (patch,) stage x of plane q+1, stages y/z of plane q with a store: no predicates --------
+    auto fast_interval = [&](auto fixc, const int q) {
+        constexpr bool FIX = decltype(fixc)::value;
+        if (((q + 2) & (S3_PTB - 1)) == 0) locate_block(q + S3_PTA, S3_PTB);
+        s3_mbar_wait(xfull + 8 * wb, wph);
+        if (tid == 0) issue(q + 2 + S3_AHEAD);
+        if (FIX) {
+            const int p = q + 2;
+            s3_mbar_wait(full + 8 * (p & (N - 1)), (p / N) & 1);
+            fixup(p);
+        }
+        {
+            const int p = q + 1;
+            const int xw = (p & 1) ? warp - XOFF : warp;
+            if (xw >= 0 && xw < XW) {
+                if (!FIX) s3_mbar_wait(full + 8 * (p & (N - 1)), (p / N) & 1);
+                s3_x_task<LXT, LYT, LZT>(P, raw_sa + (p & (N - 1)) * (RAWSZ * 4), xf_sa + ab * (XFSZ * 4), in_rows, Lx, xw, lane);
+            }
+            __syncwarp();
+            if (lane == 0) s3_mbar_arrive(xfull + 8 * ab);
+            ab = ab == S3_NXF - 1 ? 0 : ab + 1;
+        }
+        float2 m[2];
+        s3_y_task4<LXT, LYT, LZT>(P, xf_sa + (wb * XFSZ + yoff) * 4, m, Ly);
+        s3_z_update4<LXT, LYT, LZT, CS>(P, acc, m, Lz, op, P.W, nrow, nrow > 0);
+        if (wb == S3_NXF - 1) { wb = 0; wph ^= 1; } else ++wb;
+        op += P.plane;
+    };
+
+    // steady state = [max(Lz-1, 0), in_planes - 2 - AHEAD): stores on, planes q+1 and q+2+AHEAD exist
+    const int q_fast0 = tma ? min(max(Lz - 1, 0), in_planes) : in_planes, q_fast1 = tma ? max(q_fast0, in_planes - 2 - S3_AHEAD) : in_planes;
+    int q = -2;
+    for (; q < q_fast0; ++q) slow_interval(q);
+    if (fix) {
+        for (; q < q_fast1; ++q) fast_interval(std::true_type{}, q);
+    } else {
+        for (; q < q_fast1; ++q) fast_interval(std::false_type{}, q);
+    }
+    for (; q < in_planes; ++q) slow_interval(q);
 }
 
 }  // namespace b2f

@@ -433,6 +433,37 @@ def test_stream3d_parity(ifb, oracle, device, border, monkeypatch):
     assert np.max(np.abs(pa.astype(np.float64) - pb.astype(np.float64))) <= _tol([k.data.parent for k in g((4, 4, 4))], img)
 
 
+@pytest.mark.parametrize("border", BORDERS + ["fill"])
+def test_stream3d_more_tiles_than_sms(ifb, oracle, device, border):
+    """The MIXED schedule of the fused 3-D kernel — whole waves of tiles marching every plane plus the remaining tiles cut
+    into z-chunks (`bid >= nfull`, `kch > 1`; csrc/stream3d.cu) — needs more tiles than SMs: 544 x 576 x 40 is 17 x 9 = 153
+    tiles of 32 x 64 (148 whole marches + 5 tiles x 5 chunks of 8 planes on a B200).  This is the schedule the 1024^3
+    benchmark runs; every voxel is compared with the oracle."""
+    rng = np.random.default_rng(seed_of("s3-mixed", border))
+    shape = (544, 576, 40)
+    img = np.asfortranarray(rng.random(shape, dtype=np.float32))
+    kern = ifb.KernelFactors.gaussian((4, 4, 4))
+    b = ifb.Fill(0.25) if border == "fill" else border
+    pa, pb = _both(ifb, oracle, np.float32, img, kern, b)
+    assert device.last_path() == "stream3d"
+    err = np.abs(pa.astype(np.float64) - pb.astype(np.float64))
+    tol = _tol([k.data.parent for k in kern], img)
+    assert err.max() <= tol, (border, float(err.max()), np.unravel_index(err.argmax(), err.shape))
+
+
+def test_extrema_full_hd_batch(ifb, oracle, device):
+    """BASELINE config 4 at its real image size: mapwindow(extrema|minimum|maximum, img, (7,7)) on a 1920 x 1080 x 4 batch,
+    bit-exact against the oracle (src/mapwindow.jl:388-473 semantics: window truncated at the image ends)."""
+    rng = np.random.default_rng(4)
+    img = np.asfortranarray(rng.random((1920, 1080, 4), dtype=np.float32))
+    mm = ifb.mapwindow(ifb.extrema, img, (7, 7, 1))
+    assert device.last_path().startswith("extrema")
+    mo = ifb.mapwindow(ifb.extrema, img, (7, 7, 1), _library=oracle)
+    assert np.array_equal(mm["min"], mo["min"]) and np.array_equal(mm["max"], mo["max"])
+    assert np.array_equal(ifb.mapwindow(ifb.minimum, img, (7, 7, 1)), mo["min"])
+    assert np.array_equal(ifb.mapwindow(ifb.maximum, img, (7, 7, 1)), mo["max"])
+
+
 @pytest.mark.parametrize("dt", [np.float32, np.float64, np.uint8, np.int32, np.int64])
 def test_findlocalextrema_parity(ifb, oracle, device, dt):
     """Strict-peak scan (src/extrema.jl:125-162): GPU index lists == oracle index lists (same order), for plateaus
