@@ -311,7 +311,7 @@ stream3d_kernel3(const __grid_constant__ S3Params P, const __grid_constant__ S3V
         op += 2 * P.plane;
     };
     // thread 0, after its arrival: the TMAs of planes p0+N, p0+N+1 go out (their ring buffers were read by stage x in the
-    // previous step, which this step's barrier wait has seen complete); then the planes of the step after next must have landed
+    // previous step, which this step's barrier wait has seen complete)
     auto tma_work = [&](const int p0, const bool all) {
         if (tma && tid == 0) {
 #pragma unroll
@@ -328,9 +328,15 @@ stream3d_kernel3(const __grid_constant__ S3Params P, const __grid_constant__ S3V
                     }
                 }
             }
+        }
+    };
+    // thread 0, BEFORE its arrival (warp 0 runs no stage x, so this sits in otherwise idle time): the planes the next step's
+    // stage x reads have landed — they were issued two steps ago.  The arrival publishes it to the CTA.
+    auto tma_check = [&](const int p0, const bool all) {
+        if (tma && tid == 0) {
 #pragma unroll
             for (int d = 0; d < 2; ++d) {
-                const int p = p0 + 6 + d;
+                const int p = p0 + 4 + d;
                 if (all || p < in_planes) landed(p);
             }
         }
@@ -347,6 +353,7 @@ stream3d_kernel3(const __grid_constant__ S3Params P, const __grid_constant__ S3V
             if (p0 + 5 < in_planes) patch(p0 + 5);
         }
         stage_x(p0 + 2, p0 + 2 < in_planes, p0 + 3 < in_planes);
+        tma_check(p0, false);
         arrive_next();
         tma_work(p0, false);
         if (s >= 0) {
@@ -372,6 +379,7 @@ stream3d_kernel3(const __grid_constant__ S3Params P, const __grid_constant__ S3V
         if (!ok) s3_mbar_wait(xfull + 8 * bi, ph);
         if (FIX) { patch(p0 + 4); patch(p0 + 5); }
         stage_x(p0 + 2, true, true);
+        tma_check(p0, true);
         arrive_next();
         tma_work(p0, true);
         float2 ma[2], mb[2];
