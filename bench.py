@@ -1,20 +1,27 @@
 #!/usr/bin/env python
-"""bench.py — headline benchmark of the B200 FIR path (BASELINE.json metric: imfilter Gpixel/s and
-% of the HBM roofline, next to the CPU reference path).
+"""bench.py — the BASELINE.json metric: imfilter Gpixel/s and % of the HBM roofline at 1/2/4/8 B200, next to the CPU
+reference path.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--only c5,c2]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N
 
-Workload (BASELINE.json configs[1]): imgradients(img, KernelFactors.sobel, Pad(:reflect)) on
-4096x4096 N0f8 images, reference-typed outputs (two Float64 gradient planes, bit-exact mode).
-One step = one fused launch over a batch of BATCH images per GPU (weak scaling: every rank owns
-its own batch; the path has no exchange step, so there is no collective in the data path).
+Headline workload = BASELINE configs[4] ("C5"), the only config the 1/2/4/8 clause of the metric applies to and the largest one
+that fits a GPU:  imfilter(Float32, vol, KernelFactors.gaussian((4,4,4)), Pad(:symmetric)) on a 1024^3 Float32 volume
+(17+17+17 taps, 8 B/voxel algorithmic).  One step = one filter pass over the whole volume.
 
-  value      Gpixel/s, inputs and outputs resident in HBM, CUDA-event timed, max over ranks
-  e2e        same metric through the C ABI with HOST (pinned) buffers: H2D + launch + D2H per step
-  roofline   algorithmic bytes (17 B/px = 1 in + 2x8 out) / average launch time vs measured HBM peak
-  cpu_baseline  the CPU oracle's CPUThreads(FIRTiled) restatement on the host cores (bounded sample)
+  N = 1    one fused launch (csrc/stream3d_v3.cuh), volume resident in HBM (8.6 GB in+out: far larger than L2).
+  N > 1    STRONG scaling: the volume is slab-decomposed along the last axis (imagefiltering.jl_b200/sharded.py), every rank
+           owns 1024/N planes; a step = neighbour hand-shake + halo transport over NVLink + the fused kernel; timed per rank with
+           CUDA events between barriers, max over ranks.
 
-`--impl reference` times that CPU restatement alone (Julia is not in the image).
+  value      Gpixel/s of the whole job, device-resident                      e2e   same call with HOST buffers (H2D + D2H inside)
+  roofline   algorithmic bytes / average launch time vs the measured HBM peak (MEASURED_PEAKS.json)
+  configs    every BASELINE config (c1..c5) on this run's GPUs: ms, Gpixel/s, roofline, e2e, cpu_baseline
+  parity     every config checked against the CPU oracle AT ITS BENCHMARKED SIZE on sampled regions before it is timed
+             (C5: tiles of both schedules over all planes incl. both global faces, every slab seam +- 8 planes; C1..C4: a
+             full-height strip incl. three image edges and the opposite corner); a miss fails the run (exit code 3)
+  cpu_baseline / --impl reference   the oracle's restatement of CPUThreads(Algorithm.FIRTiled()) on the host cores (Julia is
+             not in the image: a C++ restatement, kind "port"), a bounded sample of the same workload
 """
 import argparse
 import ctypes as C
@@ -30,11 +37,16 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-W = H = 4096
-BATCH = 8            # images per GPU per step, device-resident arm (in 134 MB, out 2.1 GB: both > L2)
-E2E_BATCH = 2        # images per GPU per step, host-buffer arm
-BYTES_PER_PX = 1 + 2 * 8
 FALLBACK_HBM_GBS = 6650.0
+METRIC = "imfilter_gpixel_per_s"
+WORKLOAD = {
+    "c1": "C1 imfilter 2048x2048 Float32, KernelFactors.gaussian((3,3)) 13+13 taps, Pad(:replicate) (BASELINE configs[0]); batch of 64 images",
+    "c2": "C2 imgradients Sobel 4096x4096 N0f8, Pad(:reflect) -> 2x Float64 bit-exact (BASELINE configs[1]); batch of 8 images",
+    "c3": "C3 imfilter 8192x8192 Float32, Kernel.LoG(3) 27x27 dense, Pad(:circular) (BASELINE configs[2])",
+    "c4": "C4 mapwindow(extrema, img, (7,7)) over 256 1920x1080 Float32 images (BASELINE configs[3])",
+    "c5": "C5 imfilter 1024x1024x1024 Float32, KernelFactors.gaussian((4,4,4)) 17+17+17 taps, Pad(:symmetric) (BASELINE configs[4])",
+}
+HEADLINE = "c5"
 
 
 def peaks():
@@ -96,240 +108,715 @@ class ClockSampler:
             for n, v in zip(names, f[2:6]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+        busy = [x for x in sm if mx and x > 0.4 * mx] or sm
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
                 "samples": len(sm)}
 
 
-def sobel_stages(ifb, ndim=3):
-    from importlib import import_module
-    imf = import_module("imagefiltering_jl_b200.imfilter")
-    ext = (True, True) + (False,) * (ndim - 2)
-    k1 = ifb.KernelFactors.sobel(ext, 1)
-    k2 = ifb.KernelFactors.sobel(ext, 2)
-    return ifb._abi.StageList(imf.build_stages(k1, ndim) + imf.build_stages(k2, ndim)), ndim
+# =====================================================================================================================
+# CPU side: the oracle (test infrastructure) as parity checker and as the timed CPU baseline
+# =====================================================================================================================
+class Oracle:
+    def __init__(self):
+        import imagefiltering_jl_b200 as ifb
+        from importlib import import_module
+        self.ifb = ifb
+        self.imf = import_module("imagefiltering_jl_b200.imfilter")
+        path = os.path.join(ROOT, "oracle", "libb2f_oracle.so")
+        if not os.path.exists(path):
+            subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")])
+        self.lib = ifb._abi.Library(path)
+        fn = self.lib.dll.b2f_oracle_imfilter_tiled
+        A = ifb._abi
+        fn.argtypes = [C.POINTER(A.b2f_array), C.POINTER(A.b2f_array), C.POINTER(A.b2f_stage), C.c_int32, C.POINTER(A.b2f_border),
+                       C.POINTER(C.c_int64), C.c_int32]
+        self.tiled_fn = fn
+        self.threads = os.cpu_count() or 1
+
+    def tiled(self, img_desc, out_desc, stages, border, tile, threads=None):
+        """CPUThreads(Algorithm.FIRTiled(tile)) restatement (oracle.cpp b2f_oracle_imfilter_tiled; src/imfilter.jl:476-542)."""
+        t = (C.c_int64 * 4)(*(list(tile) + [1] * (4 - len(tile))))
+        rc = self.tiled_fn(C.byref(img_desc), C.byref(out_desc), stages.arr, stages.n, C.byref(border), t, threads or self.threads)
+        if rc != 0:
+            raise RuntimeError(self.lib.dll.b2f_last_error().decode())
 
 
-# ---------------------------------------------------------------------------------------------------
-def cpu_reference_run(steps, warmup, threads=None):
-    """CPUThreads(Algorithm.FIRTiled()) restatement (oracle/oracle.cpp b2f_oracle_imfilter_tiled) on ONE
-    4096x4096 N0f8 image per step: both Sobel gradients, each padded and filtered independently, exactly
-    as imgradients does (reference src/specialty.jl:47-51)."""
-    import imagefiltering_jl_b200 as ifb
-    from importlib import import_module
-    imf = import_module("imagefiltering_jl_b200.imfilter")
-    path = os.path.join(ROOT, "oracle", "libb2f_oracle.so")
-    if not os.path.exists(path):
-        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")])
-    lib = ifb._abi.Library(path)
-    fn = lib.dll.b2f_oracle_imfilter_tiled
-    fn.argtypes = [C.POINTER(ifb._abi.b2f_array), C.POINTER(ifb._abi.b2f_array), C.POINTER(ifb._abi.b2f_stage),
-                   C.c_int32, C.POINTER(ifb._abi.b2f_border), C.POINTER(C.c_int64), C.c_int32]
-    threads = threads or os.cpu_count() or 1
-    rng = np.random.default_rng(2)
-    raw = np.asfortranarray(rng.integers(0, 256, size=(W, H), dtype=np.uint8))
-    img = ifb._abi.numpy_array_desc(raw, (1, 1), ifb._abi.N0F8)
-    outs = [np.empty((W, H), dtype=np.float64, order="F") for _ in range(2)]
-    odesc = [ifb._abi.numpy_array_desc(o, (1, 1)) for o in outs]
-    border = ifb.Pad("reflect").to_abi(2)
-    stl = [ifb._abi.StageList(imf.build_stages(ifb.KernelFactors.sobel((True, True), d), 2)) for d in (1, 2)]
-    tile = (C.c_int64 * 4)(64, 64, 1, 1)     # 32 KiB Float64 tiles (L1-sized, TiledIteration.padded_tilesize's intent)
-
-    def step():
-        for d in range(2):
-            rc = fn(C.byref(img), C.byref(odesc[d]), stl[d].arr, 2, C.byref(border), tile, threads)
-            if rc != 0:
-                raise RuntimeError(lib.dll.b2f_last_error().decode())
-
+def _time_cpu(fn, steps, warmup):
     for _ in range(warmup):
-        step()
+        fn()
     t0 = time.perf_counter()
     for _ in range(steps):
-        step()
-    dt = time.perf_counter() - t0
-    return (W * H * steps) / dt / 1e9, dt / steps * 1e3, threads
+        fn()
+    return (time.perf_counter() - t0) / steps
+
+
+def cpu_sample(name, orc, steps=2, warmup=1):
+    """A bounded sample of config `name` on the host cores -> (Gpixel/s, threads, description).  Separable cascades run the
+    tiled multi-thread restatement on all cores; the dense kernel (C3) and mapwindow (C4) are single-threaded in the reference
+    whatever the resource, so they are timed on one thread."""
+    ifb, A = orc.ifb, orc.ifb._abi
+    if name in ("c1", "c5"):
+        if name == "c1":
+            shape, kern, border, tile = (2048, 2048), ifb.KernelFactors.gaussian((3, 3)), ifb.Pad("replicate"), (64, 64)
+            rng = np.random.default_rng(1)
+        else:
+            shape, kern, border, tile = (256, 256, 256), ifb.KernelFactors.gaussian((4, 4, 4)), ifb.Pad("symmetric"), (32, 48, 48)
+            rng = np.random.default_rng(5)
+        nd = len(shape)
+        img = np.asfortranarray(rng.random(shape, dtype=np.float32))
+        out = np.empty(shape, dtype=np.float64, order="F")       # reference-typed: Float64 taps -> Float64 result
+        st = A.StageList(orc.imf.build_stages(kern, nd))
+        di, do, b = A.numpy_array_desc(img, (1,) * nd), A.numpy_array_desc(out, (1,) * nd), border.to_abi(nd)
+        dt = _time_cpu(lambda: orc.tiled(di, do, st, b, tile), steps, warmup)
+        what = ("one 2048x2048 image" if name == "c1" else "a 256^3 sub-volume (1/64 of the workload; per-voxel rate extrapolates linearly)")
+        return np.prod(shape) / dt / 1e9, orc.threads, f"{what}, CPUThreads(FIRTiled{tile}) restatement on {orc.threads} threads, {dt * 1e3:.0f} ms/step"
+    if name == "c2":
+        raw = np.asfortranarray(np.random.default_rng(2).integers(0, 256, size=(4096, 4096), dtype=np.uint8))
+        img = A.numpy_array_desc(raw, (1, 1), A.N0F8)
+        outs = [np.empty((4096, 4096), dtype=np.float64, order="F") for _ in range(2)]
+        od = [A.numpy_array_desc(o, (1, 1)) for o in outs]
+        b = ifb.Pad("reflect").to_abi(2)
+        stl = [A.StageList(orc.imf.build_stages(ifb.KernelFactors.sobel((True, True), d), 2)) for d in (1, 2)]
+
+        def step():     # imgradients = two independent imfilter calls, each padding the input again (src/specialty.jl:47-51)
+            for d in range(2):
+                orc.tiled(img, od[d], stl[d], b, (64, 64))
+        dt = _time_cpu(step, steps, warmup)
+        return 4096 * 4096 / dt / 1e9, orc.threads, f"one 4096x4096 N0f8 image (both gradients), CPUThreads(FIRTiled) restatement on {orc.threads} threads, {dt * 1e3:.0f} ms/step"
+    if name == "c3":
+        shape = (512, 512)
+        img = np.asfortranarray(np.random.default_rng(3).random(shape, dtype=np.float32))
+        kern = (ifb.Kernel.LoG(3),)
+        dt = _time_cpu(lambda: ifb.imfilter(ifb.CUDALibs(ifb.Algorithm.FIR()), img, kern, ifb.Pad("circular"), _library=orc.lib), steps, warmup)
+        return np.prod(shape) / dt / 1e9, 1, f"a 512x512 crop (1/256 of the image), dense loop on 1 thread (single-threaded in the reference), {dt * 1e3:.0f} ms/step"
+    if name == "c4":
+        img = np.asfortranarray(np.random.default_rng(4).random((1920, 1080), dtype=np.float32))
+        dt = _time_cpu(lambda: ifb.mapwindow(ifb.extrema, img, (7, 7), _library=orc.lib), steps, warmup)
+        return 1920 * 1080 / dt / 1e9, 1, f"one 1920x1080 image of the 256, streaming extrema on 1 thread (single-threaded in the reference), {dt * 1e3:.0f} ms/step"
+    raise KeyError(name)
 
 
 def reference_arm(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    """--impl reference: the CPU restatement of the headline workload, one bounded sample per step, same JSON keys."""
+    if int(os.environ.get("RANK", "0")) != 0:
         return
-    steps = max(1, min(args.steps, 10))
-    gpx, ms, threads = cpu_reference_run(steps, max(1, min(args.warmup, 2)))
+    orc = Oracle()
+    ifb, A = orc.ifb, orc.ifb._abi
+    shape, kern, border, tile = (256, 256, 256), ifb.KernelFactors.gaussian((4, 4, 4)), ifb.Pad("symmetric"), (32, 48, 48)
+    img = np.asfortranarray(np.random.default_rng(5).random(shape, dtype=np.float32))
+    out = np.empty(shape, dtype=np.float64, order="F")
+    st = A.StageList(orc.imf.build_stages(kern, 3))
+    di, do, b = A.numpy_array_desc(img, (1, 1, 1)), A.numpy_array_desc(out, (1, 1, 1)), border.to_abi(3)
+    dt = _time_cpu(lambda: orc.tiled(di, do, st, b, tile), args.steps, args.warmup)
+    gpx = np.prod(shape) / dt / 1e9
+    sample = (f"each step filters a 256^3 sub-volume (1/64 of the 1024^3 workload; the per-voxel rate extrapolates linearly), "
+              f"CPUThreads(FIRTiled{tile}) restatement on {orc.threads} threads, Float64 result as the reference types it")
     line = {
-        "impl": "reference", "metric": "imfilter_gpixel_per_s", "value": gpx, "unit": "Gpixel/s", "n_gpus": args.gpus,
-        "steps": steps, "warmup": max(1, min(args.warmup, 2)), "ms_per_step": ms, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "imgradients Sobel 4096x4096 N0f8 Pad(:reflect) -> 2x Float64 (BASELINE configs[1])",
-                   "images_per_step": 1, "note": "CPU restatement of CPUThreads(Algorithm.FIRTiled()); Julia unavailable"},
-        "cpu_baseline": {"value": gpx, "unit": "Gpixel/s", "cores": threads, "kind": "port",
-                         "sample": "one 4096x4096 image per step (both gradients), %d steps" % steps},
+        "impl": "reference", "metric": METRIC, "value": gpx, "unit": "Gpixel/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": bench_config(args.gpus),
+        "cpu_baseline": {"value": gpx, "unit": "Gpixel/s", "cores": orc.threads, "kind": "port", "sample": sample},
         "e2e": {"value": gpx, "unit": "Gpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "note": "C++ restatement of the reference (oracle/oracle.cpp), not Julia: Julia is not in the image",
     }
     print(json.dumps(line), flush=True)
 
 
-# ---------------------------------------------------------------------------------------------------
-def ours_arm(args):
-    import torch
-    import torch.distributed as dist
-    import imagefiltering_jl_b200 as ifb
-    from importlib import import_module
-    lib = import_module("imagefiltering_jl_b200._lib").lib()   # raises if the CUDA extension is missing
+def bench_config(world):
+    return {"workload": WORKLOAD[HEADLINE], "volume": [1024, 1024, 1024], "kernel_taps": [17, 17, 17], "border": "Pad(:symmetric)",
+            "out_eltype": "Float32",
+            "parallelism": "one GPU, one fused launch" if world == 1 else f"{world} slabs along the last axis, halo of 8 planes per side over NVLink",
+            "l2": "working set 8.6 GB per step (4.3 GB in + 4.3 GB out), far larger than the 126 MB L2: no flush needed"}
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    dev = torch.device("cuda", local)
-    stream = torch.cuda.current_stream()
-    sptr = stream.cuda_stream
 
-    g = torch.Generator(device=dev)
-    g.manual_seed(2 + rank)
-    img = torch.randint(0, 256, (BATCH, H, W), dtype=torch.uint8, device=dev, generator=g)
-    gx = torch.empty((BATCH, H, W), dtype=torch.float64, device=dev)
-    gy = torch.empty_like(gx)
-    stages, nd = sobel_stages(ifb, 3)
-    border = ifb.Pad("reflect").to_abi(3)
-    d_img = ifb.DeviceArray.from_torch(img, n0f8=True).desc()
-    d_out = [ifb.DeviceArray.from_torch(gx).desc(), ifb.DeviceArray.from_torch(gy).desc()]
+# =====================================================================================================================
+# GPU side
+# =====================================================================================================================
+class G:
+    """Everything a config needs: torch, the package, the product library, device, stream, ranks."""
 
-    def step():
-        lib.imgradients(d_img, d_out, stages, 3, border, sptr)
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        import imagefiltering_jl_b200 as ifb
+        from importlib import import_module
+        self.torch, self.dist, self.ifb = torch, dist, ifb
+        self.imf = import_module("imagefiltering_jl_b200.imfilter")
+        self.sh = import_module("imagefiltering_jl_b200.sharded")
+        self.lib = import_module("imagefiltering_jl_b200._lib").lib()        # raises if the CUDA extension is missing
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            # pin the rank to its share of the host cores BEFORE any pinned host buffer is touched (first touch decides the
+            # NUMA node): ranks of the first half of the GPUs take the first half of the cores
+            try:
+                cores = sorted(os.sched_getaffinity(0))
+                per = max(1, len(cores) // self.world)
+                os.sched_setaffinity(0, cores[self.local * per:(self.local + 1) * per])
+            except Exception:
+                pass
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.stream = torch.cuda.current_stream()
+        self.sptr = self.stream.cuda_stream
+        self.A = ifb._abi
+        self.DA = ifb.DeviceArray
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
 
-    # clocks / throttle reasons are sampled from before the warm-up to the end of the timed region (the timed region of a
-    # short run is only a few ms long: sampling it alone could return no sample at all)
-    sampler = ClockSampler(local)
-    if rank == 0:
+    def max_over_ranks(self, vals):
+        t = self.torch.tensor(list(vals), dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return [float(x) for x in t.tolist()]
+
+    def sum_over_ranks(self, vals):
+        t = self.torch.tensor(list(vals), dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return [float(x) for x in t.tolist()]
+
+    def host_buffer(self, nbytes, np_dtype):
+        p = C.c_void_p()
+        self.lib.check(self.lib.dll.b2f_host_alloc(C.byref(p), int(nbytes)))
+        n = int(nbytes) // np.dtype(np_dtype).itemsize
+        ctype = {1: C.c_uint8, 4: C.c_float, 8: C.c_double}[np.dtype(np_dtype).itemsize]
+        arr = np.ctypeslib.as_array(C.cast(p, C.POINTER(ctype)), shape=(n,))
+        return p, arr.view(np_dtype) if arr.dtype != np.dtype(np_dtype) else arr
+
+    def host_free(self, p):
+        self.lib.dll.b2f_host_free(p)
+
+    def time_steps(self, step, steps, warmup):
+        """-> (ms per step over the whole timed region, mean ms of the individual steps), barrier + sync on both sides."""
+        t = self.torch
+        for _ in range(warmup):
+            step()
+        self.barrier()
+        ev = [(t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        a, b = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
+        self.lib.reset_launch_count()
+        a.record(self.stream)
+        for x, y in ev:
+            x.record(self.stream)
+            step()
+            y.record(self.stream)
+        b.record(self.stream)
+        self.barrier()
+        launches = self.lib.launch_count()
+        return a.elapsed_time(b) / steps, float(np.mean([x.elapsed_time(y) for x, y in ev])), launches
+
+
+def julia_view(t):
+    """torch C-contiguous (..., Y, X) tensor on any device -> numpy array in Julia axis order (X, Y, ...), Fortran-contiguous."""
+    a = t.detach().cpu().numpy()
+    return a.transpose(tuple(reversed(range(a.ndim))))
+
+
+class Parity:
+    """Accumulates oracle comparisons of one config: max |gpu - oracle| against the tolerance (0 = bit-exact required)."""
+
+    def __init__(self, tol):
+        self.tol, self.max_err, self.checked, self.bit_exact = tol, 0.0, 0, True
+
+    def add(self, got, ref):
+        got, ref = np.asarray(got), np.asarray(ref)
+        assert got.shape == ref.shape, (got.shape, ref.shape)
+        if not np.array_equal(got, ref):
+            self.bit_exact = False
+        e = float(np.max(np.abs(got.astype(np.float64) - ref.astype(np.float64)))) if got.size else 0.0
+        self.max_err = max(self.max_err, e)
+        self.checked += int(got.size)
+
+    def result(self):
+        ok = self.bit_exact if self.tol == 0 else self.max_err <= self.tol
+        return {"max_abs_err": self.max_err, "tolerance": self.tol, "bit_exact": self.bit_exact, "elements_checked": self.checked, "ok": bool(ok)}
+
+
+def _clip_block(lo, hi, n, h):
+    """Output range [lo, hi) of an axis of length n and the input block [b0, b1) the oracle needs for it: h extra elements on
+    every side that is an artificial cut; a side that is the true array edge stays the edge (the oracle pads it itself)."""
+    return max(0, lo - h), min(n, hi + h)
+
+
+def oracle_fir_region(orc, T, inp_t, kern, border, region, halo, n0f8=False):
+    """Oracle result of imfilter on the output `region` (list of (lo, hi) per Julia axis, 0-based) of the array held by torch
+    tensor `inp_t` (C order = reversed Julia axes).  Pad styles other than :circular: the block is cut out with `halo`
+    extra elements per artificial side and filtered with the real border, then cropped.  :circular: the block is gathered with
+    wrapped indices and filtered with Inner()."""
+    ifb = orc.ifb
+    nd = len(region)
+    dims = list(reversed(inp_t.shape))
+    if isinstance(border, ifb.Pad) and border.style == "circular":
+        idx = [np.arange(lo - h, hi + h) % n for (lo, hi), h, n in zip(region, halo, dims)]
+        blk = inp_t
+        for ax in range(nd):        # Julia axis ax is torch axis nd-1-ax
+            blk = blk.index_select(nd - 1 - ax, inp_t.new_tensor(idx[ax], dtype=__import__("torch").long))
+        a = np.asfortranarray(julia_view(blk))
+        r = ifb.imfilter(T, ifb.n0f8(a) if n0f8 else a, kern, ifb.Inner(), _library=orc.lib)
+        r = r.parent if isinstance(r, ifb.OffsetArray) else r
+        assert r.shape == tuple(hi - lo for lo, hi in region), (r.shape, region)
+        return r
+    cut = [_clip_block(lo, hi, n, h) for (lo, hi), h, n in zip(region, halo, dims)]
+    sl = tuple(slice(b0, b1) for b0, b1 in reversed(cut))
+    a = np.asfortranarray(julia_view(inp_t[sl]))
+    r = ifb.imfilter(T, ifb.n0f8(a) if n0f8 else a, kern, border, _library=orc.lib)
+    crop = tuple(slice(lo - b0, hi - b0) for (lo, hi), (b0, b1) in zip(region, cut))
+    return r[crop]
+
+
+def gpu_region(out_t, region):
+    sl = tuple(slice(lo, hi) for lo, hi in reversed(region))
+    return julia_view(out_t[sl])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# C1: separable 13+13-tap gaussian on a batch of 2048^2 Float32 images
+# ---------------------------------------------------------------------------------------------------------------------
+def run_c1(g, orc, steps, warmup, hbm):
+    t, ifb = g.torch, g.ifb
+    B = 64
+    gen = t.Generator(device=g.dev)
+    gen.manual_seed(1 + g.rank)
+    img = t.rand((B, 2048, 2048), device=g.dev, generator=gen)
+    kern3 = ifb.KernelFactors.gaussian((3, 3, 0))
+    st = g.A.StageList(g.imf.build_stages(kern3, 3))
+    border = ifb.Pad("replicate")
+    b = border.to_abi(3)
+    res = {}
+    kern2 = ifb.KernelFactors.gaussian((3, 3))
+    taps = [k.data.parent for k in kern2]
+    for key, T, bpp in (("f32", t.float32, 8), ("f64_reference_typed", t.float64, 12)):
+        out = t.empty((B, 2048, 2048), dtype=T, device=g.dev)
+        di, do = g.DA.from_torch(img).desc(), g.DA.from_torch(out).desc()
+        step = lambda: g.lib.imfilter(di, do, st, b, None, g.sptr)
+        step()
+        g.torch.cuda.synchronize()
+        NT = np.float32 if T == t.float32 else np.float64
+        tol = 0.0 if T == t.float64 else 1e-5 * float(np.prod([np.abs(k).sum() for k in taps]))
+        par = Parity(tol)
+        for bi in (0, B - 1):
+            for region in ([(0, 160), (0, 2048)], [(2048 - 160, 2048), (2048 - 160, 2048)]):
+                ref = oracle_fir_region(orc, NT, img[bi], kern2, border, region, (6, 6))
+                par.add(gpu_region(out[bi], region), ref)
+        ms, kms, launches = g.time_steps(step, steps, warmup)
+        ms, kms = g.max_over_ranks([ms, kms])
+        npx = B * 2048 * 2048
+        res[key] = {"ms": ms, "gpixel_per_s": g.world * npx / (ms * 1e-3) / 1e9,
+                    "roofline": {"bound": "hbm", "achieved": npx * bpp / (kms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                                 "frac": npx * bpp / (kms * 1e-3) / 1e9 / hbm, "algorithmic_bytes_per_px": bpp},
+                    "parity": par.result(), "kernel": g.lib.last_path(), "launches_per_step": launches / steps}
+        del out
+    # e2e: 8 images per step from pinned host memory, Float32 result
+    EB = 8
+    n = EB * 2048 * 2048
+    hp, hin = g.host_buffer(n * 4, np.float32)
+    op_, hout = g.host_buffer(n * 4, np.float32)
+    hin[:] = np.random.default_rng(11 + g.rank).random(n, dtype=np.float32)
+    hi_ = g.A.make_array(hp.value, g.A.F32, (2048, 2048, EB), (1, 1, 1), g.A.HOST)
+    ho_ = g.A.make_array(op_.value, g.A.F32, (2048, 2048, EB), (1, 1, 1), g.A.HOST)
+    ems, _, _ = g.time_steps(lambda: g.lib.imfilter(hi_, ho_, st, b, None, g.sptr), max(3, min(steps, 10)), 2)
+    ems, = g.max_over_ranks([ems])
+    g.host_free(hp)
+    g.host_free(op_)
+    out = {"workload": WORKLOAD["c1"], "scaling": "replicas (independent images per GPU)", "images_per_gpu_per_step": B,
+           "ms": res["f32"]["ms"], "gpixel_per_s": res["f32"]["gpixel_per_s"], "roofline": res["f32"]["roofline"],
+           "parity": res["f32"]["parity"], "kernel": res["f32"]["kernel"], "variants": res,
+           "e2e": {"value": g.world * n / (ems * 1e-3) / 1e9, "unit": "Gpixel/s", "h2d_bytes_per_step": n * 4, "d2h_bytes_per_step": n * 4,
+                   "images_per_gpu_per_step": EB}}
+    del img
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# C2: Sobel gradients of N0f8 images, two Float64 planes, bit-exact
+# ---------------------------------------------------------------------------------------------------------------------
+def run_c2(g, orc, steps, warmup, hbm):
+    t, ifb = g.torch, g.ifb
+    B, W = 8, 4096
+    gen = t.Generator(device=g.dev)
+    gen.manual_seed(2 + g.rank)
+    img = t.randint(0, 256, (B, W, W), dtype=t.uint8, device=g.dev, generator=gen)
+    ext = (True, True, False)
+    stl = g.A.StageList(g.imf.build_stages(ifb.KernelFactors.sobel(ext, 1), 3) + g.imf.build_stages(ifb.KernelFactors.sobel(ext, 2), 3))
+    border = ifb.Pad("reflect")
+    b = border.to_abi(3)
+    gx = t.empty((B, W, W), dtype=t.float64, device=g.dev)
+    gy = t.empty_like(gx)
+    di = g.DA.from_torch(img, n0f8=True).desc()
+    do = [g.DA.from_torch(gx).desc(), g.DA.from_torch(gy).desc()]
+    step = lambda: g.lib.imgradients(di, do, stl, 3, b, g.sptr)
+    step()
+    t.cuda.synchronize()
+    par = Parity(0.0)
+    for bi in (0, B - 1):
+        for region in ([(0, 256), (0, W)], [(W - 256, W), (W - 256, W)]):
+            for d, outp in ((1, gx), (2, gy)):
+                ref = oracle_fir_region(orc, np.float64, img[bi], ifb.KernelFactors.sobel((True, True), d), border, region, (1, 1), n0f8=True)
+                par.add(gpu_region(outp[bi], region), ref)
+    ms, kms, launches = g.time_steps(step, steps, warmup)
+    ms, kms = g.max_over_ranks([ms, kms])
+    npx = B * W * W
+    EB = 2
+    n = EB * W * W
+    hp, hin = g.host_buffer(n, np.uint8)
+    hin[:] = np.random.default_rng(12 + g.rank).integers(0, 256, size=n, dtype=np.uint8)
+    ops = [g.host_buffer(n * 8, np.float64) for _ in range(2)]
+    hi_ = g.A.make_array(hp.value, g.A.N0F8, (W, W, EB), (1, 1, 1), g.A.HOST)
+    ho_ = [g.A.make_array(p.value, g.A.F64, (W, W, EB), (1, 1, 1), g.A.HOST) for p, _ in ops]
+    ems, _, _ = g.time_steps(lambda: g.lib.imgradients(hi_, ho_, stl, 3, b, g.sptr), max(3, min(steps, 10)), 2)
+    ems, = g.max_over_ranks([ems])
+    g.host_free(hp)
+    for p, _ in ops:
+        g.host_free(p)
+    ach = npx * 17 / (kms * 1e-3) / 1e9
+    return {"workload": WORKLOAD["c2"], "scaling": "weak (independent images per GPU, no collective)", "images_per_gpu_per_step": B,
+            "ms": ms, "gpixel_per_s": g.world * npx / (ms * 1e-3) / 1e9,
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "algorithmic_bytes_per_px": 17},
+            "parity": par.result(), "kernel": g.lib.last_path(), "launches_per_step": launches / steps,
+            "e2e": {"value": g.world * n / (ems * 1e-3) / 1e9, "unit": "Gpixel/s", "h2d_bytes_per_step": n, "d2h_bytes_per_step": n * 16,
+                    "images_per_gpu_per_step": EB}}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# C3: dense 27x27 LoG, FP32-pipe bound
+# ---------------------------------------------------------------------------------------------------------------------
+def fp32_peak(g):
+    """Measured FP32 multiply-add peak of this GPU (a pure FFMA2 loop inside the library, CUDA-event timed)."""
+    r = C.c_double()
+    fn = g.lib.dll.b2f_bench_fma_peak
+    fn.argtypes = [C.POINTER(C.c_double), C.c_void_p]
+    g.lib.check(fn(C.byref(r), C.c_void_p(g.sptr)))
+    return float(r.value)
+
+
+def run_c3(g, orc, steps, warmup, hbm):
+    t, ifb = g.torch, g.ifb
+    n = 8192
+    gen = t.Generator(device=g.dev)
+    gen.manual_seed(3 + g.rank)
+    img = t.rand((n, n), device=g.dev, generator=gen)
+    out = t.empty_like(img)
+    kern = (ifb.Kernel.LoG(3),)
+    border = ifb.Pad("circular")
+    st = g.A.StageList(g.imf.build_stages(kern, 2))
+    b = border.to_abi(2)
+    di, do = g.DA.from_torch(img).desc(), g.DA.from_torch(out).desc()
+    step = lambda: g.lib.imfilter(di, do, st, b, None, g.sptr)
+    step()
+    t.cuda.synchronize()
+    kabs = float(np.abs(np.asarray(ifb.Kernel.LoG(3).parent, dtype=np.float64)).sum())
+    par = Parity(1e-5 * kabs)
+    for region in ([(0, 48), (0, n)], [(n - 96, n), (n - 96, n)]):      # a full-height strip on the wrap seam + the far corner
+        ref = oracle_fir_region(orc, np.float64, img, kern, border, region, (13, 13))
+        par.add(gpu_region(out, region), ref)
+    s3 = max(3, steps // 4)
+    ms, kms, launches = g.time_steps(step, s3, warmup)
+    ms, kms = g.max_over_ranks([ms, kms])
+    peak_tfma = fp32_peak(g)
+    fma = n * n * 729
+    ach = fma / (kms * 1e-3) / 1e12
+    hp, hin = g.host_buffer(n * n * 4, np.float32)
+    op_, _ = g.host_buffer(n * n * 4, np.float32)
+    hin[:] = np.random.default_rng(13 + g.rank).random(n * n, dtype=np.float32)
+    hi_ = g.A.make_array(hp.value, g.A.F32, (n, n), (1, 1), g.A.HOST)
+    ho_ = g.A.make_array(op_.value, g.A.F32, (n, n), (1, 1), g.A.HOST)
+    ems, _, _ = g.time_steps(lambda: g.lib.imfilter(hi_, ho_, st, b, None, g.sptr), 3, 1)
+    ems, = g.max_over_ranks([ems])
+    g.host_free(hp)
+    g.host_free(op_)
+    return {"workload": WORKLOAD["c3"], "scaling": "replicas (one image per GPU)", "steps": s3,
+            "ms": ms, "gpixel_per_s": g.world * n * n / (ms * 1e-3) / 1e9,
+            "roofline": {"bound": "fp32", "achieved": ach, "peak": peak_tfma, "unit": "TFMA/s", "frac": ach / peak_tfma,
+                         "peak_source": "measured: b2f_bench_fma_peak (pure FFMA2 loop) on this GPU",
+                         "hbm_frac": n * n * 8 / (kms * 1e-3) / 1e9 / hbm, "fma_per_px": 729},
+            "parity": par.result(), "kernel": g.lib.last_path(), "launches_per_step": launches / s3,
+            "e2e": {"value": g.world * n * n / (ems * 1e-3) / 1e9, "unit": "Gpixel/s", "h2d_bytes_per_step": n * n * 4,
+                    "d2h_bytes_per_step": n * n * 4}}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# C4: 7x7 running extrema over 256 full-HD images, sharded per GPU
+# ---------------------------------------------------------------------------------------------------------------------
+def run_c4(g, orc, steps, warmup, hbm):
+    t, ifb = g.torch, g.ifb
+    total, X, Y = 256, 1920, 1080
+    first, B = g.sh.slab_bounds(total, g.world, g.rank)         # 256 / N images per GPU: the batch is the sharded unit
+    gen = t.Generator(device=g.dev)
+    gen.manual_seed(4 + g.rank)
+    img = t.rand((B, Y, X), device=g.dev, generator=gen)
+    di = g.DA.from_torch(img).desc()
+    wlo, whi = (-3, -3, 0), (3, 3, 0)
+    b = ifb.Pad("replicate").to_abi(3)
+    pair = t.empty((B, Y, X, 2), device=g.dev)
+    dp = g.A.make_array(pair.data_ptr(), g.A.F32, (X, Y, B), (1, 1, 1), g.A.DEVICE)
+    step = lambda: g.lib.mapwindow_extrema(di, dp, None, True, wlo, whi, b, g.sptr)
+    step()
+    t.cuda.synchronize()
+    par = Parity(0.0)
+    for bi in (0, B - 1):
+        for region in ([(0, 128), (0, Y)], [(X - 128, X), (Y - 128, Y)]):
+            cut = [_clip_block(lo, hi, n, 3) for (lo, hi), n in zip(region, (X, Y))]
+            a = np.asfortranarray(julia_view(img[bi][cut[1][0]:cut[1][1], cut[0][0]:cut[0][1]]))
+            mo = ifb.mapwindow(ifb.extrema, a, (7, 7), _library=orc.lib)
+            crop = tuple(slice(lo - b0, hi - b0) for (lo, hi), (b0, b1) in zip(region, cut))
+            got = pair[bi][region[1][0]:region[1][1], region[0][0]:region[0][1]].cpu().numpy()      # (y, x, 2)
+            par.add(got[..., 0].T, mo["min"][crop])
+            par.add(got[..., 1].T, mo["max"][crop])
+    ms, kms, launches = g.time_steps(step, steps, warmup)
+    ms, kms = g.max_over_ranks([ms, kms])
+    npx = B * X * Y
+    ach = npx * 12 / (kms * 1e-3) / 1e9
+    res = {"workload": WORKLOAD["c4"], "scaling": "strong (256 images split over the GPUs, no collective)", "images_per_gpu_per_step": B,
+           "ms": ms, "gpixel_per_s": total * X * Y / (ms * 1e-3) / 1e9,
+           "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "algorithmic_bytes_per_px": 12},
+           "parity": par.result(), "kernel": g.lib.last_path(), "launches_per_step": launches / steps}
+    del pair
+    o = t.empty((B, Y, X), device=g.dev)
+    do = g.DA.from_torch(o).desc()
+    for name, args in (("minimum", (di, do, None)), ("maximum", (di, None, do))):
+        f = lambda a=args: g.lib.mapwindow_extrema(a[0], a[1], a[2], False, wlo, whi, b, g.sptr)
+        m2, k2, _ = g.time_steps(f, steps, warmup)
+        m2, k2 = g.max_over_ranks([m2, k2])
+        res.setdefault("variants", {})[name] = {"ms": m2, "gpixel_per_s": total * X * Y / (m2 * 1e-3) / 1e9,
+                                                "hbm_frac": npx * 8 / (k2 * 1e-3) / 1e9 / hbm, "algorithmic_bytes_per_px": 8}
+    del o
+    EB = min(8, B)
+    n = EB * X * Y
+    hp, hin = g.host_buffer(n * 4, np.float32)
+    op_, _ = g.host_buffer(n * 8, np.float32)
+    hin[:] = np.random.default_rng(14 + g.rank).random(n, dtype=np.float32)
+    hi_ = g.A.make_array(hp.value, g.A.F32, (X, Y, EB), (1, 1, 1), g.A.HOST)
+    ho_ = g.A.make_array(op_.value, g.A.F32, (X, Y, EB), (1, 1, 1), g.A.HOST)
+    ems, _, _ = g.time_steps(lambda: g.lib.mapwindow_extrema(hi_, ho_, None, True, wlo, whi, b, g.sptr), max(3, min(steps, 10)), 2)
+    ems, = g.max_over_ranks([ems])
+    g.host_free(hp)
+    g.host_free(op_)
+    res["e2e"] = {"value": g.world * n / (ems * 1e-3) / 1e9, "unit": "Gpixel/s", "h2d_bytes_per_step": n * 4, "d2h_bytes_per_step": n * 8,
+                  "images_per_gpu_per_step": EB}
+    return res
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# C5: the headline — 3-D gaussian on a 1024^3 volume; N > 1: slab-sharded with halo exchange (strong scaling)
+# ---------------------------------------------------------------------------------------------------------------------
+def run_c5(g, orc, steps, warmup, hbm, mode):
+    t, ifb = g.torch, g.ifb
+    n = 1024
+    kern = ifb.KernelFactors.gaussian((4, 4, 4))
+    taps = [k.data.parent for k in kern]
+    border = ifb.Pad("symmetric")
+    first, cnt = g.sh.slab_bounds(n, g.world, g.rank)
+    gen = t.Generator(device=g.dev)
+    gen.manual_seed(5 + 1000 * g.rank)
+    slab = t.rand((cnt, n, n), device=g.dev, generator=gen)
+    st = g.A.StageList(g.imf.build_stages(kern, 3))
+    b = border.to_abi(3)
+    f = None
+    if g.world == 1:
+        out = t.empty_like(slab)
+        di, do = g.DA.from_torch(slab).desc(), g.DA.from_torch(out).desc()
+        step = lambda: g.lib.imfilter(di, do, st, b, None, g.sptr)
+    else:
+        f = g.sh.ShardedImfilter(slab, kern, border, mode=mode)
+        out = f.out
+        step = lambda: f.run()
+    step()
+    t.cuda.synchronize()
+    path = g.lib.last_path()
+
+    # ---- parity at full size, before timing --------------------------------------------------------------------------
+    tol = 1e-5 * float(np.prod([np.abs(k).sum() for k in taps]))        # max|img| <= 1
+    par = Parity(tol)
+    h = 8
+    lo_planes = hi_planes = None
+    if g.world > 1:                 # the neighbours' raw boundary planes, fetched once for the check (untimed)
+        ex = g.sh.ShardedImfilter(slab, kern, border, mode="sendrecv")
+        ex._exchange()
+        t.cuda.synchronize()
+        lo_planes = ex.recv_lo.clone() if ex.recv_lo is not None else None
+        hi_planes = ex.recv_hi.clone() if ex.recv_hi is not None else None
+        ex.close()
+
+    def check(xr, yr, zr):
+        """output region x in xr, y in yr, LOCAL planes zr of this rank's slab, against the oracle on the block it depends on"""
+        z0, z1 = zr
+        b0 = z0 - h if (z0 - h >= 0 or lo_planes is not None) else 0
+        b1 = z1 + h if (z1 + h <= cnt or hi_planes is not None) else cnt
+        (x0, x1), (y0, y1) = _clip_block(xr[0], xr[1], n, h), _clip_block(yr[0], yr[1], n, h)
+        parts = []
+        if b0 < 0:
+            parts.append(lo_planes[h + b0:, y0:y1, x0:x1])
+        parts.append(slab[max(b0, 0):min(b1, cnt), y0:y1, x0:x1])
+        if b1 > cnt:
+            parts.append(hi_planes[:b1 - cnt, y0:y1, x0:x1])
+        blk = t.cat(parts, 0) if len(parts) > 1 else parts[0]
+        a = np.asfortranarray(julia_view(blk))
+        ref = ifb.imfilter(np.float64, a, kern, border, _library=orc.lib)
+        crop = (slice(xr[0] - x0, xr[1] - x0), slice(yr[0] - y0, yr[1] - y0), slice(z0 - b0, z1 - b0))
+        par.add(gpu_region(out, [xr, yr, (z0, z1)]), ref[crop])
+
+    if g.world == 1:
+        # whole z columns (both global faces, every z-chunk boundary) of: the first tile (marches all planes in one CTA), a tile of
+        # the chunked tail of the schedule on the far x/y corner, and one more chunked tile on the y edge
+        check((0, 32), (0, 64), (0, cnt))
+        check((n - 32, n), (n - 64, n), (0, cnt))
+        check((96, 128), (n - 64, n), (0, cnt))
+        check((480, 560), (470, 570), (cnt // 2 - 8, cnt // 2 + 8))
+    else:
+        # every plane that depends on a neighbour (or on a global face) on both ends of the slab, over two xy regions incl. an
+        # x/y corner; plus an interior block
+        for xr, yr in (((0, 40), (0, 72)), ((n - 72, n), (n - 40, n))):
+            check(xr, yr, (0, 16))
+            check(xr, yr, (cnt - 16, cnt))
+        check((480, 560), (470, 570), (0, 16))
+        check((480, 560), (470, 570), (cnt - 16, cnt))
+        check((480, 560), (470, 570), (cnt // 2 - 8, cnt // 2 + 8))
+    pres = par.result()
+    errs = g.max_over_ranks([pres["max_abs_err"], 0.0 if pres["ok"] else 1.0])
+    pres["max_abs_err"], pres["ok"] = errs[0], errs[1] == 0.0
+    pres["regions"] = ("whole-z columns of a full-march tile, two chunk-scheduled tiles (x/y corner, y edge) and a mid block" if g.world == 1
+                       else "first and last 16 planes of every slab (all seams +-8 planes, both global faces) over an x/y corner, the opposite corner and a mid block; a mid-slab block")
+
+    # ---- device-resident timing ----------------------------------------------------------------------------------------
+    sampler = ClockSampler(g.local)
+    if g.rank == 0:
         sampler.start()
         time.sleep(0.1)
-    for _ in range(args.warmup):
-        step()
-    barrier()
-    assert lib.last_path().endswith("_grad"), lib.last_path()
-    kernel_path = lib.last_path()
     t_load = time.time()
-    while time.time() - t_load < 0.3:       # untimed: keep the GPU under the same load until the sampler has readings
-        for _ in range(10):
+    while time.time() - t_load < 0.4:           # untimed: the sampler needs readings under this load
+        for _ in range(5):
             step()
-        torch.cuda.synchronize()
-    lib.reset_launch_count()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    barrier()
-    t_start = torch.cuda.Event(enable_timing=True)
-    t_end = torch.cuda.Event(enable_timing=True)
-    t_start.record(stream)
-    for a, b in ev:
-        a.record(stream)
-        step()
-        b.record(stream)
-    t_end.record(stream)
-    barrier()
-    launches = lib.launch_count()
-    total_ms = t_start.elapsed_time(t_end)
-    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
-    clocks = sampler.stop() if rank == 0 else None
+        t.cuda.synchronize()
+    ms, kms, launches = g.time_steps(step, steps, warmup)
+    clocks = sampler.stop() if g.rank == 0 else None
+    ms, kms = g.max_over_ranks([ms, kms])
+    launches = int(g.sum_over_ranks([launches])[0])
 
-    # ---- end to end through the C ABI with host buffers ------------------------------------------------
-    nin = E2E_BATCH * H * W
-    hptr = C.c_void_p()
-    lib.check(lib.dll.b2f_host_alloc(C.byref(hptr), nin))
-    hin = np.ctypeslib.as_array(C.cast(hptr, C.POINTER(C.c_uint8)), shape=(nin,))
-    hin[:] = np.random.default_rng(100 + rank).integers(0, 256, size=nin, dtype=np.uint8)
-    houts = []
-    for _ in range(2):
-        p = C.c_void_p()
-        lib.check(lib.dll.b2f_host_alloc(C.byref(p), nin * 8))
-        houts.append(p)
-    h_img = ifb._abi.make_array(hptr.value, ifb._abi.N0F8, (W, H, E2E_BATCH), (1, 1, 1), ifb._abi.HOST)
-    h_out = [ifb._abi.make_array(p.value, ifb._abi.F64, (W, H, E2E_BATCH), (1, 1, 1), ifb._abi.HOST) for p in houts]
+    # ---- end to end: the slab comes from pinned host memory and the result goes back, through the same entry point ---------
+    nvox = cnt * n * n
+    hp, hin = g.host_buffer(nvox * 4, np.float32)
+    op_, hout = g.host_buffer(nvox * 4, np.float32)
+    hin[:] = slab.cpu().numpy().ravel()
+    e2e_steps = 3
+    if g.world == 1:
+        hi_ = g.A.make_array(hp.value, g.A.F32, (n, n, cnt), (1, 1, 1), g.A.HOST)
+        ho_ = g.A.make_array(op_.value, g.A.F32, (n, n, cnt), (1, 1, 1), g.A.HOST)
+        estep = lambda: g.lib.imfilter(hi_, ho_, st, b, None, g.sptr)
+    else:
+        h_in_t = t.from_numpy(hin).view(cnt, n, n)
+        h_out_t = t.from_numpy(hout).view(cnt, n, n)
 
-    def e2e_step():
-        lib.imgradients(h_img, h_out, stages, 3, border, sptr)   # H2D, launch, D2H, sync
+        def estep():                # H2D of the slab, the sharded pass (hand-shake + halos + kernel), D2H of the result
+            slab.copy_(h_in_t, non_blocking=True)
+            f.barrier(full=True)    # the neighbours read this slab: all uploads must be complete before any rank filters
+            f.run()
+            h_out_t.copy_(f.out, non_blocking=True)
+            t.cuda.current_stream().synchronize()
+    ems, _, _ = g.time_steps(estep, e2e_steps, 1)
+    ems, = g.max_over_ranks([ems])
+    e2e_err = float(np.max(np.abs(hout[:n * n * 2] - out[:2].cpu().numpy().ravel())))
+    g.host_free(hp)
+    g.host_free(op_)
+    if f is not None:
+        f.close()
+    total_vox = n ** 3
+    ach = nvox * 8 / (kms * 1e-3) / 1e9
+    return {"workload": WORKLOAD["c5"], "scaling": "strong" if g.world > 1 else "single GPU", "planes_per_gpu": cnt,
+            "halo_transport": mode if g.world > 1 else None,
+            "ms": ms, "launch_ms": kms, "gpixel_per_s": total_vox / (ms * 1e-3) / 1e9,
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "algorithmic_bytes_per_px": 8,
+                         "algorithmic_bytes_per_launch": nvox * 8,
+                         "note": "51 FMA per 8 bytes: the FP32 pipe (>= 1.47 ms per 1024^3 at 1.965 GHz) binds before HBM (1.31 ms)"},
+            "parity": pres, "kernel": path, "launches": launches, "clocks": clocks,
+            "e2e": {"value": total_vox / (ems * 1e-3) / 1e9, "unit": "Gpixel/s", "h2d_bytes_per_step": nvox * 4 * g.world,
+                    "d2h_bytes_per_step": nvox * 4 * g.world, "steps": e2e_steps, "readback_max_abs_diff": e2e_err}}
 
-    e2e_steps = max(3, min(args.steps, 10))
-    for _ in range(2):
-        e2e_step()
-    barrier()
-    e0 = torch.cuda.Event(enable_timing=True)
-    e1 = torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(e2e_steps):
-        e2e_step()
-    e1.record(stream)
-    barrier()
-    e2e_ms = e0.elapsed_time(e1)
-    check = float(np.ctypeslib.as_array(C.cast(houts[0], C.POINTER(C.c_double)), shape=(4,))[1])
 
-    t = torch.tensor([total_ms, e2e_ms, kern_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, e2e_ms, kern_ms = (float(x) for x in t.tolist())
+RUNNERS = {"c1": run_c1, "c2": run_c2, "c3": run_c3, "c4": run_c4}
 
-    if rank == 0:
-        hbm, which = peaks()
-        px_step = BATCH * W * H
-        value = world * px_step * args.steps / (total_ms * 1e-3) / 1e9
-        achieved = px_step * BYTES_PER_PX / (kern_ms * 1e-3) / 1e9
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tp):
-            try:
-                traffic = json.load(open(tp)).get("stream2d_grad_bench_bytes_per_launch")
-            except Exception:
-                traffic = None
-        cpu = None
-        try:
-            gpx, ms, threads = cpu_reference_run(steps=3, warmup=1)
-            cpu = {"value": gpx, "unit": "Gpixel/s", "cores": threads, "kind": "port",
-                   "sample": "3 steps of one 4096x4096 N0f8 image (both Sobel gradients, Float64), "
-                             "CPUThreads(FIRTiled) restatement, %.0f ms/step" % ms}
-        except Exception as e:   # the baseline is a report, never a dependency of the GPU numbers
-            cpu = {"value": None, "unit": "Gpixel/s", "cores": 0, "kind": "port", "sample": "failed: %s" % e}
+
+def ncu_traffic(kernel_key):
+    """DRAM bytes per launch of the headline kernel from the committed ncu capture (profiles/traffic.json), or None when the capture
+    is of another kernel / size.  A live bench run cannot measure DRAM traffic (no profiler inside the timed run)."""
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        d = json.load(open(tp))
+        e = d.get(kernel_key)
+        return (e.get("dram_bytes_per_launch"), e.get("capture")) if e else (None, None)
+    except Exception:
+        return None, None
+
+
+def ours_arm(args):
+    g = G()
+    hbm, which = peaks()
+    orc = Oracle()          # the CPU oracle: parity checker (untimed) and cpu_baseline
+    only = [x for x in args.only.split(",") if x] or ["c5", "c1", "c2", "c3", "c4"]
+    if g.world > 1:         # C1 / C3 are single images (replicas only): the multi-GPU run measures what shards
+        only = [x for x in only if x in ("c5", "c4", "c2")]
+    cfg = {}
+    head = None
+    for name in only:
+        if name == "c5":
+            head = cfg["c5"] = run_c5(g, orc, args.steps, args.warmup, hbm, args.mode)
+        else:
+            cfg[name] = RUNNERS[name](g, orc, args.steps, args.warmup, hbm)
+        g.torch.cuda.empty_cache()
+    if g.rank == 0:
+        for name in cfg:        # CPU baselines after the GPU work, rank 0 at N = 1 only (the other ranks' cores stay free)
+            if g.world == 1:
+                try:
+                    v, cores, what = cpu_sample(name, orc)
+                    cfg[name]["cpu_baseline"] = {"value": v, "unit": "Gpixel/s", "cores": cores, "kind": "port", "sample": what}
+                except Exception as e:      # a report, never a dependency of the GPU numbers
+                    cfg[name]["cpu_baseline"] = {"value": None, "unit": "Gpixel/s", "cores": 0, "kind": "port", "sample": f"failed: {e}"}
+        parity = {k: v["parity"] for k, v in cfg.items()}
+        all_ok = all(p["ok"] for p in parity.values())
+        hd = head or cfg[only[0]]
+        traffic, capture = ncu_traffic("stream3d_c5_1024" if head else "")
+        roof = dict(hd["roofline"])
+        roof.update({"traffic": traffic if g.world == 1 else None, "traffic_capture": capture, "peak_source": "of " + which, "launch_ms": hd.get("launch_ms")})
         line = {
-            "metric": "imfilter_gpixel_per_s", "value": value, "unit": "Gpixel/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "imgradients Sobel 4096x4096 N0f8 Pad(:reflect) -> 2x Float64 (BASELINE configs[1])",
-                       "images_per_gpu_per_step": BATCH, "parallelism": "batch-sharded x%d, no collective" % world,
-                       "l2": "working set per step 2.3 GB per GPU, larger than the 126 MB L2",
-                       "kernel": kernel_path + " (one launch per step)"},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-                         "traffic": traffic, "peak_source": "of " + which,
-                         "algorithmic_bytes_per_launch": px_step * BYTES_PER_PX, "launch_ms": kern_ms},
-            "cpu_baseline": cpu,
-            "e2e": {"value": world * E2E_BATCH * W * H * e2e_steps / (e2e_ms * 1e-3) / 1e9, "unit": "Gpixel/s",
-                    "h2d_bytes_per_step": E2E_BATCH * W * H, "d2h_bytes_per_step": E2E_BATCH * W * H * 16,
-                    "images_per_gpu_per_step": E2E_BATCH, "steps": e2e_steps, "checksum": check},
-            "gpu_launches": launches * world,
-            "clocks": clocks,
+            "metric": METRIC, "value": hd["gpixel_per_s"], "unit": "Gpixel/s", "n_gpus": g.world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": hd["ms"], "higher_is_better": True, "scaling": "strong" if g.world > 1 else "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": bench_config(g.world) if head else {"workload": hd["workload"]},
+            "roofline": roof, "cpu_baseline": hd.get("cpu_baseline"), "e2e": hd["e2e"], "gpu_launches": hd.get("launches"),
+            "clocks": hd.get("clocks"), "parity": parity, "parity_ok": all_ok,
+            "configs": cfg,
         }
         print(json.dumps(line), flush=True)
-    for p in [hptr] + houts:
-        lib.dll.b2f_host_free(p)
-    if world > 1:
-        dist.destroy_process_group()
+        if not all_ok:
+            sys.stderr.write("PARITY FAILURE: " + json.dumps(parity) + "\n")
+    ok = all(v["parity"]["ok"] for v in cfg.values())
+    if g.world > 1:
+        g.dist.barrier()
+        g.dist.destroy_process_group()
+    if not ok:
+        sys.exit(3)
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--only", default="", help="comma-separated subset of c1..c5 (default: all that shard on this many GPUs)")
+    ap.add_argument("--mode", default="auto", choices=["auto", "staged", "p2p", "sendrecv"], help="halo transport of the sharded C5")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         reference_arm(args)
     else:
+        args.warmup = max(args.warmup, 3)
         ours_arm(args)
 
 

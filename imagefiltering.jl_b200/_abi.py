@@ -39,7 +39,7 @@ SYMBOLS = [
     "b2f_memset_async", "b2f_stream_write32", "b2f_stream_wait_geq32",
     "b2f_findlocalextrema", "b2f_scale_into_slice", "b2f_maxabs", "b2f_gather", "b2f_na_prepare", "b2f_divide",
     "b2f_normalize_dims",
-    "b2f_launch_count", "b2f_reset_launch_count", "b2f_last_path",
+    "b2f_bench_fma_peak", "b2f_launch_count", "b2f_reset_launch_count", "b2f_last_path",
 ]
 
 

@@ -281,6 +281,10 @@ int b2f_divide(const b2f_array *out, const b2f_array *den, void *stream);
  * vector of length dims[d] per axis.  Synchronous. */
 int b2f_normalize_dims(const b2f_array *out, const double *const *factors, void *stream);
 
+/* Measured FP32 multiply-add peak of the current GPU in TFMA/s (a pure fma.rn.f32x2 loop, best of 3, CUDA-event timed): the
+ * denominator bench.py reports the dense-kernel path against.  Synchronous.  (The oracle library returns 0.) */
+int b2f_bench_fma_peak(double *tfma_per_s, void *stream);
+
 /* number of CUDA kernels launched by this library on the calling thread since the last reset
  * (the oracle library always reports 0) */
 int64_t b2f_launch_count(void);

@@ -698,6 +698,7 @@ int b2f_is_device_library(void) { return 0; }
 int b2f_set_device(int) { return 0; }
 int b2f_device_count(int *count) { if (count) *count = 0; return 0; }
 int b2f_sm_count(int *count) { if (count) *count = 0; return 0; }
+int b2f_bench_fma_peak(double *tfma_per_s, void *) { if (tfma_per_s) *tfma_per_s = 0.0; return 0; }
 int b2f_malloc(void **, uint64_t) { return fail(B2F_ENOTSUP, "oracle library has no device memory"); }
 int b2f_free(void *) { return fail(B2F_ENOTSUP, "oracle library has no device memory"); }
 int b2f_host_alloc(void **, uint64_t) { return fail(B2F_ENOTSUP, "oracle library has no pinned memory"); }
