@@ -260,7 +260,8 @@ class G:
                 os.sched_setaffinity(0, cores[self.local * per:(self.local + 1) * per])
             except Exception:
                 pass
-            dist.init_process_group("nccl", device_id=self.dev)
+            import datetime
+            dist.init_process_group("nccl", device_id=self.dev, timeout=datetime.timedelta(seconds=180))
         self.stream = torch.cuda.current_stream()
         self.sptr = self.stream.cuda_stream
         self.A = ifb._abi
@@ -690,11 +691,9 @@ def run_c5(g, orc, steps, warmup, hbm, mode):
     if g.rank == 0:
         sampler.start()
         time.sleep(0.1)
-    t_load = time.time()
-    while time.time() - t_load < 0.4:           # untimed: the sampler needs readings under this load
-        for _ in range(5):
-            step()
-        t.cuda.synchronize()
+    for _ in range(120):                        # untimed (~0.4 s): the sampler needs readings under this load.  A FIXED count: every
+        step()                                  # rank must run the same number of sharded steps (neighbour hand-shake per step)
+    t.cuda.synchronize()
     ms, kms, launches = g.time_steps(step, steps, warmup)
     clocks = sampler.stop() if g.rank == 0 else None
     ms, kms = g.max_over_ranks([ms, kms])
