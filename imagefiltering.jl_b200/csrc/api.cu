@@ -254,6 +254,16 @@ int b2f_malloc(void **dptr, uint64_t bytes) { B2F_CUDA(cudaMalloc(dptr, bytes));
 int b2f_free(void *dptr) { B2F_CUDA(cudaFree(dptr)); return 0; }
 int b2f_host_alloc(void **hptr, uint64_t bytes) { B2F_CUDA(cudaHostAlloc(hptr, bytes, cudaHostAllocDefault)); return 0; }
 int b2f_host_free(void *hptr) { B2F_CUDA(cudaFreeHost(hptr)); return 0; }
+int b2f_host_register(void *hptr, uint64_t bytes) {
+    if (!hptr) return fail(B2F_EARG, "NULL argument");
+    B2F_CUDA(cudaHostRegister(hptr, bytes, cudaHostRegisterDefault));
+    return 0;
+}
+int b2f_host_unregister(void *hptr) {
+    if (!hptr) return fail(B2F_EARG, "NULL argument");
+    B2F_CUDA(cudaHostUnregister(hptr));
+    return 0;
+}
 int b2f_memcpy_h2d(void *dptr, const void *hptr, uint64_t bytes) {
     B2F_CUDA(cudaMemcpy(dptr, hptr, bytes, cudaMemcpyHostToDevice));
     return 0;

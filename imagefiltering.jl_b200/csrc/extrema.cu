@@ -7,6 +7,10 @@ namespace b2f {
 int run_extrema_generic(const b2f_array *img, const void *d_img, void *d_min, void *d_max, int interleaved,
                         const Box &out_ax, const int64_t *wlo, const int64_t *whi, int style, double fill,
                         cudaStream_t st);
+// van Herk / Gil-Werman running extrema: any window width, any eltype, any axis (extrema_vh.cu)
+bool extrema_vh_applicable(const b2f_array *img, const int64_t *wlo, const int64_t *whi);
+int run_extrema_vh(const b2f_array *img, const void *d_img, void *d_min, void *d_max, int interleaved, const Box &out_ax,
+                   const int64_t *wlo, const int64_t *whi, int style, double fill, cudaStream_t st);
 
 // Float32 images, window on axes 0/1 only (later axes are a batch), window contains its centre, <= 16 wide.
 static bool extrema2d_applicable(const b2f_array *img, const Box &out_ax, const int64_t *wlo, const int64_t *whi) {
@@ -27,9 +31,15 @@ static bool extrema2d_applicable(const b2f_array *img, const Box &out_ax, const 
 int run_extrema(const b2f_array *img, const void *d_img, void *d_min, void *d_max, int interleaved,
                 const Box &out_ax, const int64_t *wlo, const int64_t *whi, int style, double fill,
                 cudaStream_t st) {
-    const char *force = getenv("B2F_FORCE_PATH");
-    if (force || !extrema2d_applicable(img, out_ax, wlo, whi))
+    const char *force = getenv("B2F_FORCE_PATH");     // debugging knob: "generic" | "vh" bypass the faster kernels
+    const bool force_generic = force && strcmp(force, "vh") != 0;
+    if (force || !extrema2d_applicable(img, out_ax, wlo, whi)) {
+        if (!force_generic && extrema_vh_applicable(img, wlo, whi)) {
+            int rc = run_extrema_vh(img, d_img, d_min, d_max, interleaved, out_ax, wlo, whi, style, fill, st);
+            if (rc != B2F_ENOTSUP) return rc;
+        }
         return run_extrema_generic(img, d_img, d_min, d_max, interleaved, out_ax, wlo, whi, style, fill, st);
+    }
     set_path("extrema2d");
     Box ia = axes_of(img);
     E2Params P;

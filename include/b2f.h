@@ -131,6 +131,11 @@ int b2f_malloc(void **dptr, uint64_t bytes);
 int b2f_free(void *dptr);
 int b2f_host_alloc(void **hptr, uint64_t bytes);   /* pinned */
 int b2f_host_free(void *hptr);
+/* Pin an EXISTING host allocation in place (cudaHostRegister) / undo it: a Julia `Array` registered once is copied at
+ * full PCIe speed by every later call that passes it as a B2F_HOST array (an unregistered, pageable array is copied by
+ * the CUDA runtime through its own bounce buffers: about half the bandwidth, and the copy blocks the calling thread). */
+int b2f_host_register(void *hptr, uint64_t bytes);
+int b2f_host_unregister(void *hptr);
 int b2f_memcpy_h2d(void *dptr, const void *hptr, uint64_t bytes);
 int b2f_memcpy_d2h(void *hptr, const void *dptr, uint64_t bytes);
 int b2f_sync(void);
@@ -148,8 +153,10 @@ int b2f_ipc_close(void *dptr, uint64_t offset);
 /* imfilter!(r, out, img, kernel::ProcessedKernel, border)      replaces src/imfilter.jl:321-341 and
  * everything below it.  `roi_lo/roi_hi` (inclusive index bounds, may be NULL = axes(out)) is the
  * `inds` argument of the NoPad form (src/imfilter.jl:367-395).  `stream` is a cudaStream_t (NULL =
- * default stream).  Host arrays are staged through pinned memory and the call is synchronous;
- * device arrays are used in place and the call is asynchronous on `stream`.
+ * default stream).  Host arrays are copied to stream-ordered device allocations and back (cudaMemcpyAsync straight from /
+ * to the caller's memory: at full PCIe speed when that memory is pinned — b2f_host_alloc or b2f_host_register — and through
+ * the runtime's bounce buffers when it is pageable) and the call is synchronous; device arrays are used in place and the
+ * call is asynchronous on `stream`.
  *
  * Arithmetic follows the reference's typing keyed on eltype(out):
  *   out F64           — double accumulate, separate multiply and add in tap order (bit-exact

@@ -703,6 +703,8 @@ int b2f_malloc(void **, uint64_t) { return fail(B2F_ENOTSUP, "oracle library has
 int b2f_free(void *) { return fail(B2F_ENOTSUP, "oracle library has no device memory"); }
 int b2f_host_alloc(void **, uint64_t) { return fail(B2F_ENOTSUP, "oracle library has no pinned memory"); }
 int b2f_host_free(void *) { return fail(B2F_ENOTSUP, "oracle library has no pinned memory"); }
+int b2f_host_register(void *, uint64_t) { return fail(B2F_ENOTSUP, "oracle library has no pinned memory"); }
+int b2f_host_unregister(void *) { return fail(B2F_ENOTSUP, "oracle library has no pinned memory"); }
 int b2f_memcpy_h2d(void *, const void *, uint64_t) { return fail(B2F_ENOTSUP, "oracle library has no device memory"); }
 int b2f_memcpy_d2h(void *, const void *, uint64_t) { return fail(B2F_ENOTSUP, "oracle library has no device memory"); }
 int b2f_sync(void) { return 0; }

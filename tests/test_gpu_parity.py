@@ -222,6 +222,44 @@ def test_extrema_parity(ifb, oracle, device, dt):
                     assert np.array_equal(px, py), (shape, window, border)
 
 
+@pytest.mark.parametrize("dt", [np.uint8, np.int16, np.int32, np.float32, np.float64])
+@pytest.mark.parametrize("w", [17, 31, 63, 101, 18, 64])
+def test_running_extrema_van_herk(ifb, oracle, device, dt, w):
+    """Windows wider than the register kernel, and every eltype other than Float32, run the van Herk / Gil-Werman kernel
+    (csrc/extrema_vh.cu): O(1) comparisons per element whatever the window.  Bit-exact against the oracle's truncated-window
+    ground truth (src/mapwindow.jl:388-473 semantics), odd and even widths, 1-D / 2-D / 3-D (window on the slowest axis too),
+    Fill and Inner borders, N0f8 images."""
+    rng = np.random.default_rng(seed_of("vh", str(np.dtype(dt)), w))
+
+    def data(shape):
+        if np.dtype(dt).kind == "f":
+            return np.asfortranarray(rng.random(shape).astype(dt))
+        return np.asfortranarray(rng.integers(0, 200, size=shape).astype(dt))
+    cases = [((300,), (w,)), ((257, 130), (w, 1)), ((140, 211), (1, w)), ((150, 120), (w, 5)), ((40, 37, 130), (3, 1, w))]
+    for shape, window in cases:
+        img = data(shape)
+        a = ifb.mapwindow(ifb.extrema, img, window)
+        assert device.last_path() == "extrema_vh", (device.last_path(), shape, window)
+        b = ifb.mapwindow(ifb.extrema, img, window, _library=oracle)
+        assert np.array_equal(a["min"], b["min"]) and np.array_equal(a["max"], b["max"]), (shape, window)
+    if w % 2 == 1:
+        img = data((150, 140))
+        for f in (ifb.minimum, ifb.maximum):
+            for border in ("replicate", ifb.Fill(7), ifb.Inner()):
+                x = ifb.mapwindow(f, img, (w, 9), border=border)
+                assert device.last_path() == "extrema_vh"
+                y = ifb.mapwindow(f, img, (w, 9), border=border, _library=oracle)
+                px = x.parent if isinstance(x, ifb.OffsetArray) else x
+                py = y.parent if isinstance(y, ifb.OffsetArray) else y
+                assert np.array_equal(px, py), (w, border)
+    if dt == np.uint8:                                   # N0f8 images (the reference's default 8-bit eltype)
+        img8 = ifb.n0f8(rng.integers(0, 256, size=(200, 90), dtype=np.uint8))
+        a = ifb.mapwindow(ifb.extrema, img8, (w, 3))
+        b = ifb.mapwindow(ifb.extrema, img8, (w, 3), _library=oracle)
+        assert device.last_path() == "extrema_vh"
+        assert np.array_equal(np.asarray(a["min"]), np.asarray(b["min"])) and np.array_equal(np.asarray(a["max"]), np.asarray(b["max"]))
+
+
 @pytest.mark.parametrize("force", ["fused2d", "generic"])
 def test_slower_paths_stay_bit_exact(ifb, oracle, device, force, monkeypatch):
     """The smem-tiled kernel and the per-stage path are the fallbacks of the streamed kernel: force them."""
