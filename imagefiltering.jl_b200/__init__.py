@@ -17,14 +17,14 @@ from .imfilter import factorkernel, filter_type, imfilter, imfilter_, imgradient
 from .kernel import reflect
 from .localextrema import BlobLoG, blob_LoG, findlocalmaxima, findlocalminima
 from .kernelfactors import ReshapedOneD, kernelfactors
-from .mapwindow import extrema, mapwindow, mapwindow_, maximum, median, median_, minimum
+from .mapwindow import extrema, mapwindow, mapwindow_, maximum, mean, median, median_, minimum, sum_
 from .n0f8 import N0f8Array, n0f8
 from .offsetarrays import OffsetArray, centered
 from .resources import Algorithm, CPU1, CPUThreads, CUDALibs
 
 __all__ = [
     "Kernel", "KernelFactors", "Pad", "Fill", "Inner", "NoPad", "NA", "borderinstance", "imfilter",
-    "imfilter_", "imgradients", "padarray", "mapwindow", "mapwindow_", "extrema", "minimum", "maximum", "median", "median_", "centered",
+    "imfilter_", "imgradients", "padarray", "mapwindow", "mapwindow_", "extrema", "minimum", "maximum", "median", "median_", "mean", "sum_", "centered",
     "OffsetArray", "reflect", "kernelfactors", "ReshapedOneD", "Algorithm", "CUDALibs", "CPU1",
     "CPUThreads", "DeviceArray", "n0f8", "N0f8Array", "filter_type", "factorkernel",
     "ColorArray", "findlocalmaxima", "findlocalminima", "blob_LoG", "BlobLoG", "DimensionMismatch", "ArgumentError", "InexactError", "NotSupportedError", "CudaError",

@@ -20,6 +20,7 @@ HOST, DEVICE = 0, 1
 REPLICATE, CIRCULAR, SYMMETRIC, REFLECT, FILL, INNER, NOPAD = range(7)
 STAGE_1D, STAGE_DENSE = 0, 1
 TAPS_F64, TAPS_F32, TAPS_INT = 0, 1, 2
+WIN_MEDIAN, WIN_MEAN, WIN_SUM, WIN_MIN, WIN_MAX = range(5)
 OK, EDIM, EARG, EINEXACT, ECUDA, ENOTSUP, ENOMEM = 0, -1, -2, -3, -4, -5, -6
 
 DTYPE_SIZE = {U8: 1, N0F8: 1, I16: 2, I32: 4, I64: 8, F32: 4, F64: 8, U16: 2, U32: 4}
@@ -35,7 +36,7 @@ DTYPE_TO_NP[N0F8] = np.dtype(np.uint8)
 SYMBOLS = [
     "b2f_version", "b2f_last_error", "b2f_is_device_library", "b2f_set_device", "b2f_device_count", "b2f_sm_count",
     "b2f_malloc", "b2f_free", "b2f_host_alloc", "b2f_host_free", "b2f_host_register", "b2f_host_unregister", "b2f_memcpy_h2d", "b2f_memcpy_d2h",
-    "b2f_sync", "b2f_ipc_export", "b2f_ipc_open", "b2f_ipc_close", "b2f_imfilter", "b2f_imgradients", "b2f_mapwindow_extrema", "b2f_mapwindow_median", "b2f_imfilter_slab", "b2f_imfilter_slab_staged", "b2f_memcpy_async", "b2f_memcpy2d_async",
+    "b2f_sync", "b2f_ipc_export", "b2f_ipc_open", "b2f_ipc_close", "b2f_imfilter", "b2f_imgradients", "b2f_mapwindow_extrema", "b2f_mapwindow_median", "b2f_mapwindow_reduce", "b2f_imfilter_slab", "b2f_imfilter_slab_staged", "b2f_memcpy_async", "b2f_memcpy2d_async",
     "b2f_memset_async", "b2f_stream_write32", "b2f_stream_wait_geq32",
     "b2f_findlocalextrema", "b2f_scale_into_slice", "b2f_maxabs", "b2f_gather", "b2f_na_prepare", "b2f_divide",
     "b2f_normalize_dims",
@@ -189,6 +190,9 @@ class Library:
             C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(b2f_border), C.c_void_p]
         d.b2f_mapwindow_median.argtypes = [
             C.POINTER(b2f_array), C.POINTER(b2f_array), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(b2f_border), C.c_void_p]
+        d.b2f_mapwindow_reduce.argtypes = [
+            C.POINTER(b2f_array), C.POINTER(b2f_array), C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(b2f_border),
+            C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_void_p]
         d.b2f_imfilter_slab.argtypes = [
             C.POINTER(b2f_array), C.POINTER(b2f_array), C.POINTER(b2f_stage), C.c_int32,
             C.POINTER(b2f_border), C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]
@@ -286,6 +290,16 @@ class Library:
         lo = (C.c_int64 * MAXDIM)(*list(win_lo) + [0] * (MAXDIM - len(win_lo)))
         hi = (C.c_int64 * MAXDIM)(*list(win_hi) + [0] * (MAXDIM - len(win_hi)))
         self.check(self.dll.b2f_mapwindow_median(C.byref(img), C.byref(out), lo, hi, C.byref(border), C.c_void_p(stream)))
+
+    def mapwindow_reduce(self, img: b2f_array, out: b2f_array, op: int, win_lo, win_hi, border: b2f_border, idx_first=None,
+                         idx_step=None, stream: int = 0):
+        lo = (C.c_int64 * MAXDIM)(*list(win_lo) + [0] * (MAXDIM - len(win_lo)))
+        hi = (C.c_int64 * MAXDIM)(*list(win_hi) + [0] * (MAXDIM - len(win_hi)))
+        f = s = None
+        if idx_first is not None:
+            f = (C.c_int64 * MAXDIM)(*list(idx_first) + [0] * (MAXDIM - len(idx_first)))
+            s = (C.c_int64 * MAXDIM)(*list(idx_step) + [1] * (MAXDIM - len(idx_step)))
+        self.check(self.dll.b2f_mapwindow_reduce(C.byref(img), C.byref(out), op, lo, hi, C.byref(border), f, s, C.c_void_p(stream)))
 
     def imfilter_slab(self, img: b2f_array, out: b2f_array, stages: StageList, border: b2f_border,
                       global_last_dim: int, slab_first: int, halo_lo: int, n_halo_lo: int,

@@ -198,6 +198,7 @@ struct PtWin {
     long long dims[B2F_MAXDIM];       // image extent
     long long odims[B2F_MAXDIM];      // output extent
     long long ooff[B2F_MAXDIM];       // image coordinate (0-based) of output element 0
+    long long ostep[B2F_MAXDIM];      // image-coordinate step between output elements (`indices=` stride)
     int wlo[B2F_MAXDIM], wn[B2F_MAXDIM];
     int style;
     double fill;
@@ -221,7 +222,7 @@ __global__ void __launch_bounds__(128) pt_median_kernel(const void *img, int dt,
     if (o >= G.nout) return;
     long long c[B2F_MAXDIM], r = o;
 #pragma unroll
-    for (int d = 0; d < B2F_MAXDIM; ++d) { c[d] = r % G.odims[d] + G.ooff[d]; r /= G.odims[d]; }
+    for (int d = 0; d < B2F_MAXDIM; ++d) { c[d] = (r % G.odims[d]) * G.ostep[d] + G.ooff[d]; r /= G.odims[d]; }
     T buf[PT_MAXWIN];
     bool nan = false;
     int n = 0;
@@ -267,6 +268,48 @@ __global__ void __launch_bounds__(128) pt_median_kernel(const void *img, int dt,
         else res = __dadd_rn(__dmul_rn((double)buf[hiidx - 1], 0.5), __dmul_rn((double)buf[hiidx], 0.5));
         ((double *)out)[o] = res;
     }
+}
+
+// mapwindow(mean | sum | minimum | maximum, ...): the window is reduced on the fly in its memory (column-major) order; ACC is
+// the accumulator the reference's reduction has (Float32 / Float64 / Int)
+template <typename ACC>
+__global__ void __launch_bounds__(128) pt_winreduce_kernel(const void *img, int dt, void *out, int odt, int op, PtWin G) {
+    const long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= G.nout) return;
+    long long c[B2F_MAXDIM], r = o;
+#pragma unroll
+    for (int d = 0; d < B2F_MAXDIM; ++d) { c[d] = (r % G.odims[d]) * G.ostep[d] + G.ooff[d]; r /= G.odims[d]; }
+    long long stride[B2F_MAXDIM];
+    stride[0] = 1;
+#pragma unroll
+    for (int d = 1; d < B2F_MAXDIM; ++d) stride[d] = stride[d - 1] * G.dims[d - 1];
+    ACC acc = ACC(0);
+    bool first = true;
+    for (int j3 = 0; j3 < G.wn[3]; ++j3) {
+        const long long i3 = pt_win_index(G.style, c[3] + G.wlo[3] + j3, c[3] + G.wlo[3], c[3] + G.wlo[3] + G.wn[3] - 1, G.dims[3]);
+        for (int j2 = 0; j2 < G.wn[2]; ++j2) {
+            const long long i2 = pt_win_index(G.style, c[2] + G.wlo[2] + j2, c[2] + G.wlo[2], c[2] + G.wlo[2] + G.wn[2] - 1, G.dims[2]);
+            for (int j1 = 0; j1 < G.wn[1]; ++j1) {
+                const long long i1 = pt_win_index(G.style, c[1] + G.wlo[1] + j1, c[1] + G.wlo[1], c[1] + G.wlo[1] + G.wn[1] - 1, G.dims[1]);
+                for (int j0 = 0; j0 < G.wn[0]; ++j0) {
+                    const long long i0 = pt_win_index(G.style, c[0] + G.wlo[0] + j0, c[0] + G.wlo[0], c[0] + G.wlo[0] + G.wn[0] - 1, G.dims[0]);
+                    ACC v;
+                    if (i0 < 0 || i1 < 0 || i2 < 0 || i3 < 0) v = (ACC)G.fill;
+                    else v = load_elem<ACC>(img, dt, i0 + i1 * stride[1] + i2 * stride[2] + i3 * stride[3]);
+                    if (op == B2F_WIN_MIN) acc = first ? v : (v < acc ? v : acc);
+                    else if (op == B2F_WIN_MAX) acc = first ? v : (v > acc ? v : acc);
+                    else acc = first ? v : add_rn<ACC>(acc, v);
+                    first = false;
+                }
+            }
+        }
+    }
+    if (op == B2F_WIN_MEAN) {
+        if (odt == B2F_F32) ((float *)out)[o] = __fdiv_rn((float)acc, (float)G.wtotal);
+        else ((double *)out)[o] = __ddiv_rn((double)acc, (double)G.wtotal);
+        return;
+    }
+    store_elem<ACC>(out, odt, o, acc);
 }
 
 static long long numel(const b2f_array *a) {
@@ -546,15 +589,24 @@ int b2f_normalize_dims(const b2f_array *out, const double *const *factors, void 
     return 0;
 }
 
-int b2f_mapwindow_median(const b2f_array *img, const b2f_array *out, const int64_t *win_lo, const int64_t *win_hi,
-                         const b2f_border *border, void *stream) {
+// shared by b2f_mapwindow_median and b2f_mapwindow_reduce
+static int mapwindow_reduce_impl(const b2f_array *img, const b2f_array *out, int op, const int64_t *win_lo, const int64_t *win_hi,
+                                 const b2f_border *border, const int64_t *idx_first, const int64_t *idx_step, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (!img || !out || !win_lo || !win_hi || !border) return fail(B2F_EARG, "NULL argument");
+    if ((idx_first == nullptr) != (idx_step == nullptr)) return fail(B2F_EARG, "idx_first and idx_step go together");
+    if (op < B2F_WIN_MEDIAN || op > B2F_WIN_MAX) return fail(B2F_EARG, "unknown window reduction %d", op);
     const int N = img->ndim;
     if (N < 1 || N > B2F_MAXDIM || out->ndim != N) return fail(B2F_EDIM, "mapwindow needs 1..%d dims and equal rank", B2F_MAXDIM);
-    if (img->dtype == B2F_N0F8) return fail(B2F_ENOTSUP, "median of N0f8 images is not available");
-    const int want = img->dtype == B2F_F32 ? B2F_F32 : B2F_F64;       // median: Float32 stays, everything else -> Float64
-    if (out->dtype != want) return fail(B2F_EARG, "median output eltype must be %s", want == B2F_F32 ? "Float32" : "Float64");
+    if (img->dtype == B2F_N0F8) return fail(B2F_ENOTSUP, "window reductions of N0f8 images are not available");
+    const bool isf = img->dtype == B2F_F32 || img->dtype == B2F_F64;
+    int want;
+    switch (op) {
+        case B2F_WIN_MEDIAN: case B2F_WIN_MEAN: want = img->dtype == B2F_F32 ? B2F_F32 : B2F_F64; break;
+        case B2F_WIN_SUM: want = isf ? img->dtype : B2F_I64; break;
+        default: want = img->dtype; break;
+    }
+    if (out->dtype != want) return fail(B2F_EARG, "output eltype %d does not match the reduction's result type %d", out->dtype, want);
     if (border->style > B2F_INNER) return fail(B2F_ENOTSUP, "border style %d is not supported by mapwindow", border->style);
     PtWin G;
     memset(&G, 0, sizeof G);
@@ -567,22 +619,25 @@ int b2f_mapwindow_median(const b2f_array *img, const b2f_array *out, const int64
     for (int d = 0; d < B2F_MAXDIM; ++d) {
         G.dims[d] = d < N ? img->dims[d] : 1;
         G.odims[d] = d < N ? out->dims[d] : 1;
-        G.ooff[d] = d < N ? oa.lo[d] - ia.lo[d] : 0;
+        G.ostep[d] = (d < N && idx_step) ? idx_step[d] : 1;
+        G.ooff[d] = d < N ? ((idx_first ? idx_first[d] : oa.lo[d]) - ia.lo[d]) : 0;
         G.wlo[d] = d < N ? (int)win_lo[d] : 0;
         G.wn[d] = d < N ? (int)(win_hi[d] - win_lo[d] + 1) : 1;
         if (G.wn[d] < 1) return fail(B2F_EARG, "empty window");
+        if (G.ostep[d] < 1) return fail(B2F_EARG, "indices must be increasing ranges");
         G.wtotal *= G.wn[d];
         G.nout *= G.odims[d] < 0 ? 0 : G.odims[d];
-        if (d < N) {
-            if (oa.lo[d] < ia.lo[d] || oa.hi[d] > ia.hi[d]) return fail(B2F_EDIM, "output axes exceed image axes");
-            if (border->style == B2F_INNER && (oa.lo[d] + win_lo[d] < ia.lo[d] || oa.hi[d] + win_hi[d] > ia.hi[d]))
-                return fail(B2F_EDIM, "output axes are not in the interior for Inner()");
+        if (d < N && G.odims[d] > 0) {
+            const long long first = G.ooff[d], last = G.ooff[d] + (G.odims[d] - 1) * G.ostep[d];
+            if (first < 0 || last > G.dims[d] - 1) return fail(B2F_EDIM, "requested indices exceed the image axes");
+            if (border->style == B2F_INNER && (first + win_lo[d] < 0 || last + win_hi[d] > G.dims[d] - 1))
+                return fail(B2F_EDIM, "requested indices are not in the interior for Inner()");
             if (border->style != B2F_FILL && (win_lo[d] > 0 || win_hi[d] < 0) && border->style != B2F_INNER)
                 return fail(B2F_ENOTSUP, "windows that do not contain their centre need Fill or Inner borders here");
         }
     }
-    if (G.wtotal > PT_MAXWIN) return fail(B2F_ENOTSUP, "median windows hold at most %d elements", PT_MAXWIN);
-    set_path("median");
+    if (op == B2F_WIN_MEDIAN && G.wtotal > PT_MAXWIN) return fail(B2F_ENOTSUP, "median windows hold at most %d elements", PT_MAXWIN);
+    set_path(op == B2F_WIN_MEDIAN ? "median" : "winreduce");
     if (G.nout == 0 || numel(img) == 0) return 0;
     int rc = ensure_ctx();
     if (rc) return rc;
@@ -592,8 +647,16 @@ int b2f_mapwindow_median(const b2f_array *img, const b2f_array *out, const int64
     cudaError_t e = cudaSuccess;
     if (!rc) {
         const long long blocks = (G.nout + 127) / 128;
-        if (img->dtype == B2F_I64) pt_median_kernel<long long><<<(unsigned)blocks, 128, 0, st>>>(sin.dptr, img->dtype, so.dptr, out->dtype, G);
-        else pt_median_kernel<double><<<(unsigned)blocks, 128, 0, st>>>(sin.dptr, img->dtype, so.dptr, out->dtype, G);
+        if (op == B2F_WIN_MEDIAN) {
+            if (img->dtype == B2F_I64) pt_median_kernel<long long><<<(unsigned)blocks, 128, 0, st>>>(sin.dptr, img->dtype, so.dptr, out->dtype, G);
+            else pt_median_kernel<double><<<(unsigned)blocks, 128, 0, st>>>(sin.dptr, img->dtype, so.dptr, out->dtype, G);
+        } else if (img->dtype == B2F_F32) {
+            pt_winreduce_kernel<float><<<(unsigned)blocks, 128, 0, st>>>(sin.dptr, img->dtype, so.dptr, out->dtype, op, G);
+        } else if (img->dtype == B2F_F64) {
+            pt_winreduce_kernel<double><<<(unsigned)blocks, 128, 0, st>>>(sin.dptr, img->dtype, so.dptr, out->dtype, op, G);
+        } else {
+            pt_winreduce_kernel<long long><<<(unsigned)blocks, 128, 0, st>>>(sin.dptr, img->dtype, so.dptr, out->dtype, op, G);
+        }
         count_launch();
         e = cudaGetLastError();
         if (e == cudaSuccess && out->mem == B2F_HOST) {
@@ -605,8 +668,18 @@ int b2f_mapwindow_median(const b2f_array *img, const b2f_array *out, const int64
     }
     release(sin, st); release(so, st);
     if (rc) return rc;
-    if (e != cudaSuccess) return fail(B2F_ECUDA, "mapwindow median failed: %s", cudaGetErrorString(e));
+    if (e != cudaSuccess) return fail(B2F_ECUDA, "mapwindow reduction failed: %s", cudaGetErrorString(e));
     return 0;
+}
+
+int b2f_mapwindow_median(const b2f_array *img, const b2f_array *out, const int64_t *win_lo, const int64_t *win_hi,
+                         const b2f_border *border, void *stream) {
+    return mapwindow_reduce_impl(img, out, B2F_WIN_MEDIAN, win_lo, win_hi, border, nullptr, nullptr, stream);
+}
+
+int b2f_mapwindow_reduce(const b2f_array *img, const b2f_array *out, int32_t op, const int64_t *win_lo, const int64_t *win_hi,
+                         const b2f_border *border, const int64_t *idx_first, const int64_t *idx_step, void *stream) {
+    return mapwindow_reduce_impl(img, out, op, win_lo, win_hi, border, idx_first, idx_step, stream);
 }
 
 }  // extern "C"

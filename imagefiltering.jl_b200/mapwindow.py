@@ -36,10 +36,24 @@ def median(a):
 
 median_ = median        # `median!`
 
+
+def mean(a):
+    """Marker mirroring Statistics.mean."""
+    return float(np.mean(np.asarray(a)))
+
+
+def sum_(a):
+    """Marker mirroring Base.sum (`sum` is a Python builtin, which is accepted as well)."""
+    return np.asarray(a).sum()
+
+
 _MED = {median, np.median, "median", "median!"}
 _MIN = {minimum, builtins.min, np.min, np.amin, np.minimum.reduce, "minimum", "min"}
 _MAX = {maximum, builtins.max, np.max, np.amax, np.maximum.reduce, "maximum", "max"}
 _EXT = {extrema, "extrema"}
+_MEAN = {mean, np.mean, "mean"}
+_SUM = {sum_, builtins.sum, np.sum, "sum"}
+_REDUCE_OP = {"median": _abi.WIN_MEDIAN, "mean": _abi.WIN_MEAN, "sum": _abi.WIN_SUM, "min": _abi.WIN_MIN, "max": _abi.WIN_MAX}
 
 
 def _kind(f):
@@ -52,10 +66,14 @@ def _kind(f):
             return "max"
         if f in _MED:
             return "median"
+        if f in _MEAN:
+            return "mean"
+        if f in _SUM:
+            return "sum"
     except TypeError:
         pass
     raise NotSupportedError(
-        "mapwindow on the device supports f in {extrema, minimum, maximum, median}; arbitrary window functions "
+        "mapwindow on the device supports f in {extrema, minimum, maximum, median, mean, sum}; arbitrary window functions "
         "cannot cross the C ABI and there is no CPU fallback")
 
 
@@ -98,6 +116,48 @@ def _default_indices_ok(indices, first, shape):
     return tuple(indices) == want
 
 
+def _reduce_out_dtype(kind, dt):
+    """Result eltype of the window reduction (compute_output_eltype, src/mapwindow.jl:253-257, for the supported f)."""
+    isf = dt in (_abi.F32, _abi.F64)
+    if kind in ("median", "mean"):
+        return _abi.F32 if dt == _abi.F32 else _abi.F64
+    if kind == "sum":
+        return dt if isf else _abi.I64       # Julia widens small integers to Int / UInt
+    return dt
+
+
+def _mapwindow_indices(L, kind, out_spec, desc, ndim, first, shape, wlo, whi, b, indices):
+    """mapwindow(f, img, window; indices=ranges): the window function is evaluated at the listed image indices only
+    (src/mapwindow.jl:123-131,156-183,270-306).  The result has plain 1-based axes of the ranges' lengths (`axes(r, 1)` of an
+    ordinary range is OneTo(length(r)), test/mapwindow.jl:146-151)."""
+    if isinstance(indices, range):
+        indices = (indices,)
+    indices = tuple(indices)
+    if len(indices) != ndim or not all(isinstance(r, range) for r in indices):
+        raise ArgumentError("indices= takes one range per image dimension")
+    if any(r.step < 1 for r in indices):
+        raise NotSupportedError("indices= with decreasing ranges is outside the accelerated path")
+    if kind == "extrema":
+        raise NotSupportedError("mapwindow(extrema, ...; indices=...) is outside the accelerated path: take minimum and maximum separately")
+    counts = tuple(len(r) for r in indices)
+    for r, f0, n in zip(indices, first, shape):
+        if len(r) and (r[0] < f0 or r[-1] > f0 + n - 1):
+            raise DimensionMismatch("indices= must lie inside the image axes")
+    odt = _reduce_out_dtype(kind, desc.dtype)
+    idx_first, idx_step = [r.start for r in indices], [r.step for r in indices]
+    if out_spec is not None:
+        odesc, okeep = _as_output(out_spec)
+        if tuple(odesc.dims[d] for d in range(ndim)) != counts:
+            raise DimensionMismatch("out must have one element per requested index")
+        od = _abi.make_array(odesc.ptr, odesc.dtype, counts, (1,) * ndim, odesc.mem)
+        L.mapwindow_reduce(desc, od, _REDUCE_OP[kind], wlo, whi, b.to_abi(ndim), idx_first, idx_step)
+        return out_spec
+    res = np.empty(counts, dtype=_abi.DTYPE_TO_NP[odt], order="F")
+    L.mapwindow_reduce(desc, _abi.make_array(res.ctypes.data, odt, counts, (1,) * ndim, _abi.HOST), _REDUCE_OP[kind], wlo, whi,
+                       b.to_abi(ndim), idx_first, idx_step)
+    return res
+
+
 def _mapwindow(f, out_spec, img, window, border, indices, library):
     from ._lib import lib
     L = library if library is not None else lib()
@@ -111,23 +171,23 @@ def _mapwindow(f, out_spec, img, window, border, indices, library):
     if isinstance(b, Inner):
         lo = [f0 - l for f0, l in zip(first, wlo)]
         hi = [f0 + n - 1 - h for f0, n, h in zip(first, shape, whi)]
-        if indices is not None and tuple(indices) != tuple(range(l, h + 1) for l, h in zip(lo, hi)):
-            raise NotSupportedError("indices= (strided / partial evaluation) is outside the accelerated path")
+        if indices is not None and tuple(indices if not isinstance(indices, range) else (indices,)) != tuple(range(l, h + 1) for l, h in zip(lo, hi)):
+            return _mapwindow_indices(L, kind, out_spec, desc, ndim, first, shape, wlo, whi, b, indices)
     else:
-        if not _default_indices_ok(indices, first, shape):
-            raise NotSupportedError("indices= (strided / partial evaluation) is outside the accelerated path")
+        if not _default_indices_ok(indices if not isinstance(indices, range) else (indices,), first, shape):
+            return _mapwindow_indices(L, kind, out_spec, desc, ndim, first, shape, wlo, whi, b, indices)
         lo, hi = list(first), [f0 + n - 1 for f0, n in zip(first, shape)]
     oshape = tuple(max(0, h - l + 1) for l, h in zip(lo, hi))
     base = _abi.DTYPE_TO_NP[desc.dtype]
-    if kind == "median":        # generic window path, src/mapwindow.jl:270-333 with f = median!
-        odt = _abi.F32 if desc.dtype == _abi.F32 else _abi.F64
+    if kind in ("median", "mean", "sum"):        # generic window path, src/mapwindow.jl:270-333 with f = median! / mean / sum
+        odt = _reduce_out_dtype(kind, desc.dtype)
         if out_spec is not None:
             odesc, okeep = _as_output(out_spec)
             od = _abi.make_array(odesc.ptr, odesc.dtype, oshape, lo, odesc.mem)
-            L.mapwindow_median(desc, od, wlo, whi, b.to_abi(ndim))
+            L.mapwindow_reduce(desc, od, _REDUCE_OP[kind], wlo, whi, b.to_abi(ndim))
             return out_spec
         res = np.empty(oshape, dtype=_abi.DTYPE_TO_NP[odt], order="F")
-        L.mapwindow_median(desc, _abi.make_array(res.ctypes.data, odt, oshape, lo, _abi.HOST), wlo, whi, b.to_abi(ndim))
+        L.mapwindow_reduce(desc, _abi.make_array(res.ctypes.data, odt, oshape, lo, _abi.HOST), _REDUCE_OP[kind], wlo, whi, b.to_abi(ndim))
         return OffsetArray.with_first(res, lo) if any(l != 1 for l in lo) else res
 
     if out_spec is not None:  # mapwindow!

@@ -199,6 +199,22 @@ int b2f_mapwindow_extrema(const b2f_array *img, const b2f_array *out_min, const 
 int b2f_mapwindow_median(const b2f_array *img, const b2f_array *out, const int64_t *win_lo, const int64_t *win_hi,
                          const b2f_border *border, void *stream);
 
+/* mapwindow(f, img, window; border, indices) for the window reductions the reference's tests and benchmarks use
+ * (generic window loop src/mapwindow.jl:270-306; goldens test/mapwindow.jl:105-152; workloads benchmark/benchmarks.jl:21-35):
+ *   B2F_WIN_MEDIAN  as b2f_mapwindow_median;
+ *   B2F_WIN_MEAN    sum of the window in column-major order / length: Float32 for Float32 images, Float64 otherwise;
+ *   B2F_WIN_SUM     the same sum: eltype(img) for Float32 / Float64, Int64 for integer images (Julia widens small
+ *                   integers to Int / UInt);
+ *   B2F_WIN_MIN / B2F_WIN_MAX   eltype(img) (the O(prod(w)) loop; b2f_mapwindow_extrema is the fast path).
+ * `idx_first[d]` / `idx_step[d]` are the `indices=` ranges (src/mapwindow.jl:123-131,156-183): output element j along axis
+ * d is the window at image index idx_first[d] + j * idx_step[d] (image-axis coordinates, i.e. counted like origin[d]);
+ * out->dims[d] positions are evaluated.  NULL: the positions are out's own axes (step 1).  Windows are gathered with
+ * copy_win!'s border semantics (:310-333).  Float sums follow the window's memory order; Julia's `sum` may reassociate
+ * (SIMD), so bit-level agreement with Julia is unpinned for Float windows — exact for integers. */
+enum { B2F_WIN_MEDIAN = 0, B2F_WIN_MEAN = 1, B2F_WIN_SUM = 2, B2F_WIN_MIN = 3, B2F_WIN_MAX = 4 };
+int b2f_mapwindow_reduce(const b2f_array *img, const b2f_array *out, int32_t op, const int64_t *win_lo, const int64_t *win_hi,
+                         const b2f_border *border, const int64_t *idx_first, const int64_t *idx_step, void *stream);
+
 /* Slab form of a separable cascade, used by the sharded N-d path: the array's LAST axis is
  * partitioned across GPUs.  `img` and `out` hold this rank's owned planes [slab_first, slab_first + dims[ndim-1])
  * of an array whose last axis has `global_last_dim` planes.  `halo_lo` / `halo_hi` point to `n_halo_lo` /

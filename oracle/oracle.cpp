@@ -1260,43 +1260,66 @@ int64_t o_win_index(int style, int64_t k, int64_t a, int64_t b, int64_t n) {   /
 }
 }  // namespace
 
-extern "C" int b2f_mapwindow_median(const b2f_array *img, const b2f_array *out, const int64_t *win_lo, const int64_t *win_hi,
-                                    const b2f_border *border, void *) {
+static void o_store_int(const b2f_array *a, int64_t i, int64_t v) {
+    switch (a->dtype) {
+        case B2F_U8: ((uint8_t *)a->ptr)[i] = (uint8_t)v; break;
+        case B2F_I16: ((int16_t *)a->ptr)[i] = (int16_t)v; break;
+        case B2F_U16: ((uint16_t *)a->ptr)[i] = (uint16_t)v; break;
+        case B2F_I32: ((int32_t *)a->ptr)[i] = (int32_t)v; break;
+        case B2F_U32: ((uint32_t *)a->ptr)[i] = (uint32_t)v; break;
+        default: ((int64_t *)a->ptr)[i] = v; break;
+    }
+}
+
+// The generic window loop of the reference (src/mapwindow.jl:270-306) for f in {median!, mean, sum, minimum, maximum} with
+// `indices=` ranges (:123-131,156-183): output element j along axis d is the window at image index idx_first[d] + j*idx_step[d].
+// mean / sum reduce the window in its memory order with the reference's accumulator (Float32 windows in Float32, integers in Int).
+static int o_mapwindow_reduce(const b2f_array *img, const b2f_array *out, int op, const int64_t *win_lo, const int64_t *win_hi,
+                              const b2f_border *border, const int64_t *idx_first, const int64_t *idx_step) {
     if (!img || !out || !win_lo || !win_hi || !border) return fail(B2F_EARG, "NULL argument");
+    if ((idx_first == nullptr) != (idx_step == nullptr)) return fail(B2F_EARG, "idx_first and idx_step go together");
+    if (op < 0 || op > 4) return fail(B2F_EARG, "unknown window reduction %d", op);
     const int N = img->ndim;
     if (N < 1 || N > B2F_MAXDIM || out->ndim != N) return fail(B2F_EDIM, "mapwindow needs 1..4 dims and equal rank");
-    if (img->dtype == B2F_N0F8) return fail(B2F_ENOTSUP, "median of N0f8 images is not available");
-    const int want = img->dtype == B2F_F32 ? B2F_F32 : B2F_F64;
-    if (out->dtype != want) return fail(B2F_EARG, "median output eltype must be %s", want == B2F_F32 ? "Float32" : "Float64");
+    if (img->dtype == B2F_N0F8) return fail(B2F_ENOTSUP, "window reductions of N0f8 images are not available");
+    const bool isf = img->dtype == B2F_F32 || img->dtype == B2F_F64;
+    int want;
+    if (op == 0 || op == 1) want = img->dtype == B2F_F32 ? B2F_F32 : B2F_F64;
+    else if (op == 2) want = isf ? img->dtype : B2F_I64;
+    else want = img->dtype;
+    if (out->dtype != want) return fail(B2F_EARG, "output eltype %d does not match the reduction's result type %d", out->dtype, want);
     if (border->style > B2F_INNER) return fail(B2F_ENOTSUP, "border style %d is not supported by mapwindow", border->style);
     const int style = border->style == B2F_INNER ? B2F_REPLICATE : border->style;
-    int64_t dims[4], odims[4], ooff[4], wlo[4], wn[4], stride[4], nout = 1, wtotal = 1;
+    int64_t dims[4], odims[4], ooff[4], ostep[4], wlo[4], wn[4], stride[4], nout = 1, wtotal = 1;
     for (int d = 0; d < 4; ++d) {
         dims[d] = d < N ? img->dims[d] : 1;
         odims[d] = d < N ? out->dims[d] : 1;
-        ooff[d] = d < N ? out->origin[d] - img->origin[d] : 0;
+        ostep[d] = (d < N && idx_step) ? idx_step[d] : 1;
+        ooff[d] = d < N ? ((idx_first ? idx_first[d] : out->origin[d]) - img->origin[d]) : 0;
         wlo[d] = d < N ? win_lo[d] : 0;
         wn[d] = d < N ? win_hi[d] - win_lo[d] + 1 : 1;
         if (wn[d] < 1) return fail(B2F_EARG, "empty window");
+        if (ostep[d] < 1) return fail(B2F_EARG, "indices must be increasing ranges");
         wtotal *= wn[d];
         nout *= odims[d] < 0 ? 0 : odims[d];
         stride[d] = d == 0 ? 1 : stride[d - 1] * dims[d - 1];
-        if (d < N) {
-            if (ooff[d] < 0 || ooff[d] + odims[d] > dims[d]) return fail(B2F_EDIM, "output axes exceed image axes");
-            if (border->style == B2F_INNER && (ooff[d] + win_lo[d] < 0 || ooff[d] + odims[d] - 1 + win_hi[d] > dims[d] - 1))
-                return fail(B2F_EDIM, "output axes are not in the interior for Inner()");
+        if (d < N && odims[d] > 0) {
+            const int64_t first = ooff[d], last = ooff[d] + (odims[d] - 1) * ostep[d];
+            if (first < 0 || last > dims[d] - 1) return fail(B2F_EDIM, "requested indices exceed the image axes");
+            if (border->style == B2F_INNER && (first + win_lo[d] < 0 || last + win_hi[d] > dims[d] - 1))
+                return fail(B2F_EDIM, "requested indices are not in the interior for Inner()");
             if (border->style != B2F_FILL && (win_lo[d] > 0 || win_hi[d] < 0) && border->style != B2F_INNER)
                 return fail(B2F_ENOTSUP, "windows that do not contain their centre need Fill or Inner borders here");
         }
     }
-    if (wtotal > 128) return fail(B2F_ENOTSUP, "median windows hold at most 128 elements");
+    if (op == 0 && wtotal > 128) return fail(B2F_ENOTSUP, "median windows hold at most 128 elements");
     if (o_numel(img) == 0) return 0;
     const bool is_i64 = img->dtype == B2F_I64;
     std::vector<double> buf(wtotal);
     std::vector<int64_t> ibuf(wtotal);
     for (int64_t o = 0; o < nout; ++o) {
         int64_t c[4], r = o;
-        for (int d = 0; d < 4; ++d) { c[d] = r % odims[d] + ooff[d]; r /= odims[d]; }
+        for (int d = 0; d < 4; ++d) { c[d] = (r % odims[d]) * ostep[d] + ooff[d]; r /= odims[d]; }
         int n = 0;
         bool nan = false;
         for (int64_t j3 = 0; j3 < wn[3]; ++j3)
@@ -1310,11 +1333,39 @@ extern "C" int b2f_mapwindow_median(const b2f_array *img, const b2f_array *out, 
                             const int64_t a = c[d] + wlo[d], i = o_win_index(style, a + j[d], a, a + wn[d] - 1, dims[d]);
                             if (i < 0) fillv = true; else lin += i * stride[d];
                         }
-                        if (is_i64) ibuf[n] = fillv ? (int64_t)border->fill : ((const int64_t *)img->ptr)[lin];
+                        if (!isf) ibuf[n] = fillv ? (int64_t)border->fill : (is_i64 ? ((const int64_t *)img->ptr)[lin] : (int64_t)o_elem(img, lin));
                         const double v = fillv ? (img->dtype == B2F_F32 ? (double)(float)border->fill : border->fill) : o_elem(img, lin);
                         nan = nan || (v != v);
                         buf[n++] = v;
                     }
+        if (op != 0) {          // mean / sum / minimum / maximum in window (memory) order
+            if (!isf) {
+                int64_t acc = ibuf[0];
+                for (int k = 1; k < n; ++k) acc = op == 3 ? std::min(acc, ibuf[k]) : op == 4 ? std::max(acc, ibuf[k]) : acc + ibuf[k];
+                if (op == 1) ((double *)out->ptr)[o] = (double)acc / (double)n;
+                else if (op == 2) ((int64_t *)out->ptr)[o] = acc;
+                else o_store_int(out, o, acc);
+            } else if (img->dtype == B2F_F32) {
+                float acc = (float)buf[0];
+                for (int k = 1; k < n; ++k) {
+                    const float v = (float)buf[k];
+                    if (op == 3) acc = v < acc ? v : acc;
+                    else if (op == 4) acc = v > acc ? v : acc;
+                    else { volatile float t = acc + v; acc = t; }
+                }
+                ((float *)out->ptr)[o] = op == 1 ? acc / (float)n : acc;
+            } else {
+                double acc = buf[0];
+                for (int k = 1; k < n; ++k) {
+                    const double v = buf[k];
+                    if (op == 3) acc = v < acc ? v : acc;
+                    else if (op == 4) acc = v > acc ? v : acc;
+                    else { volatile double t = acc + v; acc = t; }
+                }
+                ((double *)out->ptr)[o] = op == 1 ? acc / (double)n : acc;
+            }
+            continue;
+        }
         double lo_v, hi_v;
         const int mid = n / 2;
         if (is_i64) {
@@ -1339,4 +1390,13 @@ extern "C" int b2f_mapwindow_median(const b2f_array *img, const b2f_array *out, 
         }
     }
     return 0;
+}
+
+extern "C" int b2f_mapwindow_median(const b2f_array *img, const b2f_array *out, const int64_t *win_lo, const int64_t *win_hi,
+                                    const b2f_border *border, void *) {
+    return o_mapwindow_reduce(img, out, 0, win_lo, win_hi, border, nullptr, nullptr);
+}
+extern "C" int b2f_mapwindow_reduce(const b2f_array *img, const b2f_array *out, int32_t op, const int64_t *win_lo, const int64_t *win_hi,
+                                    const b2f_border *border, const int64_t *idx_first, const int64_t *idx_step, void *) {
+    return o_mapwindow_reduce(img, out, op, win_lo, win_hi, border, idx_first, idx_step);
 }

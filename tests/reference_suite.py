@@ -660,6 +660,53 @@ def check_golden_fixtures_f(ifb, lib):
     assert np.array_equal(ifb.mapwindow(ifb.median, np.array(m["A"]), (3, 3), _library=lib), m["A_3x3"])
 
 
-ALL_CHECKS = [check_golden_fixtures_f, check_median_window, check_local_extrema, check_blob_log, check_na_border, check_color_images, check_padarray, check_1d, check_widening, check_prewitt_tiling, check_impulse_interior,
+# ---- test/mapwindow.jl:127-152, 179-186: mean / sum windows and `indices=` ----------------------------------------------
+def check_mapwindow_reductions(ifb, lib):
+    rng = np.random.default_rng(1234)
+    cases = [
+        (ifb.mean, rng.standard_normal(10), (1,), (range(1, 11, 2),)),
+        (ifb.median, rng.standard_normal(10), (range(-1, 2),), (range(1, 9, 2),)),
+        (ifb.mean, rng.standard_normal(10), (range(-1, 2),), (range(1, 9, 2),)),
+        (ifb.mean, np.asfortranarray(rng.standard_normal((10, 5))), (range(-1, 2), range(0, 1)), (range(1, 9, 2), range(1, 4))),
+        (ifb.mean, np.asfortranarray(rng.standard_normal((10, 5))), (range(-1, 2), range(0, 1)), (range(1, 3), range(1, 4))),
+    ]
+    for f, img, window, inds in cases:      # groundtruth2: mapwindow(f, A, window)[indices...]
+        full = ifb.mapwindow(f, img, window, _library=lib)
+        expected = full[tuple(slice(r.start - 1, r.stop - 1, r.step) for r in inds)]
+        got = ifb.mapwindow(f, img, window, indices=inds, _library=lib)
+        assert got.shape == expected.shape and np.array_equal(got, expected), (f, window, inds)
+        out = np.empty(expected.shape, dtype=expected.dtype, order="F")
+        assert np.array_equal(ifb.mapwindow_(f, out, img, window, indices=inds, _library=lib), expected)
+    v = rng.standard_normal(10)
+    assert ifb.mapwindow(ifb.mean, v, (3,), border="replicate", indices=range(2, 8, 2), _library=lib).shape == (3,)
+    r = ifb.mapwindow(ifb.mean, v, (3,), indices=range(2, 8), _library=lib)
+    assert not isinstance(r, ifb.OffsetArray) and r.shape == (6,)          # axes(2:7) == (OneTo(6),)
+    assert ifb.mapwindow(ifb.mean, v, (3,), _library=lib).shape == (10,)
+    # mean is the window sum over its length; replicate border at the ends
+    vp = np.concatenate([v[:1], v, v[-1:]])
+    ref = np.array([(vp[i] + vp[i + 1] + vp[i + 2]) / 3 for i in range(10)])
+    assert approx(ifb.mapwindow(ifb.mean, v, (3,), _library=lib), ref)
+    # issue 48 (test/mapwindow.jl:153-166): Inner() with indices and a one-sided window
+    img48 = 10 * np.arange(1, 11)
+    assert np.array_equal(ifb.mapwindow(ifb.minimum, img48, (range(0, 3),), border=ifb.Inner(), indices=range(2, 9, 2), _library=lib),
+                          img48[1:8:2])
+    res = ifb.mapwindow(ifb.minimum, img48, range(-2, 1), border=ifb.Inner(), _library=lib)
+    assert isinstance(res, ifb.OffsetArray) and res.first == (3,) and np.array_equal(res.parent, img48[:8])
+    # >3-D mapwindow (issue 105, test/mapwindow.jl:179-186), one dimension fewer (the ABI holds 4): sum over a (1,1,1,3) window
+    # equals the box filter with Fill(0), and the replicate sum of ones is 3 everywhere
+    img105 = np.ones((5, 5, 5, 5), order="F")
+    out105 = ifb.mapwindow(ifb.sum_, img105, (1, 1, 1, 3), border=ifb.Fill(0), _library=lib)
+    foo, bar = ifb.centered(np.array([1.0])), ifb.centered(np.array([1.0, 1.0, 1.0]))
+    ref105 = ifb.imfilter(img105, ifb.kernelfactors((foo, foo, foo, bar)), ifb.Fill(0), _library=lib)
+    assert np.array_equal(out105, ref105)
+    assert np.all(ifb.mapwindow(ifb.sum_, img105, (1, 1, 1, 3), _library=lib) == 3.0)
+    # integer windows: exact sums in Int, means in Float64
+    iv = np.arange(1, 8)
+    assert np.array_equal(ifb.mapwindow(ifb.sum_, iv, (3,), _library=lib), [4, 6, 9, 12, 15, 18, 20])
+    m = ifb.mapwindow(ifb.mean, iv, (3,), _library=lib)
+    assert m.dtype == np.float64 and approx(m, np.array([4, 6, 9, 12, 15, 18, 20]) / 3)
+
+
+ALL_CHECKS = [check_mapwindow_reductions, check_golden_fixtures_f, check_median_window, check_local_extrema, check_blob_log, check_na_border, check_color_images, check_padarray, check_1d, check_widening, check_prewitt_tiling, check_impulse_interior,
               check_impulse_corner, check_offset_axes, check_nonfinite, check_3d_box, check_cascade,
               check_gradients, check_laplacian, check_extrema_goldens, check_mapwindow_offsets]

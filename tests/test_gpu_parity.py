@@ -624,3 +624,33 @@ def test_median_window_parity(ifb, oracle, device, dt):
             r = ref.parent if isinstance(ref, ifb.OffsetArray) else ref
             assert g.dtype == r.dtype == (np.float32 if dt == np.float32 else np.float64)
             assert np.array_equal(g, r, equal_nan=True), (shape, window, border)
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64, np.int32, np.uint8, np.int64])
+def test_window_reductions_parity(ifb, oracle, device, dt):
+    """mapwindow(mean | sum | minimum | maximum | median!, ...; border, indices=strided ranges) — the generic window loop of the
+    reference (src/mapwindow.jl:270-306) — bit-equal to the oracle: sums run in the window's memory order with the
+    reference's accumulator type on both sides."""
+    rng = np.random.default_rng(seed_of("winreduce", str(np.dtype(dt))))
+    if np.dtype(dt).kind == "f":
+        img = np.asfortranarray(rng.standard_normal((61, 47)).astype(dt))
+        vol = np.asfortranarray(rng.standard_normal((20, 17, 9)).astype(dt))
+    else:
+        img = np.asfortranarray(rng.integers(0, 200, size=(61, 47)).astype(dt))
+        vol = np.asfortranarray(rng.integers(0, 200, size=(20, 17, 9)).astype(dt))
+    for f in (ifb.mean, ifb.sum_, ifb.minimum, ifb.maximum, ifb.median):
+        for border in ("replicate", "reflect", "circular", "symmetric", ifb.Fill(3), ifb.Inner()):
+            a = ifb.mapwindow(f, img, (5, 3), border=border)
+            if f in (ifb.mean, ifb.sum_):
+                assert device.last_path() == "winreduce"
+            b = ifb.mapwindow(f, img, (5, 3), border=border, _library=oracle)
+            pa = a.parent if isinstance(a, ifb.OffsetArray) else a
+            pb = b.parent if isinstance(b, ifb.OffsetArray) else b
+            assert pa.dtype == pb.dtype and np.array_equal(pa, pb, equal_nan=True), (f, border)
+        inds = (range(2, 60, 3), range(1, 47, 2))
+        a = ifb.mapwindow(f, img, (range(-2, 2), range(-1, 2)), indices=inds)
+        b = ifb.mapwindow(f, img, (range(-2, 2), range(-1, 2)), indices=inds, _library=oracle)
+        assert a.shape == (20, 23) and np.array_equal(a, b), f
+        a = ifb.mapwindow(f, vol, (3, 1, 5), border="symmetric", indices=(range(1, 21, 4), range(1, 18), range(3, 9, 2)))
+        b = ifb.mapwindow(f, vol, (3, 1, 5), border="symmetric", indices=(range(1, 21, 4), range(1, 18), range(3, 9, 2)), _library=oracle)
+        assert np.array_equal(a, b), f
