@@ -36,7 +36,7 @@ DTYPE_TO_NP[N0F8] = np.dtype(np.uint8)
 SYMBOLS = [
     "b2f_version", "b2f_last_error", "b2f_is_device_library", "b2f_set_device", "b2f_device_count", "b2f_sm_count",
     "b2f_malloc", "b2f_free", "b2f_host_alloc", "b2f_host_free", "b2f_host_register", "b2f_host_unregister", "b2f_memcpy_h2d", "b2f_memcpy_d2h",
-    "b2f_sync", "b2f_ipc_export", "b2f_ipc_open", "b2f_ipc_close", "b2f_imfilter", "b2f_imgradients", "b2f_mapwindow_extrema", "b2f_mapwindow_median", "b2f_mapwindow_reduce", "b2f_imfilter_slab", "b2f_imfilter_slab_staged", "b2f_memcpy_async", "b2f_memcpy2d_async",
+    "b2f_sync", "b2f_ipc_export", "b2f_ipc_open", "b2f_ipc_close", "b2f_imfilter", "b2f_imgradients", "b2f_mapwindow_extrema", "b2f_mapwindow_median", "b2f_mapwindow_reduce", "b2f_imfilter_slab", "b2f_imfilter_slab_staged", "b2f_shard_ctx_create", "b2f_shard_ctx_export", "b2f_shard_ctx_connect", "b2f_shard_handshake", "b2f_imfilter_sharded", "b2f_shard_ctx_destroy", "b2f_memcpy_async", "b2f_memcpy2d_async",
     "b2f_memset_async", "b2f_stream_write32", "b2f_stream_wait_geq32",
     "b2f_findlocalextrema", "b2f_scale_into_slice", "b2f_maxabs", "b2f_gather", "b2f_na_prepare", "b2f_divide",
     "b2f_normalize_dims",
@@ -201,6 +201,13 @@ class Library:
             C.POINTER(b2f_array), C.POINTER(b2f_array), C.POINTER(b2f_stage), C.c_int32,
             C.POINTER(b2f_border), C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
             C.c_int32, C.c_int32, C.c_void_p]
+        d.b2f_shard_ctx_create.argtypes = [C.POINTER(C.c_void_p), C.c_int32, C.c_int32]
+        d.b2f_shard_ctx_export.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+        d.b2f_shard_ctx_connect.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        d.b2f_shard_handshake.argtypes = [C.c_void_p, C.c_void_p]
+        d.b2f_imfilter_sharded.argtypes = [C.c_void_p, C.POINTER(b2f_array), C.POINTER(b2f_array), C.POINTER(b2f_stage), C.c_int32,
+                                           C.POINTER(b2f_border), C.c_int64, C.c_int64, C.c_void_p]
+        d.b2f_shard_ctx_destroy.argtypes = [C.c_void_p]
         d.b2f_memcpy2d_async.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p]
         d.b2f_memcpy_async.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
         d.b2f_memset_async.argtypes = [C.c_void_p, C.c_int32, C.c_uint64, C.c_void_p]

@@ -129,8 +129,8 @@ class ShardedImfilter:
         self.out = out
         self.plane_elems = int(np.prod(slab.shape[1:]))
         if mode == "auto":
-            mode = "staged" if (slab.is_cuda and self.world > 1) else "sendrecv"   # falls back to "p2p" reads when unsupported
-        if mode not in ("p2p", "staged", "sendrecv"):
+            mode = "driver" if (slab.is_cuda and self.world > 1 and self.lib.is_device_library()) else "sendrecv"
+        if mode not in ("driver", "p2p", "staged", "sendrecv"):
             raise ArgumentError(f"unknown halo transport {mode!r}")
         self.mode = mode
         self._opened = []
@@ -139,7 +139,10 @@ class ShardedImfilter:
         self._nccl = self.world > 1 and dist.get_backend(group) == "nccl"
         self._flag = torch.zeros(1, dtype=torch.int32, device=slab.device) if self._nccl else None
         self._epoch = 0
-        if self.world > 1 and (self.lower is not None or self.upper is not None or mode in ("p2p", "staged")):
+        self._ctx = None
+        if self.world > 1 and mode == "driver":
+            self._setup_driver()
+        elif self.world > 1 and (self.lower is not None or self.upper is not None or mode in ("p2p", "staged")):
             if mode == "p2p":
                 self._setup_p2p()
             elif mode == "staged":
@@ -187,6 +190,22 @@ class ShardedImfilter:
                 base = self.lib.ipc_open(h, off)
                 self._opened.append((base, off))
             self.halo_hi_ptr = base
+
+    def _setup_driver(self):
+        """The C driver (b2f_shard_*, csrc/sharded.cu): this class only moves the 256-byte blobs between the ranks."""
+        import ctypes as C
+        if not self.slab.is_cuda:
+            raise ArgumentError('halo transport "driver" needs CUDA tensors')
+        ctx = C.c_void_p()
+        self.lib.check(self.lib.dll.b2f_shard_ctx_create(C.byref(ctx), self.rank, self.world))
+        self._ctx = ctx
+        blob = C.create_string_buffer(256)
+        self.lib.check(self.lib.dll.b2f_shard_ctx_export(ctx, C.c_void_p(self.slab.data_ptr()), int(self.slab.shape[0]), blob))
+        blobs = [None] * self.world
+        self.dist.all_gather_object(blobs, blob.raw, group=self.group)
+        lo = C.create_string_buffer(blobs[self.lower], 256) if self.lower is not None else None
+        hi = C.create_string_buffer(blobs[self.upper], 256) if self.upper is not None else None
+        self.lib.check(self.lib.dll.b2f_shard_ctx_connect(ctx, lo, hi))
 
     def _setup_sendrecv(self):
         t = self.torch
@@ -240,6 +259,10 @@ class ShardedImfilter:
         4-byte all-reduce on the current stream), host-side otherwise."""
         if self.world == 1:
             return
+        if self.mode == "driver" and self._ctx is not None:
+            import ctypes as C
+            stream = self.torch.cuda.current_stream().cuda_stream
+            return self.lib.check(self.lib.dll.b2f_shard_handshake(self._ctx, C.c_void_p(stream)))
         if not full and self.mode in ("p2p", "staged") and getattr(self, "_peer_sync", None) is not None and self.handshake:
             return self._neighbour_handshake()
         if self._nccl:
@@ -270,6 +293,12 @@ class ShardedImfilter:
         (only valid when the neighbours' inputs are known to be complete and unchanged)."""
         t = self.torch
         stream = t.cuda.current_stream().cuda_stream if self.slab.is_cuda else 0
+        if self.world > 1 and self.mode == "driver":
+            import ctypes as C
+            img, out, b = _desc(self.slab, self.n0f8), _desc(self.out), self.border.to_abi(self.ndim)
+            self.lib.check(self.lib.dll.b2f_imfilter_sharded(self._ctx, C.byref(img), C.byref(out), self.stages.arr, self.stages.n, C.byref(b),
+                                                             self.global_planes, self.first, C.c_void_p(stream)))
+            return self.out
         if self.world > 1 and self.mode == "staged":
             return self._run_staged(sync, stream)
         if self.world > 1:
@@ -341,6 +370,14 @@ class ShardedImfilter:
         return self.out
 
     def close(self):
+        if self._ctx is not None:
+            self.barrier(full=True)             # nobody may still be reading my planes
+            self.torch.cuda.synchronize()
+            if self._nccl:
+                self.dist.barrier(group=self.group)
+            self.lib.check(self.lib.dll.b2f_shard_ctx_destroy(self._ctx))
+            self._ctx = None
+            return
         if self.world > 1 and self.mode in ("p2p", "staged"):
             self.barrier(full=True)             # nobody may still be reading my planes
             if self.slab.is_cuda:

@@ -248,6 +248,30 @@ int b2f_imfilter_slab_staged(const b2f_array *img, const b2f_array *out,
                              const void *halo_hi, int64_t n_halo_hi,
                              const void *flag_lo, const void *flag_hi, int32_t epoch, int32_t lo_early_rows,
                              void *stream);
+/* ---- the sharded driver: one rank per GPU, slabs along the last axis ---------------------------------------
+ * b2f_imfilter_sharded is b2f_imfilter for ONE RANK's slab of an array partitioned over `world` GPUs of a node: the
+ * result equals this rank's planes of the filter applied to the whole array.  Per pass the library performs the neighbour
+ * hand-shake (32-bit stream-ordered writes / waits over NVLink), pulls the neighbours' boundary planes with the copy engines
+ * into local halo buffers while the fused kernel is already marching, and launches the kernel — no host synchronisation,
+ * no collective, no dependency on a communication library.  Set-up:
+ *     b2f_shard_ctx_create(&ctx, rank, world);
+ *     b2f_shard_ctx_export(ctx, slab_ptr, planes, blob);        // 256-byte blob: CUDA IPC handles + plane count
+ *     ... the caller moves the blobs between ranks (MPI_Sendrecv, Distributed.jl, a file, torch.distributed) ...
+ *     b2f_shard_ctx_connect(ctx, lower_blob_or_NULL, upper_blob_or_NULL);   (NULL at a global face; under
+ *                                                                           Pad(:circular) the wrap-around ranks are neighbours too)
+ *     b2f_imfilter_sharded(ctx, img (its ptr == slab_ptr), out, stages, nstages, border, global_last_dim, slab_first, stream);
+ * Every rank must make the same sequence of b2f_imfilter_sharded / b2f_shard_handshake calls.  Before REFILLING a slab call
+ * b2f_shard_handshake(ctx, stream) (the neighbours have finished reading it once it completes).  Device arrays only. */
+#define B2F_SHARD_BLOB 256
+typedef struct b2f_shard_ctx b2f_shard_ctx;
+int b2f_shard_ctx_create(b2f_shard_ctx **ctx, int32_t rank, int32_t world);
+int b2f_shard_ctx_export(b2f_shard_ctx *ctx, const void *slab, int64_t planes, void *blob256);
+int b2f_shard_ctx_connect(b2f_shard_ctx *ctx, const void *lower_blob256, const void *upper_blob256);
+int b2f_shard_handshake(b2f_shard_ctx *ctx, void *stream);
+int b2f_imfilter_sharded(b2f_shard_ctx *ctx, const b2f_array *img, const b2f_array *out, const b2f_stage *stages, int32_t nstages,
+                         const b2f_border *border, int64_t global_last_dim, int64_t slab_first, void *stream);
+int b2f_shard_ctx_destroy(b2f_shard_ctx *ctx);
+
 /* stream-ordered device copies / byte fills (peer-mapped pointers allowed): the halo staging of the sharded path */
 int b2f_memcpy_async(void *dst, const void *src, uint64_t bytes, void *stream);
 int b2f_memcpy2d_async(void *dst, uint64_t dpitch, const void *src, uint64_t spitch, uint64_t width, uint64_t height,

@@ -36,4 +36,4 @@ def test_slab_bounds_and_halo_extent(ifb):
 @pytest.mark.gpu
 @pytest.mark.parametrize("world", [2, 3])
 def test_sharded_device_two_ranks_one_gpu(world):
-    _check(launch(world, use_device=True, modes=["p2p", "staged", "sendrecv"]), world)
+    _check(launch(world, use_device=True, modes=["driver", "p2p", "staged", "sendrecv"]), world)
