@@ -2,7 +2,7 @@
 #include <algorithm>
 #include <cstdlib>
 
-#include "stream3d_v3.cuh"
+#include "stream3d_v4.cuh"
 
 namespace b2f {
 
@@ -60,21 +60,18 @@ template <int LXT, int LYT, int LZT>
 static int s3_launch_one(S3Params &P, const float *kz, cudaStream_t st) {
     long long nblocks;
     typedef S3C<LXT, LYT, LZT> C;
-    // debugging knobs: B2F_S3_V=1 / 2 run the round-1 kernel / its one-plane-per-step successor (A/B on the same box),
-    // B2F_S3_CS=0 plain instead of streaming stores
-    static const int ver = getenv("B2F_S3_V") ? atoi(getenv("B2F_S3_V")) : 3;
+    // debugging knobs: B2F_S3_V=3 runs the previous form of the kernel (A/B on the same box), B2F_S3_CS=0 plain instead of
+    // streaming stores
+    static const int ver = getenv("B2F_S3_V") ? atoi(getenv("B2F_S3_V")) : 4;
     static const bool cs = getenv("B2F_S3_CS") ? atoi(getenv("B2F_S3_CS")) != 0 : true;
     typedef S3VC<LXT, LYT, LZT> C3;
-    const size_t smem = ver == 3 ? C3::SMEM : C::SMEM;
-    void (*kern)(const S3Params, const CUtensorMap, const CUtensorMap, const CUtensorMap) =
-        ver == 1 ? stream3d_kernel<LXT, LYT, LZT>
-                 : (cs ? stream3d_kernel2<LXT, LYT, LZT, true> : stream3d_kernel2<LXT, LYT, LZT, false>);
+    const size_t smem = C3::SMEM;
     void (*kern3)(const S3Params, const S3VTaps, const CUtensorMap, const CUtensorMap, const CUtensorMap) =
-        cs ? stream3d_kernel3<LXT, LYT, LZT, true> : stream3d_kernel3<LXT, LYT, LZT, false>;
+        ver == 3 ? (cs ? stream3d_kernel3<LXT, LYT, LZT, true> : stream3d_kernel3<LXT, LYT, LZT, false>)
+                 : (cs ? stream3d_kernel4<LXT, LYT, LZT, true> : stream3d_kernel4<LXT, LYT, LZT, false>);
     static thread_local bool configured = false;
     if (!configured) {
-        if (ver == 3) B2F_CUDA(cudaFuncSetAttribute(kern3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        else B2F_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        B2F_CUDA(cudaFuncSetAttribute(kern3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
     S3VTaps TZ;
@@ -110,8 +107,7 @@ static int s3_launch_one(S3Params &P, const float *kz, cudaStream_t st) {
         P.nfull = (int)std::min<long long>(tiles, (long long)P.nfull / ntx0 * P.ntx);
     }
     nblocks = P.nfull + ((long long)P.ntx * P.nty - P.nfull) * P.kch;
-    if (ver == 3) kern3<<<(unsigned)nblocks, S3_NT, smem, st>>>(P, TZ, m_own, m_lo, m_hi);
-    else kern<<<(unsigned)nblocks, S3_NT, smem, st>>>(P, m_own, m_lo, m_hi);
+    kern3<<<(unsigned)nblocks, S3_NT, smem, st>>>(P, TZ, m_own, m_lo, m_hi);
     count_launch();
     B2F_CUDA(cudaGetLastError());
     return 0;
@@ -132,6 +128,10 @@ int run_stream3d_slab(const Plan &Pl, const void *own, const void *lo, int64_t l
     P.Zg = (int)Pl.img_ax.len(2);
     P.W = (int)Pl.img_ax.len(0); P.H = (int)Pl.img_ax.len(1);
     P.plane = (long long)P.W * P.H;
+    static const int dbg = getenv("B2F_S3_DBG") ? atoi(getenv("B2F_S3_DBG")) : 0;
+    P.dbg = dbg;
+    P.row_b = (long long)P.W * 4;
+    P.plane_b = P.plane * 4;
     P.out = (float *)d_out;
     P.style = Pl.style; P.fill = (float)Pl.fill;
     const StageInfo &sx = Pl.stages[Pl.active[0]], &sy = Pl.stages[Pl.active[1]], &sz = Pl.stages[Pl.active[2]];
