@@ -56,30 +56,54 @@ static bool s3_make_map(CUtensorMap *m, const void *base, int W, int H, long lon
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// z-chunks.  CTAs are dispatched in blockIdx order onto `slots` concurrent CTA slots.  A chunk re-runs Lz-1 planes of stages x
+// and y, so long marches are cheapest, but whole waves of them quantise badly.  So: the first `nfull` tiles (whole waves)
+// march all planes, the remaining tiles are cut into `kch` chunks each, which fills the last wave evenly.  (nfull, kch)
+// minimise the makespan of that list schedule (closed form: w whole waves of full marches, then ceil(rest * k / slots) waves
+// of chunks).
+static int s3_geometry(S3Params &P, int ty_rows, int slots) {
+    P.ntx = (P.W + P.xsh + S3_TX - 1) / S3_TX;
+    P.nty = (P.H + ty_rows - 1) / ty_rows;
+    const long long tiles = (long long)P.ntx * P.nty, own_n = P.own_n;
+    const int ov = P.Lz - 1 + 3;
+    long long best_full = tiles, best_k = 1, best_cost = ((tiles + slots - 1) / slots) * (own_n + ov);
+    for (long long w = 0; w * slots <= tiles; ++w) {
+        const long long rest = tiles - w * slots;
+        if (rest == 0) break;
+        for (long long k = 1; k <= 16 && k <= own_n; ++k) {
+            const long long zc = (own_n + k - 1) / k;
+            if (k > 1 && zc < 8) break;
+            const long long c = w * (own_n + ov) + ((rest * k + slots - 1) / slots) * (zc + ov);
+            if (c < best_cost) { best_cost = c; best_full = w * slots; best_k = k; }
+        }
+    }
+    P.nfull = (int)best_full;
+    P.kch = (int)best_k;
+    P.zchunk = (int)((own_n + best_k - 1) / best_k);
+    if (best_full + (tiles - best_full) * best_k > 0x7fffffffLL) return fail(B2F_ENOTSUP, "stream3d grid too large");
+    return 0;
+}
+
 template <int LXT, int LYT, int LZT>
 static int s3_launch_one(S3Params &P, const float *kz, cudaStream_t st) {
-    long long nblocks;
     typedef S3C<LXT, LYT, LZT> C;
-    // debugging knobs: B2F_S3_V=3 runs the previous form of the kernel (A/B on the same box), B2F_S3_CS=0 plain instead of
-    // streaming stores
-    static const int ver = getenv("B2F_S3_V") ? atoi(getenv("B2F_S3_V")) : 4;
+    typedef S3VC<LXT, LYT, LZT> C4;
+    // debugging knobs: B2F_S3_CS=0 plain instead of streaming stores, B2F_S3_NO_TMA forces the gather loader
     static const bool cs = getenv("B2F_S3_CS") ? atoi(getenv("B2F_S3_CS")) != 0 : true;
-    typedef S3VC<LXT, LYT, LZT> C3;
-    const size_t smem = C3::SMEM;
-    void (*kern3)(const S3Params, const S3VTaps, const CUtensorMap, const CUtensorMap, const CUtensorMap) =
-        ver == 3 ? (cs ? stream3d_kernel3<LXT, LYT, LZT, true> : stream3d_kernel3<LXT, LYT, LZT, false>)
-                 : (cs ? stream3d_kernel4<LXT, LYT, LZT, true> : stream3d_kernel4<LXT, LYT, LZT, false>);
+    static const bool no_tma = getenv("B2F_S3_NO_TMA") != nullptr;
+    typedef void (*kern_t)(const S3Params, const S3VTaps, const CUtensorMap, const CUtensorMap, const CUtensorMap);
+    const kern_t k4 = cs ? stream3d_kernel4<LXT, LYT, LZT, true> : stream3d_kernel4<LXT, LYT, LZT, false>;
     static thread_local bool configured = false;
     if (!configured) {
-        B2F_CUDA(cudaFuncSetAttribute(kern3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        B2F_CUDA(cudaFuncSetAttribute(k4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C4::SMEM));
         configured = true;
     }
     S3VTaps TZ;
     memset(&TZ, 0, sizeof TZ);
     {   // z taps right-aligned in K (odd) slots, as the pairs of the paired z stage
         float kk[S3_MAXTAPS + 3] = {0};                      // kk[1 + j], j = -1 .. K
-        for (int j = 0; j < P.Lz; ++j) kk[1 + C3::K - P.Lz + j] = kz[j];
-        for (int i = 0; i <= C3::NP; ++i) {
+        for (int j = 0; j < P.Lz; ++j) kk[1 + C4::K - P.Lz + j] = kz[j];
+        for (int i = 0; i <= C4::NP; ++i) {
             TZ.p0[i] = make_float2(kk[1 + 2 * i - 1], kk[1 + 2 * i]);
             TZ.p1[i] = make_float2(kk[1 + 2 * i], kk[1 + 2 * i + 1]);
         }
@@ -87,27 +111,25 @@ static int s3_launch_one(S3Params &P, const float *kz, cudaStream_t st) {
     for (int j = 0; j < S3_MAXTAPS; ++j) P.kzr[j] = 0.f;
     for (int j = 0; j < P.Lz; ++j) P.kzr[C::LBZ - P.Lz + j] = kz[j];      // right-aligned in the LBZ slots
     alignas(64) CUtensorMap m_own, m_lo, m_hi;
-    memset(&m_own, 0, sizeof m_own); memset(&m_lo, 0, sizeof m_lo); memset(&m_hi, 0, sizeof m_hi);
-    static const bool no_tma = getenv("B2F_S3_NO_TMA") != nullptr;      // debugging knob: force the gather loader
-    bool tma = !no_tma && P.use_tma && (P.style != B2F_FILL || P.fill == 0.0f);
-    tma = tma && s3_make_map(&m_own, P.own, P.W, P.H, P.own_n, C::RH);
-    if (tma && P.lo_n > 0) tma = s3_make_map(&m_lo, P.lo, P.W, P.H, P.lo_n, C::RH);
-    if (tma && P.hi_n > 0) tma = s3_make_map(&m_hi, P.hi, P.W, P.H, P.hi_n, C::RH);
+    const bool tma_ok = !no_tma && P.use_tma && (P.style != B2F_FILL || P.fill == 0.0f);
+    auto make_maps = [&](int rows) {
+        memset(&m_own, 0, sizeof m_own); memset(&m_lo, 0, sizeof m_lo); memset(&m_hi, 0, sizeof m_hi);
+        bool ok = tma_ok && s3_make_map(&m_own, P.own, P.W, P.H, P.own_n, rows);
+        if (ok && P.lo_n > 0) ok = s3_make_map(&m_lo, P.lo, P.W, P.H, P.lo_n, rows);
+        if (ok && P.hi_n > 0) ok = s3_make_map(&m_hi, P.hi, P.W, P.H, P.hi_n, rows);
+        return ok;
+    };
+    // cp.async.bulk.tensor wants the box to start on a 16-byte boundary of the innermost axis (found the hard way:
+    // "illegal instruction" otherwise), so with TMA the tile grid is shifted left by xsh = klox mod 4 columns
+    const int xsh_tma = ((P.klox % 4) + 4) % 4, SMS = sm_count();
+    const bool tma = make_maps(C::RH);
     P.use_tma = tma ? 1 : 0;
     if (!tma && (P.flag_lo || P.flag_hi))
         return fail(B2F_ENOTSUP, "staged halos need the TMA path (row length a multiple of 4, 16-byte aligned buffers)");
-    // cp.async.bulk.tensor wants the box to start on a 16-byte boundary of the innermost axis (found the hard way:
-    // "illegal instruction" otherwise), so the tile grid is shifted left by xsh = klox mod 4 columns
-    P.xsh = tma ? ((P.klox % 4) + 4) % 4 : 0;
-    if (P.xsh & 1) P.vec_out = 0;
-    const int ntx0 = P.ntx;
-    P.ntx = (P.W + P.xsh + S3_TX - 1) / S3_TX;
-    if (P.ntx != ntx0) {                              // the shift added a tile column: keep the split, as whole tile rows
-        const long long tiles = (long long)P.ntx * P.nty;
-        P.nfull = (int)std::min<long long>(tiles, (long long)P.nfull / ntx0 * P.ntx);
-    }
-    nblocks = P.nfull + ((long long)P.ntx * P.nty - P.nfull) * P.kch;
-    kern3<<<(unsigned)nblocks, S3_NT, smem, st>>>(P, TZ, m_own, m_lo, m_hi);
+    P.xsh = tma ? xsh_tma : 0;
+    if (int rc = s3_geometry(P, S3_TY, SMS)) return rc;
+    const long long nblocks = P.nfull + ((long long)P.ntx * P.nty - P.nfull) * P.kch;
+    k4<<<(unsigned)nblocks, S3_NT, C4::SMEM, st>>>(P, TZ, m_own, m_lo, m_hi);
     count_launch();
     B2F_CUDA(cudaGetLastError());
     return 0;
@@ -128,8 +150,6 @@ int run_stream3d_slab(const Plan &Pl, const void *own, const void *lo, int64_t l
     P.Zg = (int)Pl.img_ax.len(2);
     P.W = (int)Pl.img_ax.len(0); P.H = (int)Pl.img_ax.len(1);
     P.plane = (long long)P.W * P.H;
-    static const int dbg = getenv("B2F_S3_DBG") ? atoi(getenv("B2F_S3_DBG")) : 0;
-    P.dbg = dbg;
     P.row_b = (long long)P.W * 4;
     P.plane_b = P.plane * 4;
     P.out = (float *)d_out;
@@ -147,32 +167,6 @@ int run_stream3d_slab(const Plan &Pl, const void *own, const void *lo, int64_t l
     auto al16 = [](const void *p) { return reinterpret_cast<uintptr_t>(p) % 16 == 0; };
     P.use_tma = (P.W % 4 == 0) && al16(own) && (lo_n == 0 || al16(lo)) && (hi_n == 0 || al16(hi));
     P.vec_out = (P.W % 2 == 0) && reinterpret_cast<uintptr_t>(d_out) % 8 == 0;
-    P.ntx = (P.W + S3_TX - 1) / S3_TX;
-    P.nty = (P.H + S3_TY - 1) / S3_TY;
-    // z-chunks.  One CTA per SM at a time, CTAs dispatched in blockIdx order.  A chunk re-runs Lz-1 planes of stages x and
-    // y, so long marches are cheapest, but whole waves of them quantise badly (512 tiles on 148 SMs: the 4th wave is
-    // 46% full).  So: the first `nfull` tiles (whole waves) march all planes, the remaining tiles are cut into `kch`
-    // chunks each, which fills the last wave evenly.  (nfull, kch) minimise the makespan of that list schedule.
-    const long long tiles = (long long)P.ntx * P.nty;
-    const int ov = P.Lz - 1 + 3, SMS = sm_count();
-    // closed form: w whole waves of full marches, then ceil(rest * k / SMS) waves of chunks
-    long long best_full = tiles, best_k = 1, best_cost = ((tiles + SMS - 1) / SMS) * (own_n + ov);
-    for (long long w = 0; w * SMS <= tiles; ++w) {
-        const long long rest = tiles - w * SMS;
-        if (rest == 0) break;
-        for (long long k = 1; k <= 16 && k <= own_n; ++k) {
-            const long long zc = (own_n + k - 1) / k;
-            if (k > 1 && zc < 8) break;
-            const long long c = w * (own_n + ov) + ((rest * k + SMS - 1) / SMS) * (zc + ov);
-            if (c < best_cost) { best_cost = c; best_full = w * SMS; best_k = k; }
-        }
-    }
-    P.nfull = (int)best_full;
-    P.kch = (int)best_k;
-    P.zchunk = (int)((own_n + best_k - 1) / best_k);
-    const long long nch = 0;
-    (void)nch;
-    if (best_full + (tiles - best_full) * best_k + (long long)P.nty * best_k > 0x7fffffffLL) return fail(B2F_ENOTSUP, "stream3d grid too large");
     if (P.Lx == 17 && P.Ly == 17 && P.Lz == 17) return s3_launch_one<17, 17, 17>(P, kz, st);
     if (P.Lx == 9 && P.Ly == 9 && P.Lz == 9) return s3_launch_one<9, 9, 9>(P, kz, st);
     if (P.Lx == 5 && P.Ly == 5 && P.Lz == 5) return s3_launch_one<5, 5, 5>(P, kz, st);

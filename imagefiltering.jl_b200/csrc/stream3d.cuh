@@ -68,7 +68,6 @@ struct S3Params {
     // buffer is complete (NULL: the planes are there already)
     const unsigned char *flag_lo, *flag_hi;   // flag_lo[0]: rows [0, lo_early_rows) of every lower halo plane, flag_lo[1]: the rest
     int epoch, lo_early_rows;
-    int dbg;                       // timing experiments only (B2F_S3_DBG): bits switch parts of the steady-state step off
     int use_tma;                   // the tensor maps are valid (else every cell comes through the gather loader)
     float kx[S3_MAXTAPS], ky[S3_MAXTAPS];
     float kzr[S3_MAXTAPS];         // z taps RIGHT-aligned in the instantiation's LBZ slots

@@ -240,13 +240,16 @@ stream3d_kernel4(const __grid_constant__ S3Params P, const __grid_constant__ S3V
 
     // prologue: planes 0..N-1 in flight.  Only thread 0 ever waits for a TMA to land: it checks the planes two steps before
     // stage x reads them and its next barrier arrival publishes that to the CTA (the other warps never touch the TMA
-    // barriers: one try_wait latency less per warp-task).  Border tiles patch planes 0 and 1 before the first stage x.
+    // barriers: one try_wait latency less per warp-task).  Border tiles patch planes 0 .. 3 before the first stage x.
     auto landed = [&](int p) { s3_mbar_wait(full + 8 * (p & (N - 1)), (p / N) & 1); };
     if (tma && tid == 0) {
         for (int p = 0; p < min(N, in_planes); ++p) issue(p);
         for (int p = 0; p < min(4, in_planes); ++p) landed(p);
     }
-    if (fix) patch2(0, min(2, in_planes));
+    if (fix) {                                  // planes 0 .. 3; step s patches planes 2s+6, 2s+7
+        patch2(0, min(2, in_planes));
+        if (in_planes > 2) patch2(2, min(2, in_planes - 2));
+    }
     __syncthreads();
 
     // this thread's column and 4 rows in stages y / z
@@ -341,13 +344,13 @@ stream3d_kernel4(const __grid_constant__ S3Params P, const __grid_constant__ S3V
         if (((p0 + 2) & (S3_PTB - 1)) == 0) locate_block(p0 + S3_PTA, S3_PTB);
         if (s >= 0 && !ok) s3_mbar_wait(xfull + 8 * bi, ph);
         ok = false;
-        if (fix) {                                                  // the planes of the NEXT step's stage x
-            if (p0 + 4 < in_planes) patch2(p0 + 4, min(2, in_planes - (p0 + 4)));
-        }
         stage_x(p0 + 2, p0 + 2 < in_planes, p0 + 3 < in_planes);
         tma_check(p0, false);
         arrive_next();
         tma_work(p0, false);
+        // border cells of the planes stage x reads TWO steps from now: behind the arrival, off the hand-off's critical path
+        // (the next step's arrival publishes them)
+        if (fix && p0 + 6 < in_planes) patch2(p0 + 6, min(2, in_planes - (p0 + 6)));
         if (s >= 0) {
             const int o = p0 - (Lz - 1);
             float2 ma[2], mb[2];
@@ -369,11 +372,11 @@ stream3d_kernel4(const __grid_constant__ S3Params P, const __grid_constant__ S3V
         constexpr bool FIX = decltype(fixc)::value;
         const int p0 = 2 * s;
         if (!ok) s3_mbar_wait(xfull + 8 * bi, ph);
-        if (FIX) patch2(p0 + 4, 2);
         stage_x(p0 + 2, true, true);
         tma_check(p0, true);
         arrive_next();
         tma_work(p0, true);
+        if (FIX) patch2(p0 + 6, 2);
         float2 ma[2], mb[2];
         const unsigned xa0 = xf_sa + (2 * bi * XFSZ + yoff) * 4;
         s3v_y_task4x2<LXT, LYT, LZT>(P, xa0, xa0 + XFSZ * 4, ma, mb, Ly);
