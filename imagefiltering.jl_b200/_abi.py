@@ -36,7 +36,7 @@ DTYPE_TO_NP[N0F8] = np.dtype(np.uint8)
 SYMBOLS = [
     "b2f_version", "b2f_last_error", "b2f_is_device_library", "b2f_set_device", "b2f_device_count", "b2f_sm_count",
     "b2f_malloc", "b2f_free", "b2f_host_alloc", "b2f_host_free", "b2f_host_register", "b2f_host_unregister", "b2f_memcpy_h2d", "b2f_memcpy_d2h",
-    "b2f_sync", "b2f_ipc_export", "b2f_ipc_open", "b2f_ipc_close", "b2f_imfilter", "b2f_imgradients", "b2f_mapwindow_extrema", "b2f_mapwindow_median", "b2f_mapwindow_reduce", "b2f_imfilter_slab", "b2f_imfilter_slab_staged", "b2f_shard_ctx_create", "b2f_shard_ctx_export", "b2f_shard_ctx_connect", "b2f_shard_handshake", "b2f_imfilter_sharded", "b2f_shard_ctx_destroy", "b2f_memcpy_async", "b2f_memcpy2d_async",
+    "b2f_sync", "b2f_ipc_export", "b2f_ipc_open", "b2f_ipc_close", "b2f_imfilter", "b2f_imgradients", "b2f_mapwindow_extrema", "b2f_mapwindow_median", "b2f_mapwindow_reduce", "b2f_imfilter_slab", "b2f_imfilter_slab_staged", "b2f_imfilter_slab_xy", "b2f_shard_ctx_create", "b2f_shard_ctx_export", "b2f_shard_ctx_connect", "b2f_shard_handshake", "b2f_imfilter_sharded", "b2f_shard_ctx_destroy", "b2f_memcpy_async", "b2f_memcpy2d_async",
     "b2f_memset_async", "b2f_stream_write32", "b2f_stream_wait_geq32",
     "b2f_findlocalextrema", "b2f_scale_into_slice", "b2f_maxabs", "b2f_gather", "b2f_na_prepare", "b2f_divide",
     "b2f_normalize_dims",
@@ -63,6 +63,14 @@ class b2f_border(C.Structure):
     _fields_ = [
         ("style", C.c_int32), ("npad", C.c_int32), ("fill", C.c_double),
         ("lo", C.c_int64 * MAXDIM), ("hi", C.c_int64 * MAXDIM),
+    ]
+
+
+class b2f_slab_xy(C.Structure):
+    """xy-filtered boundary planes of a slab (include/b2f.h)."""
+    _fields_ = [
+        ("xy_lo", C.c_void_p), ("lo_halo", C.c_int64), ("lo_own", C.c_int64),
+        ("xy_hi", C.c_void_p), ("hi_own", C.c_int64), ("hi_halo", C.c_int64),
     ]
 
 
@@ -201,6 +209,10 @@ class Library:
             C.POINTER(b2f_array), C.POINTER(b2f_array), C.POINTER(b2f_stage), C.c_int32,
             C.POINTER(b2f_border), C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
             C.c_int32, C.c_int32, C.c_void_p]
+        d.b2f_imfilter_slab_xy.argtypes = [
+            C.POINTER(b2f_array), C.POINTER(b2f_array), C.POINTER(b2f_stage), C.c_int32,
+            C.POINTER(b2f_border), C.c_int64, C.c_int64, C.POINTER(b2f_slab_xy), C.c_void_p, C.c_void_p,
+            C.c_int32, C.c_int32, C.c_void_p]
         d.b2f_shard_ctx_create.argtypes = [C.POINTER(C.c_void_p), C.c_int32, C.c_int32]
         d.b2f_shard_ctx_export.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
         d.b2f_shard_ctx_connect.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -324,6 +336,15 @@ class Library:
                                                      global_last_dim, slab_first, C.c_void_p(halo_lo or None), n_halo_lo,
                                                      C.c_void_p(halo_hi or None), n_halo_hi, C.c_void_p(flag_lo or None),
                                                      C.c_void_p(flag_hi or None), epoch, lo_early_rows, C.c_void_p(stream)))
+
+    def imfilter_slab_xy(self, img: b2f_array, out: b2f_array, stages: StageList, border: b2f_border,
+                         global_last_dim: int, slab_first: int, xy_lo: int, lo_halo: int, lo_own: int, xy_hi: int,
+                         hi_own: int, hi_halo: int, flag_lo: int = 0, flag_hi: int = 0, epoch: int = 0,
+                         lo_early_rows: int = 0, stream: int = 0):
+        xy = b2f_slab_xy(C.c_void_p(xy_lo or None), lo_halo, lo_own, C.c_void_p(xy_hi or None), hi_own, hi_halo)
+        self.check(self.dll.b2f_imfilter_slab_xy(C.byref(img), C.byref(out), stages.arr, stages.n, C.byref(border),
+                                                 global_last_dim, slab_first, C.byref(xy), C.c_void_p(flag_lo or None),
+                                                 C.c_void_p(flag_hi or None), epoch, lo_early_rows, C.c_void_p(stream)))
 
     def memcpy_async(self, dst: int, src: int, nbytes: int, stream: int = 0):
         self.check(self.dll.b2f_memcpy_async(C.c_void_p(dst), C.c_void_p(src), nbytes, C.c_void_p(stream)))

@@ -260,7 +260,7 @@ bool stream3d_applicable(const Plan &P, int img_dt, int out_dt);
 int run_stream3d(const Plan &P, const void *d_img, void *d_out, cudaStream_t st);
 int run_stream3d_slab(const Plan &P, const void *own, const void *lo, int64_t lo_n, const void *hi, int64_t hi_n,
                       int64_t own_first, int64_t own_n, void *d_out, cudaStream_t st, const void *flag_lo = nullptr,
-                      const void *flag_hi = nullptr, int epoch = 0, int lo_early_rows = 0);
+                      const void *flag_hi = nullptr, int epoch = 0, int lo_early_rows = 0, const b2f_slab_xy *xy = nullptr);
 // dense 2-D single stage (register-blocked FMA)
 bool dense2d_applicable(const Plan &P, int img_dt, int out_dt);
 int run_dense2d(const Plan &P, const void *d_img, int img_dt, void *d_out, int out_dt, cudaStream_t st);

@@ -263,9 +263,19 @@ using namespace b2f;
 static int imfilter_slab_impl(const b2f_array *img, const b2f_array *out, const b2f_stage *stages, int32_t nstages,
                               const b2f_border *border, int64_t global_last_dim, int64_t slab_first, const void *halo_lo,
                               int64_t n_halo_lo, const void *halo_hi, int64_t n_halo_hi, const void *flag_lo,
-                              const void *flag_hi, int32_t epoch, int32_t lo_early_rows, void *stream) {
+                              const void *flag_hi, int32_t epoch, int32_t lo_early_rows, void *stream,
+                              const b2f_slab_xy *xy = nullptr) {
     cudaStream_t st = (cudaStream_t)stream;
     if (!img || !out || !border || !stages) return fail(B2F_EARG, "NULL argument");
+    if (xy) {                                   // the halos are present as xy-filtered planes
+        if (xy->lo_halo < 0 || xy->lo_own < 0 || xy->hi_own < 0 || xy->hi_halo < 0) return fail(B2F_EARG, "negative plane count");
+        if ((xy->lo_halo + xy->lo_own > 0 && !xy->xy_lo) || (xy->hi_own + xy->hi_halo > 0 && !xy->xy_hi))
+            return fail(B2F_EARG, "NULL xy buffer");
+        n_halo_lo = xy->xy_lo ? xy->lo_halo : 0;
+        n_halo_hi = xy->xy_hi ? xy->hi_halo : 0;
+        halo_lo = n_halo_lo ? xy->xy_lo : nullptr;        // non-NULL placeholders for the checks below; never read as raw planes
+        halo_hi = n_halo_hi ? xy->xy_hi : nullptr;
+    }
     if (img->mem != B2F_DEVICE || out->mem != B2F_DEVICE) return fail(B2F_EARG, "b2f_imfilter_slab works on device arrays");
     const int N = img->ndim;
     if (N < 2 || N > B2F_MAXDIM || out->ndim != N) return fail(B2F_EDIM, "slab arrays need 2..4 dims and equal rank");
@@ -304,9 +314,11 @@ static int imfilter_slab_impl(const b2f_array *img, const b2f_array *out, const 
     rc = 0;
     if (stream3d_applicable(P, img->dtype, out->dtype)) {
         set_path("stream3d_slab");
+        if (xy && (xy->lo_own > own_n || xy->hi_own > own_n)) return fail(B2F_EDIM, "more xy-filtered own planes than the slab has");
         return run_stream3d_slab(P, img->ptr, halo_lo, n_halo_lo, halo_hi, n_halo_hi, slab_first, own_n, out->ptr, st, flag_lo, flag_hi,
-                                 epoch, lo_early_rows);
+                                 epoch, lo_early_rows, xy);
     }
+    if (xy) return fail(B2F_ENOTSUP, "xy-filtered halos are available for the fused Float32 3-D kernel only");
     if (flag_lo || flag_hi) {
         return fail(B2F_ENOTSUP, "staged halos are available for the fused Float32 3-D kernel only");
     }
@@ -360,6 +372,15 @@ int b2f_imfilter_slab_staged(const b2f_array *img, const b2f_array *out, const b
     if (epoch < 1 || epoch > 255) return fail(B2F_EARG, "epoch must be 1..255");
     return imfilter_slab_impl(img, out, stages, nstages, border, global_last_dim, slab_first, halo_lo, n_halo_lo, halo_hi,
                               n_halo_hi, flag_lo, flag_hi, epoch, lo_early_rows, stream);
+}
+
+int b2f_imfilter_slab_xy(const b2f_array *img, const b2f_array *out, const b2f_stage *stages, int32_t nstages,
+                         const b2f_border *border, int64_t global_last_dim, int64_t slab_first, const b2f_slab_xy *xy,
+                         const void *flag_lo, const void *flag_hi, int32_t epoch, int32_t lo_early_rows, void *stream) {
+    if (!xy) return fail(B2F_EARG, "NULL argument");
+    if ((flag_lo || flag_hi) && (epoch < 1 || epoch > 255)) return fail(B2F_EARG, "epoch must be 1..255");
+    return imfilter_slab_impl(img, out, stages, nstages, border, global_last_dim, slab_first, nullptr, 0, nullptr, 0, flag_lo, flag_hi,
+                              epoch, lo_early_rows, stream, xy);
 }
 
 int b2f_memcpy_async(void *dst, const void *src, uint64_t bytes, void *stream) {

@@ -115,8 +115,8 @@ static int s3_launch_one(S3Params &P, const float *kz, cudaStream_t st) {
     auto make_maps = [&](int rows) {
         memset(&m_own, 0, sizeof m_own); memset(&m_lo, 0, sizeof m_lo); memset(&m_hi, 0, sizeof m_hi);
         bool ok = tma_ok && s3_make_map(&m_own, P.own, P.W, P.H, P.own_n, rows);
-        if (ok && P.lo_n > 0) ok = s3_make_map(&m_lo, P.lo, P.W, P.H, P.lo_n, rows);
-        if (ok && P.hi_n > 0) ok = s3_make_map(&m_hi, P.hi, P.W, P.H, P.hi_n, rows);
+        if (ok && P.lo_n > 0 && P.lo) ok = s3_make_map(&m_lo, P.lo, P.W, P.H, P.lo_n, rows);
+        if (ok && P.hi_n > 0 && P.hi) ok = s3_make_map(&m_hi, P.hi, P.W, P.H, P.hi_n, rows);
         return ok;
     };
     // cp.async.bulk.tensor wants the box to start on a 16-byte boundary of the innermost axis (found the hard way:
@@ -124,8 +124,8 @@ static int s3_launch_one(S3Params &P, const float *kz, cudaStream_t st) {
     const int xsh_tma = ((P.klox % 4) + 4) % 4, SMS = sm_count();
     const bool tma = make_maps(C::RH);
     P.use_tma = tma ? 1 : 0;
-    if (!tma && (P.flag_lo || P.flag_hi))
-        return fail(B2F_ENOTSUP, "staged halos need the TMA path (row length a multiple of 4, 16-byte aligned buffers)");
+    if (!tma && (P.flag_lo || P.flag_hi || P.xy_lo || P.xy_hi))
+        return fail(B2F_ENOTSUP, "staged / xy-filtered halos need the TMA path (row length a multiple of 4, 16-byte aligned buffers)");
     P.xsh = tma ? xsh_tma : 0;
     if (int rc = s3_geometry(P, S3_TY, SMS)) return rc;
     const long long nblocks = P.nfull + ((long long)P.ntx * P.nty - P.nfull) * P.kch;
@@ -138,9 +138,16 @@ static int s3_launch_one(S3Params &P, const float *kz, cudaStream_t st) {
 // `own` holds planes [own_first, own_first+own_n) of a volume with Zg planes; lo/hi hold lo_n/hi_n planes below/above.
 int run_stream3d_slab(const Plan &Pl, const void *own, const void *lo, int64_t lo_n, const void *hi, int64_t hi_n,
                       int64_t own_first, int64_t own_n, void *d_out, cudaStream_t st, const void *flag_lo, const void *flag_hi,
-                      int epoch, int lo_early_rows) {
+                      int epoch, int lo_early_rows, const b2f_slab_xy *xy) {
     S3Params P;
     memset(&P, 0, sizeof P);
+    if (xy) {                                   // xy-filtered boundary planes: the halos exist as logical depths only
+        P.xy_lo = (const float *)xy->xy_lo; P.xlo_h = (int)xy->lo_halo; P.xlo_o = (int)xy->lo_own;
+        P.xy_hi = (const float *)xy->xy_hi; P.xhi_o = (int)xy->hi_own; P.xhi_h = (int)xy->hi_halo;
+        lo = hi = nullptr;
+        lo_n = xy->xy_lo ? xy->lo_halo : 0;
+        hi_n = xy->xy_hi ? xy->hi_halo : 0;
+    }
     P.flag_lo = lo_n > 0 ? (const unsigned char *)flag_lo : nullptr;
     P.flag_hi = hi_n > 0 ? (const unsigned char *)flag_hi : nullptr;
     P.epoch = epoch;
@@ -165,7 +172,7 @@ int run_stream3d_slab(const Plan &Pl, const void *own, const void *lo, int64_t l
     for (int j = 1; j < P.Ly; ++j) P.kyp[j] = make_float2(P.ky[j], P.ky[j - 1]);
     for (int j = 0; j < P.Lz; ++j) kz[j] = (float)sz.s->taps[j];
     auto al16 = [](const void *p) { return reinterpret_cast<uintptr_t>(p) % 16 == 0; };
-    P.use_tma = (P.W % 4 == 0) && al16(own) && (lo_n == 0 || al16(lo)) && (hi_n == 0 || al16(hi));
+    P.use_tma = (P.W % 4 == 0) && al16(own) && (lo_n == 0 || !lo || al16(lo)) && (hi_n == 0 || !hi || al16(hi));
     P.vec_out = (P.W % 2 == 0) && reinterpret_cast<uintptr_t>(d_out) % 8 == 0;
     if (P.Lx == 17 && P.Ly == 17 && P.Lz == 17) return s3_launch_one<17, 17, 17>(P, kz, st);
     if (P.Lx == 9 && P.Ly == 9 && P.Lz == 9) return s3_launch_one<9, 9, 9>(P, kz, st);

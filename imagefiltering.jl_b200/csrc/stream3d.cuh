@@ -68,6 +68,12 @@ struct S3Params {
     // buffer is complete (NULL: the planes are there already)
     const unsigned char *flag_lo, *flag_hi;   // flag_lo[0]: rows [0, lo_early_rows) of every lower halo plane, flag_lo[1]: the rest
     int epoch, lo_early_rows;
+    // xy-filtered boundary planes (multi-GPU): planes whose stages x and y were run ahead of this launch (this rank's own
+    // boundary planes, and the neighbours' through the exchange) — the march reads them in the z stage only.  xy_lo holds the
+    // source planes [own_first - xlo_h, own_first + xlo_o), xy_hi the planes [own_first + own_n - xhi_o, own_first + own_n + xhi_h);
+    // with them set, lo_n / hi_n only give the logical depth of the halos (lo / hi are not read).
+    const float *xy_lo, *xy_hi;
+    int xlo_h, xlo_o, xhi_o, xhi_h;
     int use_tma;                   // the tensor maps are valid (else every cell comes through the gather loader)
     float kx[S3_MAXTAPS], ky[S3_MAXTAPS];
     float kzr[S3_MAXTAPS];         // z taps RIGHT-aligned in the instantiation's LBZ slots

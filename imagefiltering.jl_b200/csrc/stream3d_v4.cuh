@@ -179,7 +179,14 @@ stream3d_kernel4(const __grid_constant__ S3Params P, const __grid_constant__ S3V
         if (tid < n) {
             const int p = p0 + tid;
             int which = -1, zz = 0;
-            if (p >= 0 && p < in_planes) s3_locate(P, zin0 + p, which, zz);
+            if (p >= 0 && p < in_planes) {
+                s3_locate(P, zin0 + p, which, zz);
+                // xy-filtered boundary planes (multi-GPU, see S3Params::xy_lo): 4 = a plane of xy_lo, 5 = a plane of xy_hi
+                if (which == 1 && P.xy_lo) { which = 4; }
+                else if (which == 2 && P.xy_hi) { which = 5; zz += P.xhi_o; }
+                else if (which == 0 && P.xy_lo && zz < P.xlo_o) { which = 4; zz += P.xlo_h; }
+                else if (which == 0 && P.xy_hi && zz >= P.own_n - P.xhi_o) { which = 5; zz -= P.own_n - P.xhi_o; }
+            }
             ptw[p & (S3_PT - 1)] = which;
             ptz[p & (S3_PT - 1)] = zz;
         }
@@ -200,6 +207,13 @@ stream3d_kernel4(const __grid_constant__ S3Params P, const __grid_constant__ S3V
     };
     auto issue = [&](int p) {                   // one thread: TMA of input plane p into its ring buffer
         const int which = ptw[p & (S3_PT - 1)];
+        if (which >= 4) {                       // xy-filtered plane: no TMA; a neighbour's plane may still be on its way
+            const int zq = ptz[p & (S3_PT - 1)];
+            if (which == 4 && zq < P.xlo_h && !lo_ready) { wait_flag(P.flag_lo + (y0 + TY > P.lo_early_rows ? 1 : 0)); lo_ready = true; }
+            if (which == 5 && zq >= P.xhi_o && !hi_ready) { wait_flag(P.flag_hi); hi_ready = true; }
+            s3_mbar_arrive(full + 8 * (p & (N - 1)));          // its ring slot still completes a phase: the parities stay in step
+            return;
+        }
         if (which == 1 && !lo_ready) { wait_flag(P.flag_lo + (ya + in_rows > P.lo_early_rows ? 1 : 0)); lo_ready = true; }
         if (which == 2 && !hi_ready) { wait_flag(P.flag_hi); hi_ready = true; }
         const int zz = which < 0 ? P.own_n : ptz[p & (S3_PT - 1)];         // Fill(0) plane: out of range reads zero
@@ -242,13 +256,21 @@ stream3d_kernel4(const __grid_constant__ S3Params P, const __grid_constant__ S3V
     // stage x reads them and its next barrier arrival publishes that to the CTA (the other warps never touch the TMA
     // barriers: one try_wait latency less per warp-task).  Border tiles patch planes 0 .. 3 before the first stage x.
     auto landed = [&](int p) { s3_mbar_wait(full + 8 * (p & (N - 1)), (p / N) & 1); };
+    const bool xy = P.xy_lo != nullptr || P.xy_hi != nullptr;
+    auto is_pre = [&](int p) { return xy && ptw[p & (S3_PT - 1)] >= 4; };       // valid for the planes of the current table window
     if (tma && tid == 0) {
         for (int p = 0; p < min(N, in_planes); ++p) issue(p);
-        for (int p = 0; p < min(4, in_planes); ++p) landed(p);
+        for (int p = 0; p < min(4, in_planes); ++p)
+            if (!is_pre(p)) landed(p);
     }
+    auto patch_planes = [&](const int p, const int n) {             // like patch2, minus xy-filtered planes
+        if (!xy) { patch2(p, n); return; }
+        for (int k = 0; k < n; ++k)
+            if (!is_pre(p + k)) patch2(p + k, 1);
+    };
     if (fix) {                                  // planes 0 .. 3; step s patches planes 2s+6, 2s+7
-        patch2(0, min(2, in_planes));
-        if (in_planes > 2) patch2(2, min(2, in_planes - 2));
+        patch_planes(0, min(2, in_planes));
+        if (in_planes > 2) patch_planes(2, min(2, in_planes - 2));
     }
     __syncthreads();
 
@@ -315,7 +337,7 @@ stream3d_kernel4(const __grid_constant__ S3Params P, const __grid_constant__ S3V
                 const int p = p0 + N + d;
                 if (all || (p0 >= 0 && p < in_planes)) {
                     const int rel = zin0 + p - P.own_first;
-                    if ((unsigned)rel < (unsigned)P.own_n) {                     // an owned plane: no table, no flag
+                    if ((all || !xy) && (unsigned)rel < (unsigned)P.own_n) {     // an owned plane: no table, no flag
                         const int b = p & (N - 1);
                         s3_mbar_expect_tx(full + 8 * b, (unsigned)C::RAWBYTES);
                         s3_tma_load3d(raw_sa + b * (RAWSZ * 4), &m_own, full + 8 * b, xa, ya, rel);
@@ -333,7 +355,7 @@ stream3d_kernel4(const __grid_constant__ S3Params P, const __grid_constant__ S3V
 #pragma unroll
             for (int d = 0; d < 2; ++d) {
                 const int p = p0 + 4 + d;
-                if (all || p < in_planes) landed(p);
+                if (all || (p < in_planes && !is_pre(p))) landed(p);
             }
         }
     };
@@ -344,22 +366,36 @@ stream3d_kernel4(const __grid_constant__ S3Params P, const __grid_constant__ S3V
         if (((p0 + 2) & (S3_PTB - 1)) == 0) locate_block(p0 + S3_PTA, S3_PTB);
         if (s >= 0 && !ok) s3_mbar_wait(xfull + 8 * bi, ph);
         ok = false;
-        stage_x(p0 + 2, p0 + 2 < in_planes, p0 + 3 < in_planes);
+        stage_x(p0 + 2, p0 + 2 < in_planes && !is_pre(p0 + 2), p0 + 3 < in_planes && !is_pre(p0 + 3));
         tma_check(p0, false);
         arrive_next();
         tma_work(p0, false);
         // border cells of the planes stage x reads TWO steps from now: behind the arrival, off the hand-off's critical path
         // (the next step's arrival publishes them)
-        if (fix && p0 + 6 < in_planes) patch2(p0 + 6, min(2, in_planes - (p0 + 6)));
+        if (fix && p0 + 6 < in_planes) patch_planes(p0 + 6, min(2, in_planes - (p0 + 6)));
         if (s >= 0) {
             const int o = p0 - (Lz - 1);
             float2 ma[2], mb[2];
             const unsigned xa0 = xf_sa + (2 * bi * XFSZ + yoff) * 4;
-            if (p0 + 1 < in_planes) {
+            const bool pre_a = is_pre(p0), pre_b = p0 + 1 < in_planes && is_pre(p0 + 1);
+            // an xy-filtered plane skips stages x and y: its values come straight from the xy buffer (L2, not L1: another
+            // GPU's copy engine may have written them while this kernel was running)
+            auto pre_load = [&](const int p, float2 (&m)[2]) {
+                const float *b = (ptw[p & (S3_PT - 1)] == 4 ? P.xy_lo : P.xy_hi) + (long long)ptz[p & (S3_PT - 1)] * P.plane +
+                                 (long long)gy * P.W + gx;
+                float v[4];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) v[r] = r < nrow ? __ldcg(b + (long long)r * P.W) : 0.f;
+                m[0] = make_float2(v[0], v[1]);
+                m[1] = make_float2(v[2], v[3]);
+            };
+            if (!pre_a && p0 + 1 < in_planes && !pre_b) {
                 s3v_y_task4x2<LXT, LYT, LZT>(P, xa0, xa0 + XFSZ * 4, ma, mb, Ly);
             } else {
-                s3_y_task4<LXT, LYT, LZT>(P, xa0, ma, Ly);
-                mb[0] = mb[1] = make_float2(0.f, 0.f);
+                if (pre_a) pre_load(p0, ma); else s3_y_task4<LXT, LYT, LZT>(P, xa0, ma, Ly);
+                if (p0 + 1 >= in_planes) mb[0] = mb[1] = make_float2(0.f, 0.f);
+                else if (pre_b) pre_load(p0 + 1, mb);
+                else s3_y_task4<LXT, LYT, LZT>(P, xa0 + XFSZ * 4, mb, Ly);
             }
             const float m0[4] = {ma[0].x, ma[0].y, ma[1].x, ma[1].y}, m1[4] = {mb[0].x, mb[0].y, mb[1].x, mb[1].y};
             s4_z_step<LXT, LYT, LZT, CS, false>(P, TZ, acc, m0, m1, Lz, op, nrow, false, o >= 0 && o < nout && nrow > 0,
@@ -394,6 +430,13 @@ stream3d_kernel4(const __grid_constant__ S3Params P, const __grid_constant__ S3V
     if (tma && nout + Lz - 3 >= 0 && in_planes - N - 2 >= 0) {
         s_fast0 = min(Lz >> 1, nsteps);                                      // ceil((Lz-1)/2)
         s_fast1 = max(s_fast0, min(min((nout + Lz - 3) / 2 + 1, (in_planes - N - 2) / 2 + 1), nsteps));
+        if (xy) {                               // a steady-state step touches planes 2s .. 2s+N+1: all of them must be raw own planes
+            const int ra = max(0, P.own_first + (P.xy_lo ? P.xlo_o : 0) - zin0);
+            const int rb = min(in_planes, P.own_first + P.own_n - (P.xy_hi ? P.xhi_o : 0) - zin0);
+            s_fast0 = min(max(s_fast0, (ra + 1) >> 1), nsteps);
+            s_fast1 = max(s_fast0, min(s_fast1, (rb - N - 2) / 2 + 1));
+            if (rb - N - 2 < 0) s_fast1 = s_fast0;
+        }
     }
     int s = -1;
     for (; s < s_fast0; ++s) slow_step(s);

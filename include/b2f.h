@@ -248,6 +248,31 @@ int b2f_imfilter_slab_staged(const b2f_array *img, const b2f_array *out,
                              const void *halo_hi, int64_t n_halo_hi,
                              const void *flag_lo, const void *flag_hi, int32_t epoch, int32_t lo_early_rows,
                              void *stream);
+/* xy-filtered form of the staged slab call (what b2f_imfilter_sharded uses on the fused Float32 3-D path): instead of RAW halo
+ * planes the ranks exchange boundary planes that have already been filtered along every axis but the last — a rank runs
+ * b2f_imfilter with the stages of the other axes over its own first / last boundary planes before the pass, the neighbours copy
+ * them, and the march of the fused kernel reads both its own boundary planes and the neighbours' in its last-axis stage only.
+ * No rank filters a halo plane a second time (with raw halos a slab of n planes pays for n + h_lo + h_hi planes of the other
+ * stages) and the result is bit-identical to the unsharded call.
+ *   xy_lo: lo_halo + lo_own planes = the planes [slab_first - lo_halo, slab_first + lo_own) of the array, filtered;
+ *   xy_hi: hi_own + hi_halo planes = the planes [slab_first + own - hi_own, slab_first + own + hi_halo).
+ * lo_halo / hi_halo = 0 at a global face (the border style is applied there in global plane coordinates).  The halo parts may
+ * still be on their way: flag_lo[0] / flag_lo[1] / flag_hi, epoch and lo_early_rows as in b2f_imfilter_slab_staged (NULL flags:
+ * the planes are there).  Fused Float32 3-D path with TMA only (B2F_ENOTSUP otherwise: use the raw-halo forms). */
+typedef struct b2f_slab_xy {
+    const void *xy_lo;
+    int64_t lo_halo, lo_own;
+    const void *xy_hi;
+    int64_t hi_own, hi_halo;
+} b2f_slab_xy;
+int b2f_imfilter_slab_xy(const b2f_array *img, const b2f_array *out,
+                         const b2f_stage *stages, int32_t nstages,
+                         const b2f_border *border,
+                         int64_t global_last_dim, int64_t slab_first,
+                         const b2f_slab_xy *xy,
+                         const void *flag_lo, const void *flag_hi, int32_t epoch, int32_t lo_early_rows,
+                         void *stream);
+
 /* ---- the sharded driver: one rank per GPU, slabs along the last axis ---------------------------------------
  * b2f_imfilter_sharded is b2f_imfilter for ONE RANK's slab of an array partitioned over `world` GPUs of a node: the
  * result equals this rank's planes of the filter applied to the whole array.  Per pass the library performs the neighbour

@@ -1233,6 +1233,10 @@ int b2f_imfilter_slab_staged(const b2f_array *, const b2f_array *, const b2f_sta
                              const void *, int64_t, const void *, int64_t, const void *, const void *, int32_t, int32_t, void *) {
     return fail(B2F_ENOTSUP, "oracle library has no copy engines: use b2f_imfilter_slab");
 }
+int b2f_imfilter_slab_xy(const b2f_array *, const b2f_array *, const b2f_stage *, int32_t, const b2f_border *, int64_t, int64_t,
+                         const b2f_slab_xy *, const void *, const void *, int32_t, int32_t, void *) {
+    return fail(B2F_ENOTSUP, "oracle library: the xy-filtered halo form belongs to the fused device kernel; use b2f_imfilter_slab");
+}
 int b2f_shard_ctx_create(b2f_shard_ctx **, int32_t, int32_t) { return fail(B2F_ENOTSUP, "oracle library has no device memory"); }
 int b2f_shard_ctx_export(b2f_shard_ctx *, const void *, int64_t, void *) { return fail(B2F_ENOTSUP, "oracle library has no device memory"); }
 int b2f_shard_ctx_connect(b2f_shard_ctx *, const void *, const void *) { return fail(B2F_ENOTSUP, "oracle library has no device memory"); }

@@ -432,6 +432,52 @@ def test_slab_form_matches_whole_volume(ifb, oracle, device, border, T):
                              b.to_abi(3), Z, 17, hlo.data_ptr(), 2, hhi.data_ptr(), 2)
 
 
+@pytest.mark.parametrize("border", ["symmetric", "replicate", "reflect", "circular", "fill"])
+@pytest.mark.parametrize("sigma", [4, 2, 1])
+def test_slab_xy_form_matches_whole_volume(ifb, oracle, device, border, sigma):
+    """b2f_imfilter_slab_xy on ONE device: three slabs, each handed its own and its neighbours' boundary planes ALREADY filtered
+    along x and y (what the sharded driver exchanges instead of raw halos).  The result must equal the unsharded fused kernel
+    bit for bit (the march only skips stages whose results it is given) and the oracle within the Float32 tolerance.  sigma
+    4 / 2 / 1 = 17 / 9 / 5 taps = halos of 8 / 4 / 2 planes (even and odd numbers of skipped planes per ring slot)."""
+    import torch
+    from importlib import import_module
+    imf = import_module("imagefiltering_jl_b200.imfilter")
+    rng = np.random.default_rng(91 + sigma)
+    X, Y, Z = 64, 96, 60
+    vol = np.asfortranarray(rng.random((X, Y, Z)).astype(np.float32))
+    kf = ifb.KernelFactors.gaussian((sigma, sigma, sigma))
+    h = 2 * sigma
+    b = ifb.Fill(0.0) if border == "fill" else ifb.Pad(border)
+    ref = ifb.imfilter(np.float32, vol, kf, b, _library=oracle)
+    t_vol = torch.from_numpy(np.ascontiguousarray(vol.transpose(2, 1, 0))).cuda()
+    st = ifb._abi.StageList(imf.build_stages(kf, 3))
+    st_xy = ifb._abi.StageList(imf.build_stages(kf[:2], 3))
+    DA = ifb.DeviceArray
+    whole, t_xy = torch.empty_like(t_vol), torch.empty_like(t_vol)
+    device.imfilter(DA.from_torch(t_vol).desc(), DA.from_torch(whole).desc(), st, b.to_abi(3), None, 0)
+    assert device.last_path() == "stream3d"
+    device.imfilter(DA.from_torch(t_vol).desc(), DA.from_torch(t_xy).desc(), st_xy, b.to_abi(3), None, 0)
+    out = torch.empty_like(t_vol)
+    bounds = [0, 17, 41, Z]
+    circ = border == "circular"
+    for i in range(3):
+        z0, z1 = bounds[i], bounds[i + 1]
+        lo = h if (i > 0 or circ) else 0
+        hi = h if (i < 2 or circ) else 0
+        own = t_vol[z0:z1].contiguous()
+        xy_lo = t_xy[[(z % Z) for z in range(z0 - lo, z0 + h)]].contiguous()
+        xy_hi = t_xy[[(z % Z) for z in range(z1 - h, z1 + hi)]].contiguous()
+        o = torch.empty_like(own)
+        device.imfilter_slab_xy(DA.from_torch(own).desc(), DA.from_torch(o).desc(), st, b.to_abi(3), Z, z0,
+                                xy_lo.data_ptr(), lo, h, xy_hi.data_ptr(), h, hi)
+        assert device.last_path() == "stream3d_slab"
+        out[z0:z1] = o
+    torch.cuda.synchronize()
+    assert torch.equal(out, whole)
+    got = out.cpu().numpy().transpose(2, 1, 0)
+    assert np.max(np.abs(got.astype(np.float64) - ref.astype(np.float64))) <= 1e-5
+
+
 @pytest.mark.parametrize("border", BORDERS + ["fill"])
 def test_stream3d_parity(ifb, oracle, device, border, monkeypatch):
     """Fused 3-D separable kernel (BASELINE config 5 in miniature): exact 17^3 / 9^3 / 5^3 / 3^3 instantiations and
