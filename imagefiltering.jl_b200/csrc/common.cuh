@@ -257,6 +257,7 @@ bool sepnd_applicable(const Plan &P, int img_dt, int out_dt);
 int run_sepnd(const Plan &P, const void *d_img, int img_dt, void *d_out, int out_dt, cudaStream_t st);
 // fused 3-D separable cascade (x, y, z in one launch; Float32), also in slab form (planes in own/lo/hi buffers)
 bool stream3d_applicable(const Plan &P, int img_dt, int out_dt);
+bool stream3d_xy_capable(const Plan &P);          // ... and every slab of it can take xy-filtered boundary planes (TMA path)
 int run_stream3d(const Plan &P, const void *d_img, void *d_out, cudaStream_t st);
 int run_stream3d_slab(const Plan &P, const void *own, const void *lo, int64_t lo_n, const void *hi, int64_t hi_n,
                       int64_t own_first, int64_t own_n, void *d_out, cudaStream_t st, const void *flag_lo = nullptr,

@@ -15,7 +15,10 @@
 // plane count) which the CALLER moves between ranks with whatever it has — MPI, Distributed.jl, a file, torch.distributed:
 // the library itself has no communication dependency.  Arrays other than Float32 3-D volumes on the fused kernel, or
 // volumes the TMA path cannot take, run the same sequence with direct peer reads (b2f_imfilter_slab) after the hand-shake.
+#include <cstdlib>
 #include <cstring>
+#include <vector>
+#include <algorithm>
 
 #include "common.cuh"
 
@@ -56,7 +59,22 @@ struct ShardCtx {
     uint32_t step = 0;
     int epoch = 0;
     bool staged_ok = true;
+    // xy-filtered exchange (fused Float32 3-D path): two parity blocks of [h_lo halo | h_hi own | h_lo own | h_hi halo] planes;
+    // the neighbours map the whole allocation (its IPC handle travels through the hand-shake buffer, see xy_setup)
+    bool xy_ok = true;
+    void *xy = nullptr;
+    size_t xy_bytes = 0, xy_plane_bytes = 0;
+    int64_t xy_hlo = 0, xy_hhi = 0;
+    void *lower_xy = nullptr, *upper_xy = nullptr;
+    uint64_t lower_xy_off = 0, upper_xy_off = 0;
+    uint32_t xy_calls = 0;
 };
+
+struct XyPublish {                       // at byte 64 of the hand-shake buffer
+    unsigned char handle[64];
+    uint64_t off, bytes;
+};
+constexpr size_t SYNC_BYTES = 256;
 
 }  // namespace b2f
 
@@ -71,8 +89,8 @@ int b2f_shard_ctx_create(b2f_shard_ctx **ctx, int32_t rank, int32_t world) {
     b2f_shard_ctx *p = new b2f_shard_ctx();
     p->c.rank = rank;
     p->c.world = world;
-    cudaError_t e = cudaMalloc((void **)&p->c.sync, 8);
-    if (e == cudaSuccess) e = cudaMemset(p->c.sync, 0, 8);
+    cudaError_t e = cudaMalloc((void **)&p->c.sync, SYNC_BYTES);
+    if (e == cudaSuccess) e = cudaMemset(p->c.sync, 0, SYNC_BYTES);
     if (e == cudaSuccess) e = cudaMalloc((void **)&p->c.flags, 4);
     if (e == cudaSuccess) e = cudaMemset(p->c.flags, 0, 4);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->c.side, cudaStreamNonBlocking);
@@ -147,6 +165,9 @@ int b2f_shard_ctx_destroy(b2f_shard_ctx *ctx) {
     cudaDeviceSynchronize();
     if (c.has_lower) { b2f_ipc_close(c.lower_slab, c.lower_slab_off); b2f_ipc_close(c.lower_sync, c.lower_sync_off); }
     if (c.has_upper && !c.same_peer) { b2f_ipc_close(c.upper_slab, c.upper_slab_off); b2f_ipc_close(c.upper_sync, c.upper_sync_off); }
+    if (c.lower_xy) b2f_ipc_close(c.lower_xy, c.lower_xy_off);
+    if (c.upper_xy && !c.same_peer) b2f_ipc_close(c.upper_xy, c.upper_xy_off);
+    if (c.xy) cudaFree(c.xy);
     if (c.recv_lo) cudaFree(c.recv_lo);
     if (c.recv_hi) cudaFree(c.recv_hi);
     if (c.sync) cudaFree(c.sync);
@@ -168,6 +189,117 @@ int b2f_shard_handshake(b2f_shard_ctx *ctx, void *stream) {
     if (c.has_upper && !rc) rc = b2f_stream_write32((char *)c.upper_sync, c.step, stream);         // I am its lower neighbour
     if (c.has_lower && !rc) rc = b2f_stream_wait_geq32(c.sync, c.step, stream);
     if (c.has_upper && !rc) rc = b2f_stream_wait_geq32(c.sync + 1, c.step, stream);
+    return rc;
+}
+
+// (Re)allocate the xy exchange buffer and map the neighbours' — collective over the neighbours: every rank reaches it in the
+// same call (same kernel, same plane size).  The IPC handle is published in this rank's hand-shake buffer, which the
+// neighbours have mapped since connect; a hand-shake orders "published" before "read".
+static int xy_setup(b2f_shard_ctx *ctx, size_t plane_bytes, int64_t h_lo, int64_t h_hi, void *stream) {
+    ShardCtx &c = ctx->c;
+    const size_t need = 2 * (size_t)(2 * (h_lo + h_hi)) * plane_bytes;
+    if (c.xy && c.xy_bytes == need && c.xy_plane_bytes == plane_bytes && c.xy_hlo == h_lo && c.xy_hhi == h_hi) return 0;
+    B2F_CUDA(cudaDeviceSynchronize());
+    if (c.lower_xy) { b2f_ipc_close(c.lower_xy, c.lower_xy_off); c.lower_xy = nullptr; }
+    if (c.upper_xy) { if (!c.same_peer) b2f_ipc_close(c.upper_xy, c.upper_xy_off); c.upper_xy = nullptr; }
+    if (c.xy) { cudaFree(c.xy); c.xy = nullptr; }
+    B2F_CUDA(cudaMalloc(&c.xy, need));
+    B2F_CUDA(cudaMemset(c.xy, 0, need));
+    c.xy_bytes = need; c.xy_plane_bytes = plane_bytes; c.xy_hlo = h_lo; c.xy_hhi = h_hi;
+    XyPublish pub;
+    memset(&pub, 0, sizeof pub);
+    int rc = b2f_ipc_export(c.xy, pub.handle, &pub.off);
+    if (rc) return rc;
+    pub.bytes = need;
+    B2F_CUDA(cudaMemcpy((char *)c.sync + 64, &pub, sizeof pub, cudaMemcpyHostToDevice));
+    B2F_CUDA(cudaDeviceSynchronize());
+    rc = b2f_shard_handshake(ctx, stream);
+    if (rc) return rc;
+    B2F_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    auto open_peer = [&](void *peer_sync, void **xy, uint64_t *off) -> int {
+        XyPublish q;
+        B2F_CUDA(cudaMemcpy(&q, (char *)peer_sync + 64, sizeof q, cudaMemcpyDeviceToHost));
+        if (q.bytes != need) return fail(B2F_EDIM, "the neighbour's xy exchange buffer has a different size (different kernel or plane size?)");
+        *off = q.off;
+        return b2f_ipc_open(q.handle, q.off, xy);
+    };
+    if (c.has_lower && (rc = open_peer(c.lower_sync, &c.lower_xy, &c.lower_xy_off))) return rc;
+    if (c.has_upper) {
+        if (c.same_peer) { c.upper_xy = c.lower_xy; c.upper_xy_off = c.lower_xy_off; }
+        else if ((rc = open_peer(c.upper_sync, &c.upper_xy, &c.upper_xy_off))) return rc;
+    }
+    return 0;
+}
+
+// One pass with xy-filtered boundary planes (include/b2f.h, b2f_imfilter_slab_xy): filter my first h_hi and last h_lo planes
+// along x and y, hand-shake, let the copy engines pull the neighbours' while the march is already running.
+static int sharded_xy(b2f_shard_ctx *ctx, const b2f_array *img, const b2f_array *out, const b2f_stage *stages, int32_t nstages,
+                      const b2f_border *border, int64_t global_last_dim, int64_t slab_first, int64_t h_lo, int64_t h_hi,
+                      bool use_lo, bool use_hi, void *stream) {
+    ShardCtx &c = ctx->c;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t W = img->dims[0], H = img->dims[1], own_n = img->dims[2];
+    const size_t plane_bytes = (size_t)W * H * 4, row_bytes = (size_t)W * 4;
+    int rc = xy_setup(ctx, plane_bytes, h_lo, h_hi, stream);
+    if (rc) return rc;
+    const int64_t block = 2 * (h_lo + h_hi);                  // planes of one parity block: [h_lo | h_hi | h_lo | h_hi]
+    const int q = (int)(c.xy_calls++ & 1);
+    char *mine = (char *)c.xy + (size_t)q * block * plane_bytes;
+    char *lo_halo = mine, *lo_own = mine + (size_t)h_lo * plane_bytes, *hi_own = lo_own + (size_t)h_hi * plane_bytes,
+         *hi_halo = hi_own + (size_t)h_lo * plane_bytes;
+    // 1. stages of the other axes over my boundary planes (the lower neighbour needs my first h_hi planes, the upper one my last h_lo)
+    std::vector<b2f_stage> sxy;
+    for (int i = 0; i < nstages; ++i)
+        if (!(stages[i].kind == B2F_STAGE_1D && stages[i].axis == 2)) sxy.push_back(stages[i]);
+    auto prefilter = [&](int64_t first, int64_t n, char *dst) -> int {
+        if (n <= 0) return 0;
+        b2f_array a = *img, o = *out;
+        a.ptr = (char *)img->ptr + (size_t)first * plane_bytes;
+        o.ptr = dst;
+        a.dims[2] = o.dims[2] = n;
+        return b2f_imfilter(&a, &o, sxy.data(), (int32_t)sxy.size(), border, nullptr, nullptr, stream);
+    };
+    const int64_t n_lo_own = std::min<int64_t>(h_hi, own_n), n_hi_own = std::min<int64_t>(h_lo, own_n);
+    if ((rc = prefilter(0, n_lo_own, lo_own))) return rc;
+    if ((rc = prefilter(own_n - n_hi_own, n_hi_own, hi_own))) return rc;
+    // 2. the neighbours' boundary planes are filtered (and their previous pass no longer reads my other parity block)
+    if ((rc = b2f_shard_handshake(ctx, stream))) return rc;
+    // 3. copy engines: the rows of the lower halo the first wave of tiles reads, the upper halo, the rest of the lower halo
+    c.epoch = c.epoch % 255 + 1;
+    B2F_CUDA(cudaEventRecord(c.ev_go, st));
+    B2F_CUDA(cudaStreamWaitEvent(c.side, c.ev_go, 0));
+    const char *peer_lo = use_lo ? (const char *)c.lower_xy + (size_t)q * block * plane_bytes + (size_t)(h_lo + h_hi) * plane_bytes : nullptr;
+    const char *peer_hi = use_hi ? (const char *)c.upper_xy + (size_t)q * block * plane_bytes + (size_t)h_lo * plane_bytes : nullptr;
+    int64_t early = 0;
+    if (use_lo) {
+        const int64_t tiles_x = (W + 31) / 32;
+        early = ((sm_count() + tiles_x - 1) / tiles_x + 1) * 64;
+        if (early >= H) early = 0;
+    }
+    if (use_lo && early) {
+        B2F_CUDA(cudaMemcpy2DAsync(lo_halo, plane_bytes, peer_lo, plane_bytes, (size_t)early * row_bytes, (size_t)h_lo, cudaMemcpyDefault, c.side));
+        B2F_CUDA(cudaMemsetAsync(c.flags, c.epoch, 1, c.side));
+    }
+    if (use_hi) {
+        B2F_CUDA(cudaMemcpyAsync(hi_halo, peer_hi, (size_t)h_hi * plane_bytes, cudaMemcpyDefault, c.side));
+        B2F_CUDA(cudaMemsetAsync(c.flags + 2, c.epoch, 1, c.side));
+    }
+    if (use_lo) {
+        if (early)
+            B2F_CUDA(cudaMemcpy2DAsync(lo_halo + (size_t)early * row_bytes, plane_bytes, peer_lo + (size_t)early * row_bytes, plane_bytes,
+                                       (size_t)(H - early) * row_bytes, (size_t)h_lo, cudaMemcpyDefault, c.side));
+        else
+            B2F_CUDA(cudaMemcpyAsync(lo_halo, peer_lo, (size_t)h_lo * plane_bytes, cudaMemcpyDefault, c.side));
+        B2F_CUDA(cudaMemsetAsync(c.flags + 1, c.epoch, 1, c.side));
+    }
+    B2F_CUDA(cudaEventRecord(c.ev_done, c.side));
+    // 4. the march
+    b2f_slab_xy xy;
+    xy.xy_lo = use_lo ? lo_halo : lo_own;  xy.lo_halo = use_lo ? h_lo : 0;  xy.lo_own = n_lo_own;
+    xy.xy_hi = hi_own;                     xy.hi_own = n_hi_own;            xy.hi_halo = use_hi ? h_hi : 0;
+    rc = b2f_imfilter_slab_xy(img, out, stages, nstages, border, global_last_dim, slab_first, &xy, use_lo ? c.flags : nullptr,
+                              use_hi ? c.flags + 2 : nullptr, c.epoch, (int32_t)early, stream);
+    B2F_CUDA(cudaStreamWaitEvent(st, c.ev_done, 0));
     return rc;
 }
 
@@ -199,6 +331,23 @@ int b2f_imfilter_sharded(b2f_shard_ctx *ctx, const b2f_array *img, const b2f_arr
     const char *peer_lo = use_lo ? (const char *)c.lower_slab + (size_t)(c.lower_planes - h_lo) * plane_bytes : nullptr;
     const char *peer_hi = use_hi ? (const char *)c.upper_slab : nullptr;
 
+    // fused Float32 3-D kernel: exchange xy-filtered boundary planes (B2F_SHARD_XY=0: raw halos, for A/B runs).  The decision
+    // depends on the kernel and the plane shape only, so every rank of the pass takes the same branch.
+    static const bool xy_env = !(getenv("B2F_SHARD_XY") && atoi(getenv("B2F_SHARD_XY")) == 0);
+    if (xy_env && c.xy_ok && (use_lo || use_hi) && nd == 3 && img->dtype == B2F_F32 && out->dtype == B2F_F32) {
+        b2f_array gi = *img, go = *out;
+        gi.dims[2] = go.dims[2] = global_last_dim;
+        gi.ptr = go.ptr = nullptr;
+        Plan P;
+        if (make_plan(&gi, &go, stages, nstages, border, nullptr, nullptr, P) == 0 && !P.img_ax.empty() && stream3d_xy_capable(P)) {
+            int rc = sharded_xy(ctx, img, out, stages, nstages, border, global_last_dim, slab_first, h_lo, h_hi, use_lo, use_hi, stream);
+            if (rc != B2F_ENOTSUP) return rc;
+            // this rank's slab cannot take the TMA path (alignment): it has published its planes like everybody else and reads
+            // the neighbours' RAW planes itself (their slabs are complete: the hand-shake is behind us)
+            return b2f_imfilter_slab(img, out, stages, nstages, border, global_last_dim, slab_first, peer_lo, use_lo ? h_lo : 0, peer_hi,
+                                     use_hi ? h_hi : 0, stream);
+        }
+    }
     int rc = b2f_shard_handshake(ctx, stream);
     if (rc) return rc;
     if (!use_lo && !use_hi)

@@ -25,6 +25,15 @@ bool stream3d_applicable(const Plan &P, int img_dt, int out_dt) {
     return true;
 }
 
+// the shape conditions of the TMA path, which the xy-filtered slab form needs (pointer alignment is the caller's: cudaMalloc'ed
+// slabs qualify)
+bool stream3d_xy_capable(const Plan &P) {
+    if (!stream3d_applicable(P, B2F_F32, B2F_F32)) return false;
+    const long long W = P.img_ax.len(0), H = P.img_ax.len(1);
+    if (W % 4 != 0 || W < S3_RWP || H < S3_TY + S3_MAXTAPS - 1) return false;
+    return P.style != B2F_FILL || (float)P.fill == 0.0f;
+}
+
 // cuTensorMapEncodeTiled through the runtime (no link-time dependency on libcuda)
 typedef CUresult (*s3_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,

@@ -27,6 +27,8 @@ def cases(ifb):
     out.append(("f32-3d-17taps", np.float32, (70, 45, 40), g((4, 4, 4)), "symmetric", None))
     out.append(("f32-3d-tma", np.float32, (64, 80, 37), g((2, 2, 2)), "reflect", None))        # wide enough for the TMA / staged path
     out.append(("f32-3d-tma17", np.float32, (128, 96, 48), g((4, 4, 4)), "circular", None))
+    out.append(("f32-3d-tma17-sym", np.float32, (64, 96, 40), g((4, 4, 4)), "symmetric", None))   # xy-filtered exchange at the faces
+    out.append(("f32-3d-tma5-fill0", np.float32, (64, 88, 30), g((1, 1, 1)), ifb.Fill(0.0), None))
     out.append(("f32-2d", np.float32, (33, 29), g((1, 2)), "reflect", None))
     out.append(("f32-3d-uneven", np.float32, (20, 12, 31), g((1, 1, 2)), "circular", [20, 11]))
     out.append(("f64-3d-xy-only", np.float64, (20, 12, 16), (g((1, 1, 0))[0], g((1, 1, 0))[1]), "replicate", None))
