@@ -1,0 +1,304 @@
+// longtap.cu — one 1-D stage of 18 .. 256 taps along any axis of an N-d array (K1-long).
+//
+// The reference runs a separable cascade one 1-D factor at a time whatever the factor's length (src/imfilter.jl:385-395,
+// inner loop :724-739); its own benchmark kernel KernelFactors.gaussian(sigma = 10) is 41 taps per axis
+// (benchmark/benchmarks.jl:45-49).  The register-window kernels (stream2d / stream3d) unroll over the tap count and stop at
+// 17; this kernel keeps the OUTPUTS in registers and walks the taps in chunks instead, so its code size is independent of
+// the tap count:
+//   * the array is viewed as (W, H, B) with the filtered axis = H (axis >= 1: W = product of the leading extents) or as rows
+//     of the contiguous axis (axis 0);
+//   * a CTA (256 threads) owns 32 lines x 128 outputs along the axis.  The input tile (128 + L - 1 positions, border remap and
+//     eltype conversion applied once, at load) sits in shared memory as [position][line] with a pitch of 33, so that a warp —
+//     lane = line — reads one position of 32 lines without bank conflicts, whichever axis is filtered; along axis 0 the
+//     result goes back through the same transposed layout for coalesced stores;
+//   * a thread owns 8 consecutive outputs of one line.  Float32: four float2 accumulators fed by FFMA2 in the
+//     value-broadcast x tap-pair form (value u = in[o + j] serves outputs o and o+1 with taps (k[j], k[j-1])), a sliding
+//     register window of 14 values per chunk of 8 taps: 32 FFMA2 per 8 shared-memory loads.  Float64: eight accumulators,
+//     separate multiply and add in tap order (the reference's arithmetic, src/imfilter.jl:732-737), window of 16 per 8 taps.
+// Roofline: one pass moves sizeof(in) + sizeof(out) bytes per element and issues L multiply-adds; at 41 taps Float32 the FP32
+// pipe (128 FMA / clk / SM) and HBM are within 15 % of each other.
+#include "common.cuh"
+
+namespace b2f {
+
+constexpr int LT_MAXL = 256, LT_MINL = 18;
+constexpr int LT_NT = 256, LT_TO = 128, LT_PITCH = 33;
+
+template <typename CT>
+struct LtParams {
+    const void *src;
+    CT *dst;
+    int src_dt, L, klo, style, along_x;
+    long long W, H, B;          // the (W, H, B) view; along_x: W = the axis, H = number of rows, B = 1
+    long long Ag, a_first;      // global length of the filtered axis and the global index of local position 0 (slab form)
+    long long o0, on;           // outputs [o0, o0 + on) along the axis (local positions); the output array has `on` of them
+    long long ntl, nta;         // tiles across the lines / along the axis
+    CT fill;
+    CT k[LT_MAXL];
+};
+
+__device__ __forceinline__ float2 lt_fma2(float v, float2 k, float2 c) {
+    unsigned long long rk = *reinterpret_cast<unsigned long long *>(&k), rc = *reinterpret_cast<unsigned long long *>(&c), rv, rd;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(rv) : "f"(v));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(rv), "l"(rk), "l"(rc));
+    return *reinterpret_cast<float2 *>(&rd);
+}
+
+// 8 outputs of one line: sp = the line's tile entry of the first output's first input, positions LT_PITCH apart
+__device__ __forceinline__ void lt_line8(const float *sp, const float *k, const float2 *kp, const int L, float (&out)[8]) {
+    float2 acc[4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) acc[p] = make_float2(sp[(2 * p) * LT_PITCH] * k[0], 0.f);      // j = 0: the even output only
+    float w[14];
+#pragma unroll
+    for (int t = 0; t < 6; ++t) w[t] = sp[(1 + t) * LT_PITCH];
+    int j0 = 1;
+    for (; j0 + 8 <= L; j0 += 8) {                                   // taps j0 .. j0+7 (all < L): value u = 2p + j is w[u - j0]
+#pragma unroll
+        for (int t = 0; t < 8; ++t) w[6 + t] = sp[(j0 + 6 + t) * LT_PITCH];
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+            const float2 kk = kp[j0 + jj];
+#pragma unroll
+            for (int p = 0; p < 4; ++p) acc[p] = lt_fma2(w[2 * p + jj], kk, acc[p]);
+        }
+#pragma unroll
+        for (int t = 0; t < 6; ++t) w[t] = w[8 + t];
+    }
+    if (j0 < L) {                                                    // the last, partial chunk (the tile is padded: loads stay inside)
+#pragma unroll
+        for (int t = 0; t < 8; ++t) w[6 + t] = sp[(j0 + 6 + t) * LT_PITCH];
+#pragma unroll
+        for (int jj = 0; jj < 7; ++jj) {
+            if (j0 + jj < L) {
+                const float2 kk = kp[j0 + jj];
+#pragma unroll
+                for (int p = 0; p < 4; ++p) acc[p] = lt_fma2(w[2 * p + jj], kk, acc[p]);
+            }
+        }
+    }
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {                                    // j = L: the odd output only
+        acc[p].y = fmaf(sp[(2 * p + L) * LT_PITCH], k[L - 1], acc[p].y);
+        out[2 * p] = acc[p].x;
+        out[2 * p + 1] = acc[p].y;
+    }
+}
+
+__device__ __forceinline__ void lt_line8(const double *sp, const double *k, const double *, const int L, double (&out)[8]) {
+    double acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.0;
+    double w[16];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) w[t] = sp[t * LT_PITCH];
+    int j0 = 0;
+    for (; j0 + 8 <= L; j0 += 8) {
+#pragma unroll
+        for (int t = 0; t < 8; ++t) w[8 + t] = sp[(j0 + 8 + t) * LT_PITCH];
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+            const double kk = k[j0 + jj];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] = mac<double>(acc[i], w[i + jj], kk);
+        }
+#pragma unroll
+        for (int t = 0; t < 8; ++t) w[t] = w[8 + t];
+    }
+    if (j0 < L) {
+#pragma unroll
+        for (int t = 0; t < 8; ++t) w[8 + t] = sp[(j0 + 8 + t) * LT_PITCH];
+#pragma unroll
+        for (int jj = 0; jj < 7; ++jj) {
+            if (j0 + jj < L) {
+                const double kk = k[j0 + jj];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[i] = mac<double>(acc[i], w[i + jj], kk);
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) out[i] = acc[i];
+}
+
+template <typename CT> struct LtPair { typedef CT type; };
+template <> struct LtPair<float> { typedef float2 type; };
+
+// The tile load.  Every thread issues its loads in batches of LT_UB independent, unconditional loads (out-of-range cells read
+// element 0 and are replaced afterwards): the load phase is latency-bound otherwise — a warp has ~24 cells to fetch and a
+// dependent address -> load -> store chain per cell costs a full DRAM round trip each.
+constexpr int LT_UB = 8;
+template <typename IT, bool N0, typename CT>
+__device__ __forceinline__ void lt_load_tile(const LtParams<CT> &P, CT *tile, const long long line0, const long long out0,
+                                             const long long b, const long long nlines, const int npos, const int npos_pad) {
+    const IT *src = reinterpret_cast<const IT *>(P.src);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    auto conv = [](IT x) -> CT { return N0 ? N0f8Conv<CT>::f((unsigned)x) : (CT)x; };
+    if (P.along_x) {
+        // lines = rows (stride W), positions contiguous: lanes run along the positions (coalesced), smem [pos][line]
+        const int per_line = (npos_pad + 31) >> 5, total = 4 * per_line;          // a warp loads lines warp, warp + 8, ...
+        for (int i0 = 0; i0 < total; i0 += LT_UB) {
+            IT x[LT_UB];
+            int st[LT_UB];                      // tile offset, or -1 (nothing to store), | flags in the two top bits
+#pragma unroll
+            for (int u = 0; u < LT_UB; ++u) {
+                const int i = i0 + u, li = i / per_line, ln = warp + 8 * li, q = (i - li * per_line) * 32 + lane;
+                const long long row = line0 + ln;
+                long long off = 0;
+                st[u] = -1;
+                if (i < total && q < npos_pad) {
+                    st[u] = q * LT_PITCH + ln;
+                    if (q < npos && row < nlines) {
+                        const long long a = remap_index(P.style, out0 + P.klo + q, P.W);
+                        if (a >= 0) { off = row * P.W + a; st[u] |= 1 << 30; } else st[u] |= 1 << 29;
+                    }
+                }
+                x[u] = src[off];
+            }
+#pragma unroll
+            for (int u = 0; u < LT_UB; ++u)
+                if (st[u] >= 0) tile[st[u] & 0xFFFFFF] = (st[u] >> 30) & 1 ? conv(x[u]) : ((st[u] >> 29) & 1 ? P.fill : (CT)0);
+        }
+    } else {
+        const long long xg = line0 + lane;
+        const bool xin = xg < nlines;
+        for (int q0 = warp; q0 < npos_pad; q0 += LT_UB * (LT_NT / 32)) {
+            IT x[LT_UB];
+            int st[LT_UB];
+#pragma unroll
+            for (int u = 0; u < LT_UB; ++u) {
+                const int q = q0 + u * (LT_NT / 32);
+                long long off = 0;
+                st[u] = -1;
+                if (q < npos_pad) {
+                    st[u] = 0;
+                    if (q < npos && xin) {
+                        long long a = remap_index(P.style, P.a_first + out0 + P.klo + q, P.Ag);
+                        if (a >= 0) a -= P.a_first;
+                        // a slab holds the planes its outputs need (checked by the caller); anything else is a Fill cell
+                        if (a >= 0 && a < P.H) { off = (b * P.H + a) * P.W + xg; st[u] = 2; } else st[u] = 1;
+                    }
+                }
+                x[u] = src[off];
+            }
+#pragma unroll
+            for (int u = 0; u < LT_UB; ++u)
+                if (st[u] >= 0) tile[(q0 + u * (LT_NT / 32)) * LT_PITCH + lane] = st[u] == 2 ? conv(x[u]) : (st[u] == 1 ? P.fill : (CT)0);
+        }
+    }
+}
+
+// shared memory: taps k[Lp] | (Float32) tap pairs kp[Lp] | tile [npos_pad][33]
+template <typename CT>
+__global__ void __launch_bounds__(LT_NT) longtap_kernel(const __grid_constant__ LtParams<CT> P) {
+    typedef typename LtPair<CT>::type PT;
+    extern __shared__ __align__(16) unsigned char lt_smem[];
+    const int L = P.L, Lp = (L + 8) & ~7;
+    CT *k = reinterpret_cast<CT *>(lt_smem);
+    PT *kp = reinterpret_cast<PT *>(k + Lp);
+    CT *tile = reinterpret_cast<CT *>(kp + (sizeof(CT) == 4 ? Lp : 0));
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int npos = LT_TO + L - 1, npos_pad = LT_TO + Lp + 8;
+
+    long long t = blockIdx.x;
+    const long long ta = t % P.nta; t /= P.nta;
+    const long long tl = t % P.ntl;
+    const long long b = t / P.ntl;
+    const long long line0 = tl * 32, out0 = P.o0 + ta * LT_TO;        // first line / first output position of this tile
+    const long long nlines = P.along_x ? P.H : P.W;
+
+    for (int j = tid; j < Lp; j += LT_NT) {
+        k[j] = j < L ? P.k[j] : (CT)0;
+        if (sizeof(CT) == 4) {
+            float2 pr = make_float2(j < L ? (float)P.k[j] : 0.f, (j >= 1 && j <= L) ? (float)P.k[j - 1] : 0.f);
+            reinterpret_cast<float2 *>(kp)[j] = pr;
+        }
+    }
+    // ---- tile load: position q of the tile is input position out0 + klo + q ------------------------------------------------
+    switch (P.src_dt) {
+        case B2F_U8: lt_load_tile<uint8_t, false>(P, tile, line0, out0, b, nlines, npos, npos_pad); break;
+        case B2F_N0F8: lt_load_tile<uint8_t, true>(P, tile, line0, out0, b, nlines, npos, npos_pad); break;
+        case B2F_F32: lt_load_tile<float, false>(P, tile, line0, out0, b, nlines, npos, npos_pad); break;
+        default: lt_load_tile<double, false>(P, tile, line0, out0, b, nlines, npos, npos_pad); break;
+    }
+    __syncthreads();
+    // ---- compute: group g = 8 consecutive outputs; 16 groups per tile, two per warp -----------------------------------------
+    CT res[2][8];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int g = warp + 8 * h;
+        lt_line8(tile + (8 * g) * LT_PITCH + lane, k, kp, L, res[h]);
+    }
+    const long long oend = P.o0 + P.on;
+    if (!P.along_x) {
+        const long long x = line0 + lane;
+        if (x < nlines) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const long long o = out0 + 8 * (warp + 8 * h);
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    if (o + i < oend) P.dst[(b * P.on + (o + i - P.o0)) * P.W + x] = res[h][i];
+            }
+        }
+    } else {
+        __syncthreads();                            // every warp is done reading the tile: reuse its first 128 positions
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int g = warp + 8 * h;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) tile[(8 * g + i) * LT_PITCH + lane] = res[h][i];
+        }
+        __syncthreads();
+        for (int idx = tid; idx < 32 * LT_TO; idx += LT_NT) {
+            const int ln = idx >> 7, q = idx & (LT_TO - 1);
+            const long long row = line0 + ln, o = out0 + q;
+            if (row < nlines && o < oend) P.dst[row * P.on + (o - P.o0)] = tile[q * LT_PITCH + ln];
+        }
+    }
+}
+
+bool longtap_ok(int64_t L) { return L >= LT_MINL && L <= LT_MAXL; }
+
+// One pass: `taps` (L of them, first tap at offset klo) along the H axis of the (W, H, B) view, or along W when along_x.
+// Slab form (axis >= 1 only): the source holds H positions starting at global position a_first of an axis of global length
+// Ag; outputs [o0, o0 + on) in local positions.  Ag = 0: the axis is whole (Ag = H, a_first = 0, all outputs).
+template <typename CT>
+int run_longtap(const void *src, int src_dt, CT *dst, const double *taps, int64_t L, int64_t klo, bool along_x, int64_t W, int64_t H,
+                int64_t B, int style, CT fill, int64_t Ag, int64_t a_first, int64_t o0, int64_t on, cudaStream_t st) {
+    if (!longtap_ok(L)) return fail(B2F_ENOTSUP, "longtap: %lld taps (takes %d .. %d)", (long long)L, LT_MINL, LT_MAXL);
+    LtParams<CT> P;
+    memset(&P, 0, sizeof P);
+    P.src = src; P.dst = dst; P.src_dt = src_dt; P.L = (int)L; P.klo = (int)klo; P.style = style; P.along_x = along_x ? 1 : 0;
+    P.W = W; P.H = H; P.B = along_x ? 1 : B;
+    const int64_t axis_len = along_x ? W : H;
+    P.Ag = Ag > 0 ? Ag : axis_len; P.a_first = Ag > 0 ? a_first : 0;
+    P.o0 = Ag > 0 ? o0 : 0; P.on = Ag > 0 ? on : axis_len;
+    P.fill = fill;
+    for (int j = 0; j < L; ++j) P.k[j] = (CT)taps[j];
+    const int64_t nlines = along_x ? H : W;
+    P.ntl = (nlines + 31) / 32;
+    P.nta = (P.on + LT_TO - 1) / LT_TO;
+    const long long blocks = P.ntl * P.nta * P.B;
+    if (blocks <= 0) return 0;
+    if (blocks >= (1LL << 31)) return fail(B2F_ENOTSUP, "longtap: array too large for one launch");
+    const int Lp = ((int)L + 8) & ~7;
+    const size_t smem = (size_t)Lp * sizeof(CT) * (sizeof(CT) == 4 ? 3 : 1) + (size_t)(LT_TO + Lp + 8) * LT_PITCH * sizeof(CT);
+    static thread_local bool attr_set[2] = {false, false};
+    bool &as = attr_set[sizeof(CT) == 4 ? 0 : 1];
+    if (!as) {
+        B2F_CUDA(cudaFuncSetAttribute(longtap_kernel<CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
+        as = true;
+    }
+    longtap_kernel<CT><<<(unsigned)blocks, LT_NT, smem, st>>>(P);
+    count_launch(1);
+    B2F_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template int run_longtap<float>(const void *, int, float *, const double *, int64_t, int64_t, bool, int64_t, int64_t, int64_t, int, float,
+                                int64_t, int64_t, int64_t, int64_t, cudaStream_t);
+template int run_longtap<double>(const void *, int, double *, const double *, int64_t, int64_t, bool, int64_t, int64_t, int64_t, int,
+                                 double, int64_t, int64_t, int64_t, int64_t, cudaStream_t);
+
+}  // namespace b2f

@@ -31,7 +31,13 @@ B2F_S2_DECL(float, double)
 B2F_S2_DECL(double, float)
 B2F_S2_DECL(double, double)
 
-static bool taps_ok_single(int64_t L) { return L >= 1 && (L <= 16 || L == 17); }
+// 18 .. 256 taps: the chunked-tap kernel of longtap.cu (one pass per stage)
+bool longtap_ok(int64_t L);
+template <typename CT>
+int run_longtap(const void *src, int src_dt, CT *dst, const double *taps, int64_t L, int64_t klo, bool along_x, int64_t W, int64_t H,
+                int64_t B, int style, CT fill, int64_t Ag, int64_t a_first, int64_t o0, int64_t on, cudaStream_t st);
+
+static bool taps_ok_single(int64_t L) { return L >= 1 && (L <= 17 || longtap_ok(L)); }
 static bool taps_ok_pair(int64_t Lx, int64_t Ly) { return (Lx <= 16 && Ly <= 16) || (Lx == 17 && Ly == 17); }
 
 bool sepnd_applicable(const Plan &P, int img_dt, int out_dt) {
@@ -106,6 +112,11 @@ static int run_pass(const int64_t *dims, const StageInfo *sx, const StageInfo *s
     } else {
         W = dims[0]; H = dims[1] * dims[2] * dims[3]; nbatch = 1;
     }
+    if (sx && !sy && sx->s->len[0] > 17)
+        return run_longtap<CT>(src, src_dt, (CT *)dst, sx->s->taps, sx->s->len[0], sx->lo[0], true, W, H, 1, style, fill, 0, 0, 0, 0, st);
+    if (sy && !sx && sy->s->len[yaxis] > 17)
+        return run_longtap<CT>(src, src_dt, (CT *)dst, sy->s->taps, sy->s->len[yaxis], sy->lo[yaxis], false, W, H, nbatch, style, fill,
+                               Hg > 0 ? Hg : 0, y_first, ry0, rh > 0 ? rh : H, st);
     if (W >= (1LL << 30) || H >= (1LL << 30)) return fail(B2F_ENOTSUP, "array extent too large for the streamed pass");
     P.img = src;
     P.n0_r = src_dt == B2F_N0F8 ? (CT)1 / (CT)255 : (CT)1;

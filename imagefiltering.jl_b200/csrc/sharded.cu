@@ -331,9 +331,12 @@ int b2f_imfilter_sharded(b2f_shard_ctx *ctx, const b2f_array *img, const b2f_arr
     const char *peer_lo = use_lo ? (const char *)c.lower_slab + (size_t)(c.lower_planes - h_lo) * plane_bytes : nullptr;
     const char *peer_hi = use_hi ? (const char *)c.upper_slab : nullptr;
 
-    // fused Float32 3-D kernel: exchange xy-filtered boundary planes (B2F_SHARD_XY=0: raw halos, for A/B runs).  The decision
-    // depends on the kernel and the plane shape only, so every rank of the pass takes the same branch.
-    static const bool xy_env = !(getenv("B2F_SHARD_XY") && atoi(getenv("B2F_SHARD_XY")) == 0);
+    // fused Float32 3-D kernel, B2F_SHARD_XY=1: exchange xy-filtered boundary planes instead of raw ones.  OFF by default: it
+    // removes the x / y stages of the 2 x 8 halo planes from the march (-7 % of its multiply-adds on a 128-plane slab) but puts
+    // two pre-filter launches and their hand-shake in front of it, and measured slower on 1024^3 (2 GPUs: 1.579 vs 1.506 ms,
+    // 8 GPUs: 0.598 vs 0.499 ms; profiles/r2_sharded_xy_ab.jsonl).  The decision depends on the environment, the kernel and the
+    // plane shape only, so every rank of the pass takes the same branch.
+    static const bool xy_env = getenv("B2F_SHARD_XY") && atoi(getenv("B2F_SHARD_XY")) == 1;
     if (xy_env && c.xy_ok && (use_lo || use_hi) && nd == 3 && img->dtype == B2F_F32 && out->dtype == B2F_F32) {
         b2f_array gi = *img, go = *out;
         gi.dims[2] = go.dims[2] = global_last_dim;

@@ -402,3 +402,123 @@ def imfilter_sharded(slab, kernel, border="replicate", *, out=None, group=None, 
         return res
     finally:
         f.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Slab-sharded mapwindow (one volume too large for one GPU, or already distributed)
+# ---------------------------------------------------------------------------------------------------------------------
+class ShardedMapwindow:
+    """`mapwindow(f, A, window; border)` for f in {extrema, minimum, maximum, median, mean, sum} on an array whose LAST Julia axis
+    is partitioned over the ranks (reference src/mapwindow.jl:75-121; the window loop needs, along the sharded axis, the
+    `-window_lo` planes below and `window_hi` planes above every owned plane).
+
+    Each rank keeps ONE buffer [lower halo | own planes | upper halo]; `self.slab` is the view of its own planes (fill it in
+    place, or pass a tensor to `run`).  `run()` exchanges the raw boundary planes (NCCL send/recv over NVLink into the halo
+    parts of the buffer; gloo in the CPU tests), then calls the single-GPU entry point (`b2f_mapwindow_extrema` /
+    `b2f_mapwindow_reduce`) on the buffer with the OUTPUT restricted to the owned planes — the kernels evaluate exactly the
+    indices of `out`'s axes, so no halo plane is computed twice.  A face of the buffer is either a seam (never reached by an
+    owned plane's window) or a face of the whole array (where the border rule then applies unchanged), so the result equals
+    the owned planes of `mapwindow` on the whole array.  No collective in the data path.
+
+        f = ShardedMapwindow(ifb.extrema, slab, (7, 7, 7))
+        lo, hi = f.run()            # extrema: (min, max); the other window functions: one tensor
+    """
+
+    def __init__(self, f, slab, window, border="replicate", *, group=None, _library=None):
+        import torch
+        import torch.distributed as dist
+        from .border import Inner, NoPad
+        from .mapwindow import _REDUCE_OP, _kind, _reduce_out_dtype, resolve_window
+        self.torch, self.dist, self.group = torch, dist, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        if _library is not None:
+            self.lib = _library
+        else:
+            from ._lib import lib
+            self.lib = lib()                      # raises when the CUDA extension is missing: no CPU path
+        if slab.dim() < 2 or slab.dim() > _abi.MAXDIM:
+            raise NotSupportedError("slab-sharded arrays need 2..4 dimensions")
+        self.kind = _kind(f)
+        self.ndim = slab.dim()
+        self.wlo, self.whi = resolve_window(window, self.ndim, allow_even=False)
+        b = borderinstance(border)
+        if isinstance(b, (Inner, NoPad)) or not isinstance(b, (Pad, Fill)):
+            raise NotSupportedError("the sharded mapwindow takes Pad(style) / Fill(value) borders")
+        self.border = b
+        dts = {torch.uint8: _abi.U8, torch.int16: _abi.I16, torch.int32: _abi.I32, torch.int64: _abi.I64, torch.float32: _abi.F32,
+               torch.float64: _abi.F64}
+        if slab.dtype not in dts:
+            raise NotSupportedError(f"slab eltype {slab.dtype} is not supported")
+        self.dt = dts[slab.dtype]
+        self.h_lo, self.h_hi = max(0, -self.wlo[-1]), max(0, self.whi[-1])
+        n = int(slab.shape[0])
+        counts = [n]
+        if self.world > 1:
+            counts = [None] * self.world
+            dist.all_gather_object(counts, n, group=group)
+        self.counts = counts
+        self.first, self.global_planes = int(sum(counts[:self.rank])), int(sum(counts))
+        # no wrap-around neighbour, Pad(:circular) included: the window loop pads the IN-IMAGE PART OF EACH WINDOW
+        # (copy_win!, src/mapwindow.jl:310-333), so a window at a face of the array never sees the opposite face
+        self.lower = self.rank - 1 if self.rank > 0 else None
+        self.upper = self.rank + 1 if self.rank + 1 < self.world else None
+        if self.h_lo == 0:
+            self.lower = None
+        if self.h_hi == 0:
+            self.upper = None
+        if self.world > 1 and min(counts) <= max(self.h_lo, self.h_hi):
+            raise DimensionMismatch(f"every rank must own more planes than the window reaches ({max(self.h_lo, self.h_hi)}); counts = {counts}")
+        self.n_lo = self.h_lo if self.lower is not None else 0
+        self.n_hi = self.h_hi if self.upper is not None else 0
+        shp = tuple(slab.shape[1:])
+        self.ext = torch.empty((self.n_lo + n + self.n_hi,) + shp, dtype=slab.dtype, device=slab.device)
+        self.slab = self.ext[self.n_lo:self.n_lo + n]
+        self.slab.copy_(slab)
+        self.recv_lo = self.ext[:self.n_lo] if self.n_lo else None
+        self.recv_hi = self.ext[self.n_lo + n:] if self.n_hi else None
+        self._nccl = self.world > 1 and dist.get_backend(group) == "nccl"
+        odt = {v: k for k, v in dts.items()}
+        if self.kind in ("extrema", "min", "max"):
+            self.out_dt = self.dt
+            self._op = None
+        else:
+            self.out_dt = _reduce_out_dtype(self.kind, self.dt)
+            self._op = _REDUCE_OP[self.kind]
+        mk = lambda: torch.empty(slab.shape, dtype=odt[self.out_dt], device=slab.device)
+        self.out = (mk(), mk()) if self.kind == "extrema" else mk()
+
+    _exchange = ShardedImfilter._exchange
+    _grank = ShardedImfilter._grank
+
+    def run(self, slab=None):
+        t = self.torch
+        if slab is not None:
+            self.slab.copy_(slab)
+        if self.world > 1:
+            self._exchange()
+        stream = t.cuda.current_stream().cuda_stream if self.ext.is_cuda else 0
+        nd = self.ndim
+        mem = _abi.DEVICE if self.ext.is_cuda else _abi.HOST
+        img = _abi.make_array(self.ext.data_ptr(), self.dt, tuple(reversed(self.ext.shape)), (1,) * nd, mem)
+        odims = tuple(reversed(self.slab.shape))
+        ofirst = (1,) * (nd - 1) + (1 + self.n_lo,)                   # the owned planes, in the buffer's coordinates
+        od = lambda x: _abi.make_array(x.data_ptr(), self.out_dt, odims, ofirst, mem)
+        b = self.border.to_abi(nd)
+        if self.kind == "extrema":
+            self.lib.mapwindow_extrema(img, od(self.out[0]), od(self.out[1]), False, self.wlo, self.whi, b, stream)
+        elif self.kind in ("min", "max"):
+            self.lib.mapwindow_extrema(img, od(self.out) if self.kind == "min" else None, od(self.out) if self.kind == "max" else None,
+                                       False, self.wlo, self.whi, b, stream)
+        else:
+            self.lib.mapwindow_reduce(img, od(self.out), self._op, self.wlo, self.whi, b, None, None, stream)
+        return self.out
+
+
+def mapwindow_sharded(f, slab, window, border="replicate", *, group=None, _library=None):
+    """One-shot form of ShardedMapwindow: this rank's planes of mapwindow(f, whole, window; border)."""
+    m = ShardedMapwindow(f, slab, window, border, group=group, _library=_library)
+    res = m.run()
+    if slab.is_cuda:
+        m.torch.cuda.synchronize()
+    return res

@@ -35,8 +35,9 @@ def cases(ifb):
     return out
 
 
-def run(rank, world, port, use_device, modes, errq):
+def run(rank, world, port, use_device, modes, errq, env=None):
     try:
+        os.environ.update(env or {})
         import torch
         import torch.distributed as dist
         import imagefiltering_jl_b200 as ifb
@@ -87,7 +88,62 @@ def run(rank, world, port, use_device, modes, errq):
         errq.put((rank, ["EXC: " + traceback.format_exc()]))
 
 
-def launch(world, use_device, modes):
+def run_mapwindow(rank, world, port, use_device, modes, errq, env=None):
+    """ShardedMapwindow: every rank's planes against mapwindow of the oracle on the whole array."""
+    try:
+        os.environ.update(env or {})
+        import torch
+        import torch.distributed as dist
+        import imagefiltering_jl_b200 as ifb
+        from importlib import import_module
+        sh = import_module("imagefiltering_jl_b200.sharded")
+        dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+        oracle = ifb._abi.Library(os.path.join(ROOT, "oracle", "libb2f_oracle.so"))
+        lib = None if use_device else oracle
+        if use_device:
+            torch.cuda.set_device(0)
+        failures = []
+        cases = [("ext-f32-3d", ifb.extrema, np.float32, (40, 22, 37), (5, 3, 7), "replicate"),
+                 ("ext-u8-3d-wide", ifb.extrema, np.uint8, (33, 20, 64), (3, 5, 21), "replicate"),
+                 ("max-i32-2d", ifb.maximum, np.int32, (50, 41), (3, 9), "symmetric"),
+                 ("min-f64-3d-circ", ifb.minimum, np.float64, (20, 12, 31), (1, 3, 5), "circular"),
+                 ("max-f32-3d-fill", ifb.maximum, np.float32, (24, 18, 30), (3, 3, 5), ifb.Fill(0.5)),
+                 ("min-f32-3d-asym", ifb.minimum, np.float32, (24, 18, 30), (range(0, 1), range(-1, 2), range(-1, 4)), "reflect"),
+                 ("mean-f32-3d", ifb.mean, np.float32, (18, 14, 25), (3, 3, 5), "replicate"),
+                 ("sum-u8-3d", sum, np.uint8, (18, 14, 25), (3, 1, 3), "symmetric"),
+                 ("median-f64-3d", ifb.median, np.float64, (12, 10, 22), (3, 3, 3), "replicate"),
+                 ("ext-f32-3d-noz", ifb.extrema, np.float32, (30, 20, 12), (7, 7, 1), "replicate")]
+        for name, f, T, shape, window, border in cases:
+            rng = np.random.default_rng(sum(map(ord, name)))
+            whole = np.asfortranarray((rng.random(shape) * 200).astype(T))
+            ref = ifb.mapwindow(f, whole, window, border=border, _library=oracle)
+            first, n = sh.slab_bounds(shape[-1], world, rank)
+            t_whole = torch.from_numpy(np.ascontiguousarray(whole.transpose()))
+            slab = t_whole[first:first + n].contiguous()
+            if use_device:
+                slab = slab.cuda()
+            m = sh.ShardedMapwindow(f, slab, window, border, _library=lib)
+            assert (m.first, m.global_planes) == (first, shape[-1])
+            got = m.run()
+            if use_device:
+                torch.cuda.synchronize()
+            if f is ifb.extrema:
+                want = (ref["min"][..., first:first + n], ref["max"][..., first:first + n])
+                ok = all(np.array_equal(g.cpu().numpy().transpose(), w) for g, w in zip(got, want))
+            else:
+                g = got.cpu().numpy().transpose()
+                w = np.asarray(ref)[..., first:first + n]
+                ok = g.dtype == w.dtype and np.array_equal(g, w)
+            if not ok:
+                failures.append((name, rank))
+        dist.barrier()
+        dist.destroy_process_group()
+        errq.put((rank, failures))
+    except Exception:
+        errq.put((rank, ["EXC: " + traceback.format_exc()]))
+
+
+def launch(world, use_device, modes, env=None, target=None):
     import socket
     import torch.multiprocessing as mp
     s = socket.socket()
@@ -96,7 +152,7 @@ def launch(world, use_device, modes):
     s.close()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=run, args=(r, world, port, use_device, modes, q)) for r in range(world)]
+    procs = [ctx.Process(target=target or run, args=(r, world, port, use_device, modes, q, env)) for r in range(world)]
     for p in procs:
         p.start()
     results = []

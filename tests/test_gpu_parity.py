@@ -700,3 +700,41 @@ def test_window_reductions_parity(ifb, oracle, device, dt):
         a = ifb.mapwindow(f, vol, (3, 1, 5), border="symmetric", indices=(range(1, 21, 4), range(1, 18), range(3, 9, 2)))
         b = ifb.mapwindow(f, vol, (3, 1, 5), border="symmetric", indices=(range(1, 21, 4), range(1, 18), range(3, 9, 2)), _library=oracle)
         assert np.array_equal(a, b), f
+
+
+@pytest.mark.parametrize("border", BORDERS + ["fill"])
+@pytest.mark.parametrize("dt", ["f32", "f64", "n0f8"])
+def test_long_separable_factors(ifb, oracle, device, border, dt):
+    """18 .. 256 taps per axis (csrc/longtap.cu): the reference's benchmark kernel KernelFactors.gaussian(sigma = 10) is 41 taps
+    (benchmark/benchmarks.jl:45-49).  Float64 outputs bit-exact, Float32 within the stated tolerance; 2-D and 3-D, tap counts
+    around the chunk size of 8, mixed with short factors, pads larger than the array."""
+    rng = np.random.default_rng(seed_of(("long", border, dt)))
+    g = ifb.KernelFactors.gaussian
+    b = ifb.Fill(0.25) if border == "fill" else border
+    cases = [((150, 131), g((10, 10))),                  # 41 x 41
+             ((300, 40), g((5, 8))),                     # 21 x 33
+             ((33, 70, 45), g((1, 6, 5))),               # 5, 25, 21: short x factor, long y and z
+             ((20, 19, 50), g((7, 1, 16))),              # 29 taps on an axis of 20, 65 on an axis of 50
+             ((260, 37), g((0, 9)))]                     # y only, 37 taps
+    for shape, kern in cases:
+        if dt == "n0f8":
+            img = ifb.n0f8(rng.integers(0, 256, size=shape, dtype=np.uint8))
+        else:
+            img = np.asfortranarray(rng.random(shape).astype(np.float32 if dt == "f32" else np.float64))
+        T = np.float32 if dt == "f32" else np.float64
+        pa, pb = _both(ifb, oracle, T, img, kern, b)
+        assert device.last_path() == "sepnd", (device.last_path(), shape)
+        if T == np.float64:
+            assert np.array_equal(pa, pb), (shape, border, dt)
+        else:
+            tol = _tol([k.data.parent for k in kern], img)
+            assert np.max(np.abs(pa.astype(np.float64) - pb.astype(np.float64))) <= tol, (shape, border)
+    # tap counts 18 .. 34 and 255 / 256 with an asymmetric (non-centred) factor along each axis in turn
+    img = np.asfortranarray(rng.random((70, 61, 9)))
+    for L in (18, 23, 24, 25, 26, 33, 34, 255, 256):
+        taps = rng.random(L) - 0.3
+        for axis in (0, 1, 2):
+            k = ifb.ReshapedOneD(3, axis, ifb.OffsetArray.with_first(taps, (-(L // 3),)))
+            pa, pb = _both(ifb, oracle, np.float64, img, (k,), b)
+            assert device.last_path() == "sepnd"
+            assert np.array_equal(pa, pb), (L, axis, border)

@@ -7,7 +7,7 @@ pointers read by the fused kernel, "staged" = copy-engine staging overlapped wit
 exchanged halo buffers)."""
 import pytest
 
-from sharded_worker import launch
+from sharded_worker import launch, run_mapwindow
 
 
 def _check(results, world):
@@ -37,3 +37,22 @@ def test_slab_bounds_and_halo_extent(ifb):
 @pytest.mark.parametrize("world", [2, 3])
 def test_sharded_device_two_ranks_one_gpu(world):
     _check(launch(world, use_device=True, modes=["driver", "p2p", "staged", "sendrecv"]), world)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_driver_xy_filtered_exchange(world):
+    """B2F_SHARD_XY=1: the driver exchanges xy-filtered boundary planes (b2f_imfilter_slab_xy) instead of raw halos"""
+    _check(launch(world, use_device=True, modes=["driver"], env={"B2F_SHARD_XY": "1"}), world)
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_mapwindow_host_logic_gloo_cpu(world):
+    """ShardedMapwindow (one huge volume): partition, halo planes of the window, global faces"""
+    _check(launch(world, use_device=False, modes=[], target=run_mapwindow), world)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_mapwindow_device(world):
+    _check(launch(world, use_device=True, modes=[], target=run_mapwindow), world)
