@@ -3,7 +3,7 @@
 (benchmark/benchmarks.jl:45-49) — and neighbours on one GPU: device-resident arrays, CUDA events, best of 5 x 10 launches.
 Prints one JSON line per case with the per-pass roofline (one pass per stage: sizeof(in) + sizeof(out) bytes per element).
 
-    python benchmarks/longtap_time.py
+    python benchmarks/longtap_time.py [substring of the case names to run]
 """
 import json
 import os
@@ -31,6 +31,8 @@ def main():
              ("gaussian6_F32_8192x8192_fused2d", (8192, 8192), (6, 6), torch.float32, None),
              ("gaussian6_F32_8192x8192_sepnd", (8192, 8192), (6, 6), torch.float32, "sepnd"),
              ("gaussian4_F32_8192x8192_stream2d", (8192, 8192), (4, 4), torch.float32, None)]
+    if len(sys.argv) > 1:
+        cases = [c for c in cases if sys.argv[1] in c[0]]
     for name, shape, sig, dt, force in cases:
         if force:
             os.environ["B2F_FORCE_PATH"] = force

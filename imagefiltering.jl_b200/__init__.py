@@ -13,7 +13,7 @@ from ._abi import (ArgumentError, CudaError, DimensionMismatch, InexactError, No
 from .border import Fill, Inner, NA, NoPad, Pad, borderinstance
 from .color import ColorArray
 from .device import DeviceArray
-from .imfilter import factorkernel, filter_type, imfilter, imfilter_, imgradients, padarray
+from .imfilter import accum_mode, factorkernel, filter_type, imfilter, imfilter_, imgradients, padarray
 from .kernel import reflect
 from .localextrema import BlobLoG, blob_LoG, findlocalmaxima, findlocalminima
 from .kernelfactors import ReshapedOneD, kernelfactors

@@ -33,6 +33,8 @@ DTYPE_TO_NP = {v: k for k, v in NP_TO_DTYPE.items()}
 DTYPE_TO_NP[N0F8] = np.dtype(np.uint8)
 
 # every symbol include/b2f.h declares (tests check the built library exports all of them)
+ACCUM_EXACT, ACCUM_FMA = 0, 1
+
 SYMBOLS = [
     "b2f_version", "b2f_last_error", "b2f_is_device_library", "b2f_set_device", "b2f_device_count", "b2f_sm_count",
     "b2f_malloc", "b2f_free", "b2f_host_alloc", "b2f_host_free", "b2f_host_register", "b2f_host_unregister", "b2f_memcpy_h2d", "b2f_memcpy_d2h",
@@ -40,7 +42,7 @@ SYMBOLS = [
     "b2f_memset_async", "b2f_stream_write32", "b2f_stream_wait_geq32",
     "b2f_findlocalextrema", "b2f_scale_into_slice", "b2f_maxabs", "b2f_gather", "b2f_na_prepare", "b2f_divide",
     "b2f_normalize_dims",
-    "b2f_bench_fma_peak", "b2f_launch_count", "b2f_reset_launch_count", "b2f_last_path",
+    "b2f_bench_fma_peak", "b2f_set_accum_mode", "b2f_launch_count", "b2f_reset_launch_count", "b2f_last_path",
 ]
 
 
@@ -182,6 +184,7 @@ class Library:
         d.b2f_memcpy_h2d.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
         d.b2f_memcpy_d2h.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
         d.b2f_set_device.argtypes = [C.c_int]
+        d.b2f_set_accum_mode.argtypes = [C.c_int32]
         d.b2f_device_count.argtypes = [C.POINTER(C.c_int)]
         d.b2f_sm_count.argtypes = [C.POINTER(C.c_int)]
         d.b2f_ipc_export.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
@@ -248,6 +251,13 @@ class Library:
 
     def is_device_library(self) -> bool:
         return bool(self.dll.b2f_is_device_library())
+
+    def set_accum_mode(self, mode: int) -> int:
+        """b2f_set_accum_mode: ACCUM_EXACT (0) / ACCUM_FMA (1) for the calling thread; returns the previous mode."""
+        prev = int(self.dll.b2f_set_accum_mode(int(mode)))
+        if prev < 0:
+            self.check(prev)
+        return prev
 
     def sm_count(self) -> int:
         n = C.c_int()

@@ -33,6 +33,8 @@ int fail(int code, const char *fmt, ...) {
 }
 void set_path(const char *name) { g_path = name; }
 void count_launch(int n) { g_launches += n; }
+static thread_local int g_accum = B2F_ACCUM_EXACT;
+int accum_mode() { return g_accum; }
 
 int sm_count() {
     static thread_local int cached_dev = -1, cached = 0;
@@ -238,6 +240,12 @@ int b2f_is_device_library(void) { return 1; }
 int64_t b2f_launch_count(void) { return g_launches; }
 void b2f_reset_launch_count(void) { g_launches = 0; }
 const char *b2f_last_path(void) { return g_path.c_str(); }
+int b2f_set_accum_mode(int32_t mode) {
+    if (mode != B2F_ACCUM_EXACT && mode != B2F_ACCUM_FMA) return fail(B2F_EARG, "unknown accumulate mode %d", (int)mode);
+    const int prev = g_accum;
+    g_accum = mode;
+    return prev;
+}
 
 int b2f_set_device(int device) { B2F_CUDA(cudaSetDevice(device)); return 0; }
 int b2f_device_count(int *count) {

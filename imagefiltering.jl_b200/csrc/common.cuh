@@ -17,6 +17,7 @@ int fail(int code, const char *fmt, ...);
 int sm_count();
 void set_path(const char *name);
 void count_launch(int n = 1);
+int accum_mode();            // B2F_ACCUM_* of the calling thread (b2f_set_accum_mode)
 #define B2F_CUDA(expr)                                                                         \
     do {                                                                                       \
         cudaError_t e__ = (expr);                                                              \

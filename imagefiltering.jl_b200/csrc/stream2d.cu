@@ -48,6 +48,7 @@ static int run_typed(const Plan *plans, const void *d_img, int img_dt, void *con
     P.rx0 = (int)(P0.roi.lo[0] - P0.img_ax.lo[0]); P.ry0 = (int)(P0.roi.lo[1] - P0.img_ax.lo[1]);
     P.rw = (int)P0.roi.len(0); P.rh = (int)P0.roi.len(1);
     P.style = P0.style; P.fill = (CT)P0.fill;
+    P.fma = accum_mode() == B2F_ACCUM_FMA;
     bool aligned = (P.out_pitch % PX == 0) && (P.out_plane % PX == 0) && ((P.rx0 - P.out_ox) % PX == 0);
     for (int p = 0; p < NPL; ++p) {
         P.out[p] = d_outs[p];

@@ -51,6 +51,7 @@ struct S2Params {
     int nsx, nsy;             // strips along x / y
     long long nstrips;        // nsx * nsy * batch
     int vec_ok;               // output rows are 16-byte aligned for every strip
+    int fma;                  // host side only: accum mode B2F_ACCUM_FMA (Float64 compute: fused multiply-add where instantiated)
     CT kx[NPL][S2_MAXTAPS];
     CT ky[NPL][S2_MAXTAPS];   // y taps, ascending (filled by the host set-up)
     CT kyt[NPL][S2_MAXTAPS];  // the same taps RIGHT-aligned in the instantiation's LBY slots (filled by the launcher)
@@ -115,7 +116,14 @@ __device__ __forceinline__ int s2_remap(int style, int i, int n) {
 // One input row r of a strip (u = r % RB, a literal after the caller's unrolling): stage 1 from the smem ring, stage 2
 // through the register pipeline, emit the finished output row o = r - (Ly-1).  Only output rows 0 <= o < th are
 // stored; everything else is computed and dropped.
-template <typename CT, int LXT, int LYT, int LB, int NPL, int RB, int ROT, bool XS, bool YS>
+// the multiply-accumulate of the kernel: common.cuh's mac (the reference's separate multiply and add for Float64), or — FMA,
+// accum mode B2F_ACCUM_FMA — one fused multiply-add (half the FP64 instructions, one rounding instead of two)
+template <typename CT, bool FMA> __device__ __forceinline__ CT s2_mac(CT acc, CT a, CT k) {
+    if constexpr (FMA && sizeof(CT) == 8) return fma(a, k, acc);
+    else return mac<CT>(acc, a, k);
+}
+
+template <typename CT, int LXT, int LYT, int LB, int NPL, int RB, int ROT, bool XS, bool YS, bool FMA>
 __device__ __forceinline__ void s2_row(const int u, const int r, const S2Params<CT, NPL> &P, const int Lx, const int Ly,
                                        const int th, const CT *__restrict__ sblk, const int lane,
                                        const int tw, const bool lane_full, const bool lane_live,
@@ -174,7 +182,7 @@ __device__ __forceinline__ void s2_row(const int u, const int r, const S2Params<
                 for (int p = 0; p < NPL; ++p) {
                     const CT kj = P.kx[p][j];
 #pragma unroll
-                    for (int q = 0; q < PX; ++q) mid[p][q] = mac<CT>(mid[p][q], v[q + j], kj);
+                    for (int q = 0; q < PX; ++q) mid[p][q] = s2_mac<CT, FMA>(mid[p][q], v[q + j], kj);
                 }
             }
         }
@@ -200,7 +208,7 @@ __device__ __forceinline__ void s2_row(const int u, const int r, const S2Params<
                 }
             } else {
 #pragma unroll
-                for (int q = 0; q < PX; ++q) fin[p][q] = mac<CT>(acc[p][LBY - 1][q], mid[p][q], kj);
+                for (int q = 0; q < PX; ++q) fin[p][q] = s2_mac<CT, FMA>(acc[p][LBY - 1][q], mid[p][q], kj);
             }
         }
 #pragma unroll
@@ -218,7 +226,7 @@ __device__ __forceinline__ void s2_row(const int u, const int r, const S2Params<
                         }
                     } else {
 #pragma unroll
-                        for (int q = 0; q < PX; ++q) acc[p][j + 1][q] = mac<CT>(acc[p][j][q], mid[p][q], kj);
+                        for (int q = 0; q < PX; ++q) acc[p][j + 1][q] = s2_mac<CT, FMA>(acc[p][j][q], mid[p][q], kj);
                     }
                 }
             }
@@ -252,7 +260,7 @@ __device__ __forceinline__ void s2_row(const int u, const int r, const S2Params<
     }
 }
 
-template <typename IT, typename CT, int LXT, int LYT, int LB, int NPL, int RB, int ROT, bool XS = true, bool YS = true>
+template <typename IT, typename CT, int LXT, int LYT, int LB, int NPL, int RB, int ROT, bool XS = true, bool YS = true, bool FMA = false>
 __global__ void __launch_bounds__(S2_WARPS * 32) stream2d_kernel(const __grid_constant__ S2Params<CT, NPL> P) {
     constexpr int PX = S2Vec<CT>::PX;
     constexpr int CW = 32 * PX;                              // strip width
@@ -364,7 +372,7 @@ __global__ void __launch_bounds__(S2_WARPS * 32) stream2d_kernel(const __grid_co
         fetch_block(blk + 1);                                     // loads fly while this block is computed
 #pragma unroll
         for (int u = 0; u < RB; ++u)
-            s2_row<CT, LXT, LYT, LB, NPL, RB, ROT, XS, YS>(u, rbase + u, P, Lx, Ly, th, sbuf + (blk & 1) * (RB * PW), lane, tw, lane_full,
+            s2_row<CT, LXT, LYT, LB, NPL, RB, ROT, XS, YS, FMA>(u, rbase + u, P, Lx, Ly, th, sbuf + (blk & 1) * (RB * PW), lane, tw, lane_full,
                                                            lane_live, acc, outp);
         park_block(blk + 1);
         __syncwarp();

@@ -6,7 +6,7 @@
 
 namespace b2f {
 
-template <typename IT, typename CT, int LXT, int LYT, int LB, int NPL, int RB, int ROT, bool XS = true, bool YS = true>
+template <typename IT, typename CT, int LXT, int LYT, int LB, int NPL, int RB, int ROT, bool XS = true, bool YS = true, bool FMA = false>
 static int s2_launch_one(const S2Params<CT, NPL> &P, cudaStream_t st) {
     constexpr int PX = S2Vec<CT>::PX;
     constexpr int LBX = XS ? (LXT ? LXT : LB) : 1;
@@ -24,7 +24,7 @@ static int s2_launch_one(const S2Params<CT, NPL> &P, cudaStream_t st) {
     }
     const long long blocks = (P.nstrips + S2_WARPS - 1) / S2_WARPS;
     if (blocks > 0x7fffffffLL) return fail(B2F_ENOTSUP, "stream2d grid too large");
-    stream2d_kernel<IT, CT, LXT, LYT, LB, NPL, RB, ROT, XS, YS><<<(unsigned)blocks, S2_WARPS * 32, smem, st>>>(Q);
+    stream2d_kernel<IT, CT, LXT, LYT, LB, NPL, RB, ROT, XS, YS, FMA><<<(unsigned)blocks, S2_WARPS * 32, smem, st>>>(Q);
     count_launch();
     B2F_CUDA(cudaGetLastError());
     return 0;
@@ -35,6 +35,20 @@ template <typename IT, typename CT, int NPL>
 static int s2_launch(const S2Params<CT, NPL> &P, cudaStream_t st) {
     const int Lx = P.Lx, Ly = P.Ly;
     const int L = Lx > Ly ? Lx : Ly;
+    // accum mode B2F_ACCUM_FMA is a permission, not an obligation: the fused form exists for Float64 compute with the hot tap
+    // counts (the reference-typed configs C1 = 13 x 13 and C2 = two 3 x 3 planes, and their neighbours)
+    if constexpr (sizeof(CT) == 8) {
+        if (P.fma) {
+            if (Lx == 3 && Ly == 3) return s2_launch_one<IT, CT, 3, 3, 4, NPL, 6, 3, true, true, true>(P, st);
+            if constexpr (NPL == 1) {
+                if (Lx == 5 && Ly == 5) return s2_launch_one<IT, CT, 5, 5, 8, 1, 3, 6, true, true, true>(P, st);
+                if (Lx == 7 && Ly == 7) return s2_launch_one<IT, CT, 7, 7, 8, 1, 4, 8, true, true, true>(P, st);
+                if (Lx == 9 && Ly == 9) return s2_launch_one<IT, CT, 9, 9, 16, 1, 3, 9, true, true, true>(P, st);
+                if (Lx == 13 && Ly == 13) return s2_launch_one<IT, CT, 13, 13, 16, 1, 4, 16, true, true, true>(P, st);
+                if (Lx == 17 && Ly == 17) return s2_launch_one<IT, CT, 17, 17, 20, 1, 3, 18, true, true, true>(P, st);
+            }
+        }
+    }
     if (Lx == 3 && Ly == 3) return s2_launch_one<IT, CT, 3, 3, 4, NPL, 6, 3>(P, st);
     if constexpr (NPL == 1) {
         if (Lx == 5 && Ly == 5) return s2_launch_one<IT, CT, 5, 5, 8, 1, 3, 6>(P, st);

@@ -470,3 +470,24 @@ def padarray(*args, _library=None):
     out = OffsetArray.with_first(np.empty(oshape, dtype=T, order="F"), lo)
     _run(None, out, desc, ndim, [], border, None, _library)
     return out
+
+
+
+class accum_mode:
+    """Context manager over b2f_set_accum_mode (include/b2f.h): `with accum_mode("fma"): imfilter(...)` lets the library fuse the
+    multiply and the add of Float64 accumulations (SURVEY Appendix C typing: the reference's Float64 results come from separate
+    multiplies and adds, which "exact" — the default — reproduces bit for bit)."""
+
+    def __init__(self, mode, _library=None):
+        self.mode = {"exact": _abi.ACCUM_EXACT, "fma": _abi.ACCUM_FMA}[mode] if isinstance(mode, str) else int(mode)
+        self._library = _library
+
+    def __enter__(self):
+        from ._lib import lib
+        self._lib = self._library if self._library is not None else lib()
+        self.prev = self._lib.set_accum_mode(self.mode)
+        return self
+
+    def __exit__(self, *exc):
+        self._lib.set_accum_mode(self.prev)
+        return False

@@ -170,6 +170,19 @@ int b2f_imfilter(const b2f_array *img, const b2f_array *out,
                  const int64_t *roi_lo, const int64_t *roi_hi,
                  void *stream);
 
+/* Accumulate mode of the Float64 arithmetic on the CALLING THREAD (like the current device; default B2F_ACCUM_EXACT):
+ *   B2F_ACCUM_EXACT  separate multiply and add, as the reference's `tmp += A[i+j]*k[j]` compiles on the CPU
+ *                    (src/imfilter.jl:732-737): Float64 outputs are bit-equal to the reference;
+ *   B2F_ACCUM_FMA    the library MAY fuse them (one rounding instead of two, half the FP64 instructions: the reference-typed
+ *                    configs — Float64 outputs of non-dyadic taps — are FP64-pipe-bound).  A permission, not an obligation:
+ *                    the fused form exists for the streamed 2-D kernel with 3x3 (1 or 2 planes), 5x5, 7x7, 9x9, 13x13 and
+ *                    17x17 taps; everything else computes as under B2F_ACCUM_EXACT.  Results differ from the reference's by
+ *                    at most the rounding of one product per tap (<= 1e-15 * prod_stage(sum|k|) * max|img|).
+ * Returns the previous mode, or a negative status for an unknown mode.  Float32 and integer arithmetic are unaffected. */
+#define B2F_ACCUM_EXACT 0
+#define B2F_ACCUM_FMA 1
+int b2f_set_accum_mode(int32_t mode);
+
 /* imgradients(img, kernelfun, border)  (src/specialty.jl:39-53): `nplanes` independent cascades
  * of `nstages_each` stages, all reading the same `img`; plane p uses
  * stages[p*nstages_each … (p+1)*nstages_each-1] and writes outs[p].  The product library reads

@@ -696,6 +696,8 @@ const char *b2f_last_error(void) { return g_err.c_str(); }
 int b2f_is_device_library(void) { return 0; }
 
 int b2f_set_device(int) { return 0; }
+// the oracle IS the exact arithmetic: the mode is accepted and ignored (B2F_ACCUM_FMA is a permission)
+int b2f_set_accum_mode(int32_t mode) { return (mode == 0 || mode == 1) ? 0 : fail(B2F_EARG, "unknown accumulate mode"); }
 int b2f_device_count(int *count) { if (count) *count = 0; return 0; }
 int b2f_sm_count(int *count) { if (count) *count = 0; return 0; }
 int b2f_bench_fma_peak(double *tfma_per_s, void *) { if (tfma_per_s) *tfma_per_s = 0.0; return 0; }

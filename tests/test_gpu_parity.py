@@ -738,3 +738,30 @@ def test_long_separable_factors(ifb, oracle, device, border, dt):
             pa, pb = _both(ifb, oracle, np.float64, img, (k,), b)
             assert device.last_path() == "sepnd"
             assert np.array_equal(pa, pb), (L, axis, border)
+
+
+def test_accum_mode_fma(ifb, oracle, device):
+    """b2f_set_accum_mode(B2F_ACCUM_FMA): Float64 outputs may come from fused multiply-adds.  Non-dyadic taps: within one
+    rounding per tap of the oracle (and not all bit-equal: the fused kernel really ran); dyadic taps on N0f8 data (Sobel): the
+    products are exact either way, so the result stays bit-equal.  The mode is per thread and restored by the context manager."""
+    rng = np.random.default_rng(77)
+    img = np.asfortranarray(rng.random((300, 211, 3), dtype=np.float32))
+    for sig, L in ((3, 13), (1, 5), (4, 17)):
+        kern = ifb.KernelFactors.gaussian((sig, sig, 0))
+        exact, ref = _both(ifb, oracle, np.float64, img, kern, "replicate")
+        assert np.array_equal(exact, ref)
+        with ifb.accum_mode("fma"):
+            fused = ifb.imfilter(np.float64, img, kern, "replicate")
+            assert device.last_path() == "stream2d"
+        tol = 1e-15 * float(np.prod([np.abs(k.data.parent).sum() for k in kern[:2]]))
+        assert np.max(np.abs(fused - ref)) <= tol
+        assert not np.array_equal(fused, ref), "the fused kernel did not run"
+        again = ifb.imfilter(np.float64, img, kern, "replicate")
+        assert np.array_equal(again, ref), "accum mode was not restored"
+    raw = ifb.n0f8(rng.integers(0, 256, size=(257, 130), dtype=np.uint8))
+    ref = ifb.imgradients(raw, ifb.KernelFactors.sobel, "reflect", _library=oracle)
+    with ifb.accum_mode("fma"):
+        g = ifb.imgradients(raw, ifb.KernelFactors.sobel, "reflect")
+    for a, b in zip(g, ref):
+        assert np.array_equal(a, b)
+    assert device.set_accum_mode(0) == 0
