@@ -364,9 +364,18 @@ static int imfilter_planes(const b2f_array *img, const b2f_array *outs, int npla
         for (int p = 0; p < nplanes; ++p) { dout[p] = souts[p].dptr; odt[p] = outs[p].dtype; }
         const char *force = getenv("B2F_FORCE_PATH");   // debugging knob: "fused2d" | "sepnd" | "generic"
         const bool allow_stream = !force, allow_fused = !force || !strcmp(force, "fused2d");
+        // 18 .. 32 taps: the chunked-tap passes of sepnd / longtap beat the shared-memory tiled fused2d (25 x 25 taps on
+        // 8192^2 Float32: 0.45 vs 1.15 ms, profiles/r2_longtap.jsonl) wherever sepnd applies (whole-array outputs)
+        bool long_taps = false;
+        for (int p = 0; p < nplanes; ++p)
+            for (int a : plans[p].active) {
+                const StageInfo &si = plans[p].stages[a];
+                if (si.s->kind == B2F_STAGE_1D && si.s->len[si.s->axis] > 17) long_taps = true;
+            }
+        const bool prefer_sepnd = !force && long_taps && nplanes == 1 && sepnd_applicable(plans[0], img->dtype, odt[0]);
         if (allow_stream && stream2d_applicable(plans.data(), nplanes, img->dtype, odt.data())) {
             rc = run_stream2d(plans.data(), nplanes, sin.dptr, img->dtype, dout.data(), odt.data(), st);
-        } else if (allow_fused && fused2d_applicable(plans.data(), nplanes, img->dtype, odt.data())) {
+        } else if (!prefer_sepnd && allow_fused && fused2d_applicable(plans.data(), nplanes, img->dtype, odt.data())) {
             rc = run_fused2d(plans.data(), nplanes, sin.dptr, img->dtype, dout.data(), odt.data(), st);
         } else {
             for (int p = 0; p < nplanes && !rc; ++p) {

@@ -124,66 +124,73 @@ __device__ __forceinline__ void lt_line8(const double *sp, const double *k, cons
 template <typename CT> struct LtPair { typedef CT type; };
 template <> struct LtPair<float> { typedef float2 type; };
 
-// The tile load.  Every thread issues its loads in batches of LT_UB independent, unconditional loads (out-of-range cells read
-// element 0 and are replaced afterwards): the load phase is latency-bound otherwise — a warp has ~24 cells to fetch and a
-// dependent address -> load -> store chain per cell costs a full DRAM round trip each.
-constexpr int LT_UB = 8;
+// Border remap in 32-bit arithmetic (axes are < 2^31, checked by the host side): the in-range test inline, the folds out of line
+// (common.cuh's 64-bit remap_index inlines two 64-bit divisions into every unrolled load).
+static __device__ __noinline__ int lt_remap_slow(int style, int i, int n) { return (int)remap_index(style, (int64_t)i, (int64_t)n); }
+__device__ __forceinline__ int lt_remap(int style, int i, int n) {
+    if ((unsigned)i < (unsigned)n) return i;
+    return lt_remap_slow(style, i, n);
+}
+
+// The tile load.  Every thread issues its loads in batches of independent, unconditional loads (cells outside the array read
+// element 0 of their line and are replaced afterwards): a dependent address -> load -> store chain per cell would cost a full
+// DRAM round trip each.  Cell codes: >= 0 source position, -1 Fill value, -2 not a cell of this thread, -3 padding (zero).
 template <typename IT, bool N0, typename CT>
-__device__ __forceinline__ void lt_load_tile(const LtParams<CT> &P, CT *tile, const long long line0, const long long out0,
-                                             const long long b, const long long nlines, const int npos, const int npos_pad) {
+__device__ __forceinline__ void lt_load_tile(const LtParams<CT> &P, CT *tile, const long long line0, const int out0, const long long b,
+                                             const long long nlines, const int npos, const int npos_pad) {
     const IT *src = reinterpret_cast<const IT *>(P.src);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     auto conv = [](IT x) -> CT { return N0 ? N0f8Conv<CT>::f((unsigned)x) : (CT)x; };
     if (P.along_x) {
         // lines = rows (stride W), positions contiguous: lanes run along the positions (coalesced), smem [pos][line]
-        const int per_line = (npos_pad + 31) >> 5, total = 4 * per_line;          // a warp loads lines warp, warp + 8, ...
-        for (int i0 = 0; i0 < total; i0 += LT_UB) {
-            IT x[LT_UB];
-            int st[LT_UB];                      // tile offset, or -1 (nothing to store), | flags in the two top bits
+        constexpr int UB = 6;
+        const int Wi = (int)P.W, p0 = out0 + P.klo;
+#pragma unroll 1
+        for (int ln = warp; ln < 32; ln += LT_NT / 32) {
+            const long long row = line0 + ln;
+            const bool rowok = row < nlines;
+            const IT *rp = src + (rowok ? row * P.W : 0);
+#pragma unroll 1
+            for (int q0 = lane; q0 < npos_pad; q0 += 32 * UB) {
+                IT x[UB];
+                int a[UB];
 #pragma unroll
-            for (int u = 0; u < LT_UB; ++u) {
-                const int i = i0 + u, li = i / per_line, ln = warp + 8 * li, q = (i - li * per_line) * 32 + lane;
-                const long long row = line0 + ln;
-                long long off = 0;
-                st[u] = -1;
-                if (i < total && q < npos_pad) {
-                    st[u] = q * LT_PITCH + ln;
-                    if (q < npos && row < nlines) {
-                        const long long a = remap_index(P.style, out0 + P.klo + q, P.W);
-                        if (a >= 0) { off = row * P.W + a; st[u] |= 1 << 30; } else st[u] |= 1 << 29;
-                    }
+                for (int u = 0; u < UB; ++u) {
+                    const int q = q0 + 32 * u;
+                    a[u] = q < npos_pad ? -3 : -2;
+                    if (q < npos && rowok) a[u] = lt_remap(P.style, p0 + q, Wi);
+                    x[u] = rp[a[u] >= 0 ? a[u] : 0];
                 }
-                x[u] = src[off];
-            }
 #pragma unroll
-            for (int u = 0; u < LT_UB; ++u)
-                if (st[u] >= 0) tile[st[u] & 0xFFFFFF] = (st[u] >> 30) & 1 ? conv(x[u]) : ((st[u] >> 29) & 1 ? P.fill : (CT)0);
+                for (int u = 0; u < UB; ++u)
+                    if (a[u] != -2) tile[(q0 + 32 * u) * LT_PITCH + ln] = a[u] >= 0 ? conv(x[u]) : (a[u] == -1 ? P.fill : (CT)0);
+            }
         }
     } else {
+        constexpr int UB = 8, NW = LT_NT / 32;
         const long long xg = line0 + lane;
         const bool xin = xg < nlines;
-        for (int q0 = warp; q0 < npos_pad; q0 += LT_UB * (LT_NT / 32)) {
-            IT x[LT_UB];
-            int st[LT_UB];
+        const int Hi = (int)P.H, Agi = (int)P.Ag, af = (int)P.a_first, p0 = af + out0 + P.klo;
+        const IT *cp = src + b * P.H * P.W + (xin ? xg : 0);
+#pragma unroll 1
+        for (int q0 = warp; q0 < npos_pad; q0 += NW * UB) {
+            IT x[UB];
+            int a[UB];
 #pragma unroll
-            for (int u = 0; u < LT_UB; ++u) {
-                const int q = q0 + u * (LT_NT / 32);
-                long long off = 0;
-                st[u] = -1;
-                if (q < npos_pad) {
-                    st[u] = 0;
-                    if (q < npos && xin) {
-                        long long a = remap_index(P.style, P.a_first + out0 + P.klo + q, P.Ag);
-                        if (a >= 0) a -= P.a_first;
-                        // a slab holds the planes its outputs need (checked by the caller); anything else is a Fill cell
-                        if (a >= 0 && a < P.H) { off = (b * P.H + a) * P.W + xg; st[u] = 2; } else st[u] = 1;
-                    }
+            for (int u = 0; u < UB; ++u) {
+                const int q = q0 + NW * u;
+                a[u] = q < npos_pad ? -3 : -2;
+                if (q < npos && xin) {
+                    int r = lt_remap(P.style, p0 + q, Agi);
+                    if (r >= 0) r -= af;
+                    // a slab holds the planes its outputs need (checked by the caller); anything else is a Fill cell
+                    a[u] = (r >= 0 && r < Hi) ? r : -1;
                 }
-                x[u] = src[off];
+                x[u] = cp[(long long)(a[u] >= 0 ? a[u] : 0) * P.W];
             }
 #pragma unroll
-            for (int u = 0; u < LT_UB; ++u)
-                if (st[u] >= 0) tile[(q0 + u * (LT_NT / 32)) * LT_PITCH + lane] = st[u] == 2 ? conv(x[u]) : (st[u] == 1 ? P.fill : (CT)0);
+            for (int u = 0; u < UB; ++u)
+                if (a[u] != -2) tile[(q0 + NW * u) * LT_PITCH + lane] = a[u] >= 0 ? conv(x[u]) : (a[u] == -1 ? P.fill : (CT)0);
         }
     }
 }
@@ -204,7 +211,8 @@ __global__ void __launch_bounds__(LT_NT) longtap_kernel(const __grid_constant__ 
     const long long ta = t % P.nta; t /= P.nta;
     const long long tl = t % P.ntl;
     const long long b = t / P.ntl;
-    const long long line0 = tl * 32, out0 = P.o0 + ta * LT_TO;        // first line / first output position of this tile
+    const long long line0 = tl * 32;                                  // first line of this tile
+    const int out0 = (int)(P.o0 + ta * LT_TO);                        // ... and its first output position (axes are < 2^31)
     const long long nlines = P.along_x ? P.H : P.W;
 
     for (int j = tid; j < Lp; j += LT_NT) {
@@ -229,16 +237,17 @@ __global__ void __launch_bounds__(LT_NT) longtap_kernel(const __grid_constant__ 
         const int g = warp + 8 * h;
         lt_line8(tile + (8 * g) * LT_PITCH + lane, k, kp, L, res[h]);
     }
-    const long long oend = P.o0 + P.on;
+    const int oend = (int)(P.o0 + P.on);
     if (!P.along_x) {
         const long long x = line0 + lane;
         if (x < nlines) {
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-                const long long o = out0 + 8 * (warp + 8 * h);
+                const int o = out0 + 8 * (warp + 8 * h);
+                CT *dp = P.dst + ((b * P.on + (o - (int)P.o0)) * P.W + x);
 #pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    if (o + i < oend) P.dst[(b * P.on + (o + i - P.o0)) * P.W + x] = res[h][i];
+                for (int i = 0; i < 8; ++i, dp += P.W)
+                    if (o + i < oend) *dp = res[h][i];
             }
         }
     } else {
@@ -250,10 +259,13 @@ __global__ void __launch_bounds__(LT_NT) longtap_kernel(const __grid_constant__ 
             for (int i = 0; i < 8; ++i) tile[(8 * g + i) * LT_PITCH + lane] = res[h][i];
         }
         __syncthreads();
-        for (int idx = tid; idx < 32 * LT_TO; idx += LT_NT) {
-            const int ln = idx >> 7, q = idx & (LT_TO - 1);
-            const long long row = line0 + ln, o = out0 + q;
-            if (row < nlines && o < oend) P.dst[row * P.on + (o - P.o0)] = tile[q * LT_PITCH + ln];
+        const int o = out0 + tid % LT_TO;                       // a thread stores one output position of 16 lines
+        if (o < oend) {
+#pragma unroll 4
+            for (int ln = tid / LT_TO; ln < 32; ln += LT_NT / LT_TO) {
+                const long long row = line0 + ln;
+                if (row < nlines) P.dst[row * P.on + (o - (int)P.o0)] = tile[(tid % LT_TO) * LT_PITCH + ln];
+            }
         }
     }
 }
@@ -281,7 +293,8 @@ int run_longtap(const void *src, int src_dt, CT *dst, const double *taps, int64_
     P.nta = (P.on + LT_TO - 1) / LT_TO;
     const long long blocks = P.ntl * P.nta * P.B;
     if (blocks <= 0) return 0;
-    if (blocks >= (1LL << 31)) return fail(B2F_ENOTSUP, "longtap: array too large for one launch");
+    if (blocks >= (1LL << 31) || axis_len >= (1LL << 31) - 4096 || P.Ag >= (1LL << 31) - 4096)
+        return fail(B2F_ENOTSUP, "longtap: array too large for one launch");
     const int Lp = ((int)L + 8) & ~7;
     const size_t smem = (size_t)Lp * sizeof(CT) * (sizeof(CT) == 4 ? 3 : 1) + (size_t)(LT_TO + Lp + 8) * LT_PITCH * sizeof(CT);
     static thread_local bool attr_set[2] = {false, false};

@@ -72,7 +72,7 @@ def test_separable_f32_tolerance(ifb, oracle, device, border, shape):
         assert pa.dtype == np.float32
         tol = _tol([k.data.parent for k in kf], img)
         assert np.max(np.abs(pa.astype(np.float64) - pb.astype(np.float64))) <= tol
-        assert device.last_path() in ("stream2d", "fused2d")
+        assert device.last_path() in ("stream2d", "fused2d", "sepnd")
         # float32 taps too (KernelFactors.gaussian(σ::Float32))
         kf32 = ifb.KernelFactors.gaussian(tuple(np.float32(s) for s in sig) + (np.float32(0),) * (nd - 2))
         pa, pb = _both(ifb, oracle, img, kf32, b)
