@@ -54,8 +54,8 @@ struct ShardCtx {
     uint64_t lower_slab_off = 0, upper_slab_off = 0, lower_sync_off = 0, upper_sync_off = 0;
     int64_t lower_planes = 0, upper_planes = 0;
     bool same_peer = false;              // two ranks with a circular wrap: one neighbour on both sides
-    cudaStream_t side = nullptr;
-    cudaEvent_t ev_go = nullptr, ev_done = nullptr;
+    cudaStream_t side = nullptr, side2 = nullptr;       // copy streams: lower halo / upper halo (different peers: they run concurrently)
+    cudaEvent_t ev_go = nullptr, ev_done = nullptr, ev_done2 = nullptr;
     uint32_t step = 0;
     int epoch = 0;
     bool staged_ok = true;
@@ -96,6 +96,8 @@ int b2f_shard_ctx_create(b2f_shard_ctx **ctx, int32_t rank, int32_t world) {
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->c.side, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->c.ev_go, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->c.ev_done, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->c.side2, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->c.ev_done2, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { delete p; return fail(B2F_ECUDA, "shard context: %s", cudaGetErrorString(e)); }
     *ctx = p;
@@ -175,6 +177,8 @@ int b2f_shard_ctx_destroy(b2f_shard_ctx *ctx) {
     if (c.side) cudaStreamDestroy(c.side);
     if (c.ev_go) cudaEventDestroy(c.ev_go);
     if (c.ev_done) cudaEventDestroy(c.ev_done);
+    if (c.side2) cudaStreamDestroy(c.side2);
+    if (c.ev_done2) cudaEventDestroy(c.ev_done2);
     delete ctx;
     return 0;
 }
@@ -371,6 +375,11 @@ int b2f_imfilter_sharded(b2f_shard_ctx *ctx, const b2f_array *img, const b2f_arr
         c.epoch = c.epoch % 255 + 1;
         B2F_CUDA(cudaEventRecord(c.ev_go, st));
         B2F_CUDA(cudaStreamWaitEvent(c.side, c.ev_go, 0));
+        // the upper halo comes from another GPU than the lower one: its copy runs on a second stream, concurrently (one stream
+        // would serialise 2 x 32 MB behind each other: ~100 us at link speed, as long as the first wave's march on a thin slab)
+        static const bool two_streams = !(getenv("B2F_SHARD_STREAMS") && atoi(getenv("B2F_SHARD_STREAMS")) == 1);
+        cudaStream_t hs = two_streams ? c.side2 : c.side;
+        if (two_streams && use_hi) B2F_CUDA(cudaStreamWaitEvent(c.side2, c.ev_go, 0));
         const size_t row_bytes = (size_t)img->dims[0] * esz;
         const int64_t nrows = plane_elems / img->dims[0];
         // copy order = order of need: the rows of the lower halo the first wave of tiles reads, the upper halo (read when the
@@ -386,8 +395,9 @@ int b2f_imfilter_sharded(b2f_shard_ctx *ctx, const b2f_array *img, const b2f_arr
             B2F_CUDA(cudaMemsetAsync(c.flags, c.epoch, 1, c.side));
         }
         if (use_hi) {
-            B2F_CUDA(cudaMemcpyAsync(c.recv_hi, peer_hi, (size_t)h_hi * plane_bytes, cudaMemcpyDefault, c.side));
-            B2F_CUDA(cudaMemsetAsync(c.flags + 2, c.epoch, 1, c.side));
+            B2F_CUDA(cudaMemcpyAsync(c.recv_hi, peer_hi, (size_t)h_hi * plane_bytes, cudaMemcpyDefault, hs));
+            B2F_CUDA(cudaMemsetAsync(c.flags + 2, c.epoch, 1, hs));
+            if (two_streams) B2F_CUDA(cudaEventRecord(c.ev_done2, c.side2));
         }
         if (use_lo) {
             if (early)
@@ -402,6 +412,7 @@ int b2f_imfilter_sharded(b2f_shard_ctx *ctx, const b2f_array *img, const b2f_arr
                                       use_lo ? h_lo : 0, use_hi ? c.recv_hi : nullptr, use_hi ? h_hi : 0, c.flags, c.flags + 2, c.epoch,
                                       (int32_t)early, stream);
         B2F_CUDA(cudaStreamWaitEvent(st, c.ev_done, 0));
+        if (two_streams && use_hi) B2F_CUDA(cudaStreamWaitEvent(st, c.ev_done2, 0));
         if (rc != B2F_ENOTSUP) return rc;
         c.staged_ok = false;               // not the fused kernel / not TMA-capable: direct peer reads from now on
     }

@@ -398,6 +398,9 @@ stream3d_kernel4(const __grid_constant__ S3Params P, const __grid_constant__ S3V
                 else s3_y_task4<LXT, LYT, LZT>(P, xa0 + XFSZ * 4, mb, Ly);
             }
             const float m0[4] = {ma[0].x, ma[0].y, ma[1].x, ma[1].y}, m1[4] = {mb[0].x, mb[0].y, mb[1].x, mb[1].y};
+            // as in the steady state: the next step's barrier is tested a z stage ahead of its use (ramp-up and drain are 13 of
+            // the 72 steps of a 128-plane slab)
+            ok = s3_mbar_test(xfull + 8 * (bi == 2 ? 0 : bi + 1), bi == 2 ? (ph ^ 1) : ph);
             s4_z_step<LXT, LYT, LZT, CS, false>(P, TZ, acc, m0, m1, Lz, op, nrow, false, o >= 0 && o < nout && nrow > 0,
                                                 o + 1 >= 0 && o + 1 < nout && nrow > 0);
         }
