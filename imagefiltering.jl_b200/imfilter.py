@@ -21,10 +21,10 @@ from .border import AbstractBorder, Fill, Inner, NA, NoPad, Pad, borderinstance
 from .color import ColorArray, lift_kernel
 from .device import DeviceArray
 from .kernel import Laplacian
-from .kernelfactors import ReshapedOneD
+from .kernelfactors import ReshapedOneD, TriggsSdika
 from .n0f8 import N0f8Array, n0f8
 from .offsetarrays import OffsetArray, centered
-from .resources import AbstractResource, Alg, CUDALibs, FIR, FIRTiled
+from .resources import AbstractResource, Alg, CUDALibs, FIR, FIRTiled, IIR
 
 STAGE_LAPLACIAN = 2
 
@@ -62,6 +62,8 @@ def _mul_type(S, K):
 def _kernel_dtype(k):
     if isinstance(k, Laplacian):
         return None
+    if isinstance(k, TriggsSdika):
+        return k.dtype
     if isinstance(k, (ReshapedOneD, OffsetArray)):
         return k.dtype
     return np.asarray(k).dtype
@@ -259,6 +261,99 @@ def _split_tail(args):
     return borderinstance(border), alg
 
 
+# ---- IIR (Triggs-Sdika) kernels: src/imfilter.jl:890-1092 -------------------------------------------------------------
+def _iir_factors(kernel, ndim=None):
+    """-> [(axis, TriggsSdika), ...] when every factor of `kernel` is an IIR filter, None when none is (the FIR ladder goes
+    on).  A bare TriggsSdika in position d of a tuple filters axis d (_imfilter_inplace_tuple!, :946-960); a ReshapedOneD
+    carries its axis.  Tuples mixing FIR and IIR factors are the reference's Algorithm.Mixed (outside this package)."""
+    ks = kernel if isinstance(kernel, tuple) else (kernel,)
+    is_iir = [isinstance(k, TriggsSdika) or (isinstance(k, ReshapedOneD) and isinstance(k.data, TriggsSdika)) for k in ks]
+    if not any(is_iir):
+        return None
+    if not all(is_iir):
+        raise NotSupportedError("kernels mixing FIR and IIR factors (Algorithm.Mixed) are outside the accelerated path")
+    out = []
+    for d, k in enumerate(ks):
+        if isinstance(k, ReshapedOneD):
+            if ndim is not None and k.N != ndim:
+                raise DimensionMismatch(f"kernel factor is for {k.N}-d arrays, image has {ndim} dims")
+            out.append((k.Npre, k.data))
+        else:
+            out.append((d, k))
+    if ndim is not None and len(out) > ndim:
+        raise DimensionMismatch("cannot have more kernels than dimensions")
+    return out
+
+
+def _iir_border(border):
+    if isinstance(border, NA):
+        return border
+    if isinstance(border, Fill):
+        return border
+    if isinstance(border, Pad) and border.style == "replicate":
+        return border
+    raise ArgumentError('only "replicate" is supported')                 # src/imfilter.jl:897
+
+
+def _iir_abi_border(border, ndim):
+    return (Fill(border.value) if isinstance(border, Fill) else Pad("replicate")).to_abi(ndim)
+
+
+def _run_iir(L, odesc, img_desc, ndim, factors, border):
+    """The cascade: the first factor reads img, the later ones filter out in place (:946-960)."""
+    if isinstance(border, NA):
+        return _run_iir_na(L, odesc, img_desc, ndim, factors, border)
+    b = _iir_abi_border(border, ndim)
+    src = img_desc
+    if not factors:
+        raise ArgumentError("empty IIR kernel")
+    for axis, k in factors:
+        L.iir(src, odesc, axis, k.coefficients(), b)
+        src = odesc
+
+
+def _run_iir_na(L, odesc, img_desc, ndim, factors, border):
+    """imfilter!(r, out, img, kernel::Tuple{IIR...}, NA(na)): src/imfilter.jl:282-318 with the IIR methods :1094-1108 (NaNs:
+    zero them, filter image and validity mask in place with Fill(0), divide) and :1222-1232 (no NaNs: filter with Fill(0),
+    divide by the per-axis responses to a vector of ones)."""
+    if odesc.dtype not in (_abi.F32, _abi.F64):
+        raise NotSupportedError("NA() needs a Float32 / Float64 output")
+    dims = [int(odesc.dims[d]) for d in range(ndim)]
+    can_na = img_desc.dtype in (_abi.F32, _abi.F64)
+    hasna = L.na_prepare(img_desc, border.mode) if can_na else False
+    fill0 = Fill(0)
+    if not hasna:
+        if len(factors) != ndim:
+            raise TypeError("MethodError: no method matching normalize_separable! (one kernel factor per dimension)")
+        _run_iir(L, odesc, img_desc, ndim, factors, fill0)
+        facs = [None] * ndim
+        for axis, k in factors:
+            ones = np.ones(dims[axis])
+            d1 = _abi.numpy_array_desc(ones, (1,))
+            L.iir(d1, d1, 0, k.coefficients(), fill0.to_abi(1))
+            facs[axis] = ones
+        L.normalize_dims(odesc, facs)
+        return
+    n = int(np.prod(dims))
+    origin = [int(img_desc.origin[d]) for d in range(ndim)]
+    if img_desc.mem == _abi.DEVICE:
+        p = L.malloc(n * _abi.DTYPE_SIZE[odesc.dtype])
+        valid = _abi.make_array(p, odesc.dtype, dims, origin, _abi.DEVICE)
+    else:
+        p = None
+        va = np.empty(dims, dtype=_abi.DTYPE_TO_NP[odesc.dtype], order="F")
+        valid = _abi.numpy_array_desc(va, origin)
+    try:
+        L.na_prepare(img_desc, border.mode, odesc, valid)
+        _run_iir(L, odesc, odesc, ndim, factors, fill0)
+        _run_iir(L, valid, valid, ndim, factors, fill0)
+        L.divide(odesc, valid)
+    finally:
+        if p is not None:
+            L.check(L.dll.b2f_sync())
+            L.free(p)
+
+
 def imfilter(*args, _library=None):
     """imfilter([r], [T], img, kernel, [border], [alg]) -> filtered array   (src/imfilter.jl:2-49)."""
     args = list(args)
@@ -271,9 +366,18 @@ def imfilter(*args, _library=None):
     if r is not None and alg is not None:
         raise TypeError("MethodError: a resource and an algorithm cannot both be given")
     r_given = r is not None
-    r = _resolve_resource(r, alg)
+    iir = _iir_factors(kernel)
+    r = _resolve_resource(r, alg, iir is not None)
     if isinstance(img, ColorArray):
         return _imfilter_color(r, T, img, kernel, border, _library)
+    if iir is not None:
+        T = np.dtype(T if T is not None else filter_type(img, kernel))
+        desc, ndim, first, shape, keep = _as_input(img)
+        factors = _iir_factors(kernel, ndim)
+        out = allocate_output(T, first, shape, [], Pad("replicate"))
+        from ._lib import lib
+        _run_iir(_library if _library is not None else lib(), _as_output(out)[0], desc, ndim, factors, _iir_border(border))
+        return out
     if T is None:
         T = filter_type(img, kernel)
     T = np.dtype(T)
@@ -317,7 +421,15 @@ def _imfilter_color(r, T, img, kernel, border, library):
     return ColorArray(out)
 
 
-def _resolve_resource(r, alg):
+def _resolve_resource(r, alg, iir=False):
+    """filter_algorithm (src/imfilter.jl:1200-1209): all-IIR kernels run Algorithm.IIR(), everything else FIR."""
+    if iir:
+        given = r.settings if r is not None else alg
+        if r is not None and not isinstance(r, CUDALibs):
+            raise NotSupportedError(f"{r!r}: this package has no CPU execution path")
+        if given is not None and not isinstance(given, IIR):
+            raise TypeError(f"MethodError: no method matching imfilter! for an IIR kernel with {given!r}")
+        return CUDALibs(IIR())
     if r is None:
         if alg is not None and not isinstance(alg, (FIR, FIRTiled)):
             raise NotSupportedError(f"{alg!r} is outside the accelerated FIR path")
@@ -336,10 +448,25 @@ def imfilter_(*args, _library=None):
     inds = None
     if rest and isinstance(rest[-1], (tuple, list)) and rest[-1] and isinstance(rest[-1][0], (range, tuple, list)):
         inds = rest.pop()
+    dim = None
+    if isinstance(kernel, TriggsSdika) and rest and isinstance(rest[0], (int, np.integer)):
+        dim = int(rest.pop(0))                  # imfilter!(r, out, img, kernel::TriggsSdika, dim, border), 1-based (:922)
     border, alg = _split_tail(rest)
     if r is not None and alg is not None:
         raise TypeError("MethodError: a resource and an algorithm cannot both be given")
-    r = _resolve_resource(r, alg)
+    iir = _iir_factors(kernel)
+    r = _resolve_resource(r, alg, iir is not None)
+    if iir is not None:
+        desc, ndim, first, shape, keep = _as_input(img)
+        factors = [(dim - 1, kernel)] if dim is not None else _iir_factors(kernel, ndim)
+        if dim is not None and not 1 <= dim <= ndim:
+            raise DimensionMismatch(f"dimension {dim} outside a {ndim}-d array")
+        odesc, okeep = _as_output(out)
+        if odesc.ndim != ndim or any(int(odesc.dims[d]) != int(desc.dims[d]) for d in range(ndim)):
+            raise DimensionMismatch("out must have the axes of img")
+        from ._lib import lib
+        _run_iir(_library if _library is not None else lib(), odesc, desc, ndim, factors, _iir_border(border))
+        return out
     if not isinstance(kernel, tuple):
         kernel = factorkernel(kernel)
     desc, ndim, first, shape, keep = _as_input(img)

@@ -14,10 +14,67 @@ from ._abi import ArgumentError
 from .offsetarrays import OffsetArray, centered
 
 
+class TriggsSdika:
+    """TriggsSdika(a, b, scale, M) / TriggsSdika(ab, scale)  (src/kernelfactors.jl:463-505): a recursive (IIR) 1-D filter with a
+    forward filter `a`, a backward filter `b` (3 coefficients each), the Triggs-Sdika boundary matrix `M` (3 x 3) and a final
+    `scale`.  Coefficients are numpy scalars of one float type T; every derived quantity is computed in T, in the reference's
+    order of operations."""
+    __slots__ = ("a", "b", "scale", "M", "asum", "bsum", "dtype")
+
+    def __init__(self, a, b=None, scale=None, M=None, dtype=None):
+        if scale is None:                            # TriggsSdika(ab, scale)
+            b, scale = None, b
+        T = np.dtype(dtype if dtype is not None else np.result_type(*[np.asarray(x).dtype for x in a])).type
+        if np.dtype(T).kind != "f":
+            T = np.float64
+        a = tuple(T(x) for x in a)
+        if len(a) != 3:
+            raise ArgumentError("only length 3 filters are currently supported")
+        if b is None:
+            a1, a2, a3 = a
+            one = T(1)
+            Mdenom = (one + a1 - a2 + a3) * (one - a1 - a2 - a3) * (one + a2 + (a1 - a3) * a3)
+            M = [[-a3 * a1 + one - a3 * a3 - a2, (a3 + a1) * (a2 + a3 * a1), a3 * (a1 + a3 * a2)],
+                 [a1 + a3 * a2, -(a2 - one) * (a2 + a3 * a1), -(a3 * a1 + a3 * a3 + a2 - one) * a3],
+                 [a3 * a1 + a2 + a1 * a1 - a2 * a2, a1 * a2 + a3 * (a2 * a2) - a1 * (a3 * a3) - a3 * a3 * a3 - a3 * a2 + a3,
+                  a3 * (a1 + a3 * a2)]]
+            M = [[T(x / Mdenom) for x in row] for row in M]
+            b = a
+        else:
+            b = tuple(T(x) for x in b)
+            if len(b) != 3:
+                raise ArgumentError("only length 3 filters are currently supported")
+            M = [[T(x) for x in row] for row in np.asarray(M).reshape(3, 3)]
+        self.a, self.b, self.scale, self.M = a, b, T(scale), M
+        self.asum = (a[0] + a[1]) + a[2]
+        self.bsum = (b[0] + b[1]) + b[2]
+        self.dtype = np.dtype(T)
+
+    @property
+    def ndim(self):
+        return 1
+
+    def iscopy(self):
+        """src/imfilter.jl:1254"""
+        return all(x == 0 for x in self.a) and all(x == 0 for x in self.b) and self.scale == 1
+
+    def coefficients(self):
+        """The 18 doubles of b2f_iir (include/b2f.h): a[3], b[3], scale, M[9] row-major, 1 - asum, 1 - bsum (both formed in T)."""
+        T = self.dtype.type
+        return np.array(list(self.a) + list(self.b) + [self.scale] + [x for row in self.M for x in row] +
+                        [T(1) - self.asum, T(1) - self.bsum], dtype=np.float64)
+
+    def __repr__(self):
+        return f"TriggsSdika{{{self.dtype}}}(a={tuple(float(x) for x in self.a)}, scale={float(self.scale)})"
+
+
 class ReshapedOneD:
     __slots__ = ("N", "Npre", "data")
 
     def __init__(self, N, Npre, data):
+        if isinstance(data, TriggsSdika):            # an IIR factor acting on axis Npre (src/kernelfactors.jl:560-565, iirg)
+            self.N, self.Npre, self.data = int(N), int(Npre), data
+            return
         if not isinstance(data, OffsetArray):
             data = OffsetArray.with_first(np.asarray(data), (1,))
         if data.ndim != 1:
@@ -35,7 +92,8 @@ class ReshapedOneD:
     @property
     def axes(self):
         ax = [range(0, 1)] * self.N
-        ax[self.Npre] = self.data.axes[0]
+        if not isinstance(self.data, TriggsSdika):   # Base.axes1(::TriggsSdika) = 0:0
+            ax[self.Npre] = self.data.axes[0]
         return tuple(ax)
 
     def dense(self):
@@ -156,3 +214,45 @@ def gaussian(sigma, l=None):
         ls = [None] * len(sigma) if l is None else list(l)
         return kernelfactors(tuple(_gaussian1(s, ll) for s, ll in zip(sigma, ls)))
     return _gaussian1(sigma, l)
+
+
+def _iirgaussian1(T, sigma, emit_warning=True):
+    """IIRGaussian(T, σ)  (src/kernelfactors.jl:533-549; Young, van Vliet & van Ginkel 2002).  The reference forms q in the
+    arithmetic of σ mixed with Float64 literals (i.e. Float64), converts it to T and continues in T."""
+    import warnings
+    if emit_warning and sigma < 1 and sigma != 0:
+        warnings.warn("σ is too small for accuracy")
+    T = np.dtype(T).type
+    sg = float(sigma)
+    m0, m1, m2 = T(1.16680), T(1.10783), T(1.40586)
+    q = T(1.31564 * (math.sqrt(1 + 0.490811 * sg * sg) - 1))
+    two, three, four = T(2), T(3), T(4)
+    ascale = (m0 + q) * (m1 * m1 + m2 * m2 + (two * m1) * q + q * q)
+    t = (m0 * (m1 * m1 + m2 * m2)) / ascale
+    B = t * t
+    a1 = (q * ((two * m0) * m1 + m1 * m1 + m2 * m2 + (two * m0 + four * m1) * q + (three * q) * q)) / ascale
+    a2 = ((-q * q) * (m0 + two * m1 + three * q)) / ascale
+    a3 = ((q * q) * q) / ascale
+    return TriggsSdika((a1, a2, a3), B, dtype=T)
+
+
+def _iirgt(sigma):
+    return np.float32 if isinstance(sigma, np.float32) else np.float64
+
+
+def IIRGaussian(*args, emit_warning=True):
+    """IIRGaussian([T], σ) -> TriggsSdika;  IIRGaussian([T], (σ1, σ2, …)) -> tuple of IIR factors, one per dimension
+    (src/kernelfactors.jl:517-565).  T defaults to the float type of σ (Float64 for Python numbers)."""
+    args = list(args)
+    T = None
+    if len(args) == 2:
+        T, sigma = args
+    else:
+        (sigma,) = args
+    if isinstance(sigma, (tuple, list, np.ndarray)):
+        sig = tuple(sigma)
+        if T is None:
+            T = np.result_type(*[_iirgt(x) for x in sig])
+        N = len(sig)
+        return tuple(ReshapedOneD(N, d, _iirgaussian1(T, x, emit_warning)) for d, x in enumerate(sig))
+    return _iirgaussian1(T if T is not None else _iirgt(sigma), sigma, emit_warning)

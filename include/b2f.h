@@ -366,6 +366,20 @@ int b2f_divide(const b2f_array *out, const b2f_array *den, void *stream);
  * vector of length dims[d] per axis.  Synchronous. */
 int b2f_normalize_dims(const b2f_array *out, const double *const *factors, void *stream);
 
+/* ---- IIR filtering -----------------------------------------------------------------------------------
+ * imfilter!(r, out, img, kernel::TriggsSdika, dim, border)   replaces src/imfilter.jl:922-1092 (_imfilter_dim!, leftborder!,
+ * rightborder!, rightΔu): a Young / van Vliet recursive filter along ONE axis with Triggs-Sdika boundary conditions —
+ * forward recursion u[i] = x[i] + a1 u[i-1] + a2 u[i-2] + a3 u[i-3] started from the steady state of the value left of the
+ * line, backward recursion v[i] = u[i] + b1 v[i+1] + b2 v[i+2] + b3 v[i+3] started from M (u[n-1..n-3] - u+) + v+, final
+ * scaling.  `coef` holds 18 doubles: a[3], b[3], scale, M[9] (row-major), 1 - sum(a), 1 - sum(b) (the last two formed in the
+ * kernel's own float type, as the reference does).  `border` is B2F_REPLICATE (the line's first / last element continues) or
+ * B2F_FILL (border->fill continues); anything else is B2F_EARG ("only replicate is supported", src/imfilter.jl:897).  out is
+ * F32 or F64 and every operation (separate multiplies and adds, in the reference's order) is carried out in eltype(out); img
+ * may be any real eltype and may BE out (the filter is in-place safe, :890).  A line of 3 or fewer elements is B2F_EDIM
+ * (:981-983).  The cascade over several axes (IIRGaussian((s1, s2, ...))) is one call per axis, the later ones in place on
+ * out (_imfilter_inplace_tuple!, :946-960).  A kernel that is a copy (all a, b zero and scale 1, :1254) copies. */
+int b2f_iir(const b2f_array *img, const b2f_array *out, int32_t axis, const double *coef, const b2f_border *border, void *stream);
+
 /* Measured FP32 multiply-add peak of the current GPU in TFMA/s (a pure fma.rn.f32x2 loop, best of 3, CUDA-event timed): the
  * denominator bench.py reports the dense-kernel path against.  Synchronous.  (The oracle library returns 0.) */
 int b2f_bench_fma_peak(double *tfma_per_s, void *stream);

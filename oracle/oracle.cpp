@@ -1413,3 +1413,80 @@ extern "C" int b2f_mapwindow_reduce(const b2f_array *img, const b2f_array *out, 
                                     const b2f_border *border, const int64_t *idx_first, const int64_t *idx_step, void *) {
     return o_mapwindow_reduce(img, out, op, win_lo, win_hi, border, idx_first, idx_step);
 }
+
+
+// ---- IIR: imfilter!(r, out, img, kernel::TriggsSdika, dim, border) (reference src/imfilter.jl:922-1092) ---------------------
+// One line at a time, every operation in T = eltype(out), separate multiplies and adds in the reference's order (this file is
+// compiled with -ffp-contract=off).  The 3 x 3 product kernel.M * rightΔu is StaticArrays' unrolled row . vector sum, taken here
+// as ((M[r,1] d1 + M[r,2] d2) + M[r,3] d3); its association inside StaticArrays is NOT pinned at the bit level (third-party,
+// not vendored) — the reference's own tests for this path (test/triggs.jl) are tolerance tests, restated in
+// tests/test_iir.py.
+namespace {
+template <typename T>
+int o_iir_typed(const b2f_array *img, const b2f_array *out, int axis, const double *coef, int style, double fill) {
+    const int N = img->ndim;
+    int64_t W = 1, H = img->dims[axis], B = 1;
+    for (int d = 0; d < axis; ++d) W *= img->dims[d];
+    for (int d = axis + 1; d < N; ++d) B *= img->dims[d];
+    const T a1 = (T)coef[0], a2 = (T)coef[1], a3 = (T)coef[2], b1 = (T)coef[3], b2 = (T)coef[4], b3 = (T)coef[5], scale = (T)coef[6];
+    T M[3][3];
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) M[r][c] = (T)coef[7 + 3 * r + c];
+    const T oma = (T)coef[16], omb = (T)coef[17];
+    const bool copy = a1 == 0 && a2 == 0 && a3 == 0 && b1 == 0 && b2 == 0 && b3 == 0 && scale == 1;     // iscopy, :1254
+    T *o = (T *)out->ptr;
+    std::vector<T> x((size_t)H);
+    for (int64_t bb = 0; bb < B; ++bb)
+        for (int64_t w = 0; w < W; ++w) {
+            const int64_t base = bb * H * W + w;
+            for (int64_t i = 0; i < H; ++i) {                      // accumfilter(img[i], one(T)): the pixel in T
+                int rc = load_as<T>(img->ptr, img->dtype, base + i * W, x[(size_t)i]);
+                if (rc) return fail(rc, "unsupported image eltype for IIR filtering");
+            }
+            auto O = [&](int64_t i) -> T & { return o[base + i * W]; };
+            if (copy) { for (int64_t i = 0; i < H; ++i) O(i) = x[(size_t)i]; continue; }
+            const int64_t n = H;
+            // leftborder!, :1017-1046
+            const T iminus = style == B2F_FILL ? (T)fill : x[0];
+            const T uminus = iminus / oma;
+            { T t = x[0]; t += a1 * uminus; t += a2 * uminus; t += a3 * uminus; O(0) = t; }
+            { T t = x[1]; t += a1 * O(0); t += a2 * uminus; t += a3 * uminus; O(1) = t; }
+            { T t = x[2]; t += a1 * O(1); t += a2 * O(0); t += a3 * uminus; O(2) = t; }
+            // forward, :990-998 (the last point is left to rightborder!)
+            for (int64_t i = 3; i <= n - 2; ++i) { T t = x[(size_t)i]; t += a1 * O(i - 1); t += a2 * O(i - 2); t += a3 * O(i - 3); O(i) = t; }
+            // rightborder!, :1048-1084
+            const T iplus = style == B2F_FILL ? (T)fill : x[(size_t)(n - 1)];
+            { T t = x[(size_t)(n - 1)]; t += a1 * O(n - 2); t += a2 * O(n - 3); t += a3 * O(n - 4); O(n - 1) = t; }
+            const T uplus = iplus / oma, vplus = uplus / omb;
+            const T d1 = O(n - 1) - uplus, d2 = O(n - 2) - uplus, d3 = O(n - 3) - uplus;
+            T vr[3];
+            for (int r = 0; r < 3; ++r) vr[r] = ((M[r][0] * d1 + M[r][1] * d2) + M[r][2] * d3) + vplus;
+            O(n - 1) = vr[0];
+            { T t = O(n - 2); t += b1 * O(n - 1); t += b2 * vr[1]; t += b3 * vr[2]; O(n - 2) = t; }
+            { T t = O(n - 3); t += b1 * O(n - 2); t += b2 * O(n - 1); t += b3 * vr[1]; O(n - 3) = t; }
+            // backward, :1003-1011
+            for (int64_t i = n - 4; i >= 0; --i) { T t = O(i); t += b1 * O(i + 1); t += b2 * O(i + 2); t += b3 * O(i + 3); O(i) = t; }
+            for (int64_t i = 0; i < n; ++i) O(i) *= scale;          // :1013-1017
+        }
+    return 0;
+}
+}  // namespace
+
+extern "C" int b2f_iir(const b2f_array *img, const b2f_array *out, int32_t axis, const double *coef, const b2f_border *border, void *) {
+    if (!img || !out || !coef || !border) return fail(B2F_EARG, "NULL argument");
+    const int N = img->ndim;
+    if (N < 1 || N > B2F_MAXDIM || out->ndim != N) return fail(B2F_EDIM, "IIR filtering needs 1..4 dims and equal rank");
+    if (axis < 0 || axis >= N) return fail(B2F_EARG, "axis %d outside the array", (int)axis);
+    for (int d = 0; d < N; ++d)
+        if (img->dims[d] != out->dims[d]) return fail(B2F_EDIM, "out must have the axes of img");
+    if (border->style != B2F_REPLICATE && border->style != B2F_FILL) return fail(B2F_EARG, "only \"replicate\" is supported");
+    if (out->dtype != B2F_F32 && out->dtype != B2F_F64) return fail(B2F_ENOTSUP, "IIR filtering produces Float32 / Float64 arrays");
+    if (o_numel(img) == 0) return 0;
+    bool copy = coef[6] == 1.0;
+    for (int i = 0; i < 6; ++i) copy = copy && coef[i] == 0.0;
+    if (!copy && img->dims[axis] <= 3)
+        return fail(B2F_EDIM, "size %lld of img along dimension %d is too small for filtering with IIR kernel of length 3",
+                    (long long)img->dims[axis], (int)axis + 1);
+    return out->dtype == B2F_F32 ? o_iir_typed<float>(img, out, axis, coef, border->style, border->fill)
+                                 : o_iir_typed<double>(img, out, axis, coef, border->style, border->fill);
+}
