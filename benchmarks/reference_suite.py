@@ -71,7 +71,7 @@ def main():
                     d_out = ifb.DeviceArray.from_torch(t_out)
                     dev_ms = best_of(lambda: ifb.imfilter_(d_out, d_in, kern, "replicate"), torch.cuda.synchronize, inner=20)
                     emit(name, path=path, out_eltype=str(np.dtype(T)), device_ms=dev_ms, host_ms=host_ms,
-                         device_gpixel_per_s=img.size / dev_ms / 1e6)
+                         device_gpixel_per_s=t_in.numel() / dev_ms / 1e6)
                 except Exception as e:                                  # a report: name the gap, keep going
                     emit(name, error=f"{type(e).__name__}: {e}")
             for kname in ("FFT",):

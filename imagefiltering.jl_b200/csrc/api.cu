@@ -385,6 +385,8 @@ static int imfilter_planes(const b2f_array *img, const b2f_array *outs, int npla
                     rc = run_sepnd(plans[p], sin.dptr, img->dtype, dout[p], odt[p], st);
                 else if (!force && dense2d_applicable(plans[p], img->dtype, odt[p]))
                     rc = run_dense2d(plans[p], sin.dptr, img->dtype, dout[p], odt[p], st);
+                else if (!force && dense3d_applicable(plans[p], img->dtype, odt[p]))
+                    rc = run_dense3d(plans[p], sin.dptr, img->dtype, dout[p], odt[p], st);
                 else
                     rc = run_generic(plans[p], sin.dptr, img->dtype, dout[p], odt[p], st);
             }

@@ -266,6 +266,9 @@ int run_stream3d_slab(const Plan &P, const void *own, const void *lo, int64_t lo
 // dense 2-D single stage (register-blocked FMA)
 bool dense2d_applicable(const Plan &P, int img_dt, int out_dt);
 int run_dense2d(const Plan &P, const void *d_img, int img_dt, void *d_out, int out_dt, cudaStream_t st);
+// dense 3-D single stage (shared-memory block, 4 outputs per thread)
+bool dense3d_applicable(const Plan &P, int img_dt, int out_dt);
+int run_dense3d(const Plan &P, const void *d_img, int img_dt, void *d_out, int out_dt, cudaStream_t st);
 // running extrema
 int run_extrema(const b2f_array *img, const void *d_img, void *d_min, void *d_max, int interleaved,
                 const Box &out_ax, const int64_t *wlo, const int64_t *whi, int style, double fill,

@@ -124,7 +124,7 @@ def test_generic_path_cases(ifb, oracle, device):
         for border in BORDERS + [ifb.Fill(0.3), ifb.Inner()]:
             pa, pb = _both(ifb, oracle, img, kern, border)
             assert np.array_equal(pa, pb), (img.shape, border)
-            assert device.last_path() in ("generic", "dense2d", "sepnd", "fused2d", "stream2d")
+            assert device.last_path() in ("generic", "dense2d", "dense3d", "sepnd", "fused2d", "stream2d")
 
 
 def test_integer_exact_and_inexact(ifb, oracle, device):
@@ -765,3 +765,30 @@ def test_accum_mode_fma(ifb, oracle, device):
     for a, b in zip(g, ref):
         assert np.array_equal(a, b)
     assert device.set_accum_mode(0) == 0
+
+
+@pytest.mark.parametrize("border", BORDERS + ["fill", "inner"])
+def test_dense3d_parity(ifb, oracle, device, border):
+    """One dense 3-D stage (csrc/dense3d.cu; reference loop src/imfilter.jl:624-669; its benchmark kernels 3x3x3 and the
+    13x13x13 DoG, benchmark/benchmarks.jl:36-49): Float64 outputs bit-exact (taps in column-major order, separate multiply and
+    add), Float32 within tolerance; asymmetric offsets, a 4-th batch axis, N0f8 input."""
+    rng = np.random.default_rng(seed_of(("dense3d", border)))
+    b = {"fill": ifb.Fill(0.3), "inner": ifb.Inner()}.get(border, border)
+    k3 = ifb.centered(rng.random((3, 3, 3)) - 0.4)
+    kdog = ifb.Kernel.DoG((2, 2, 2))
+    kasym = ifb.OffsetArray.with_first(rng.random((5, 2, 3)) - 0.5, (-1, 0, -2))
+    for shape, kern in (((40, 37, 21), k3), ((50, 33, 30), kdog), ((37, 20, 9), kasym), ((33, 9, 6, 3), k3)):
+        img = np.asfortranarray(rng.random(shape))
+        kk = kern
+        if len(shape) == 4:
+            kk = ifb.OffsetArray.with_first(kern.parent.reshape(kern.parent.shape + (1,)), tuple(kern.first) + (0,))
+        pa, pb = _both(ifb, oracle, img, (kk,), b)
+        assert device.last_path() == "dense3d", device.last_path()
+        assert pa.dtype == np.float64 and np.array_equal(pa, pb), (shape, border)
+    img32 = np.asfortranarray(rng.random((45, 31, 17), dtype=np.float32))
+    pa, pb = _both(ifb, oracle, np.float32, img32, (kdog,), b)
+    assert device.last_path() == "dense3d"
+    assert np.max(np.abs(pa.astype(np.float64) - pb.astype(np.float64))) <= _tol([kdog.parent], img32)
+    raw = ifb.n0f8(np.asfortranarray(rng.integers(0, 256, size=(35, 18, 11), dtype=np.uint8)))
+    pa, pb = _both(ifb, oracle, raw, (k3,), b)
+    assert device.last_path() == "dense3d" and np.array_equal(pa, pb)
