@@ -333,6 +333,107 @@ static int check_types(const b2f_array *img, const b2f_array *out, const Plan &P
     return 0;
 }
 
+// ---- pipelined host path -------------------------------------------------------------------------------------------------------
+// A large host-to-host call is PCIe-bound (C5: 4.3 GB up, 3 ms of kernel, 4.3 GB down).  When both arrays are pinned
+// (b2f_host_alloc / b2f_host_register) and the cascade has a slab form (b2f_imfilter_slab: separable, whole-array output), the
+// array is cut into chunks of planes along its last axis and the three phases run as a pipeline on three streams — upload of
+// chunk c+1, kernel of chunk c (its halo planes are its neighbours' planes in the same device buffer, the array's faces are
+// handled in global coordinates by the slab form), download of chunk c-1 — so that both directions of the link are busy at
+// once.  Results are those of the unpipelined call (the slab form is tested against the whole-array path plane by plane).
+struct HostPipe {
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    std::vector<cudaEvent_t> ev;
+    int device = -1;
+};
+static thread_local HostPipe g_pipe;
+
+static bool host_pinned(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+// returns 1 when the call was handled here, 0 when the ordinary path should run, < 0 on error
+static int imfilter_host_pipelined(const b2f_array *img, const b2f_array *out, const b2f_stage *stages, int nstages,
+                                   const b2f_border *border, const Plan &P, cudaStream_t st) {
+    static const bool enabled = !(getenv("B2F_HOST_PIPELINE") && atoi(getenv("B2F_HOST_PIPELINE")) == 0);
+    if (!enabled || img->mem != B2F_HOST || out->mem != B2F_HOST || img->ndim < 2 || getenv("B2F_FORCE_PATH")) return 0;
+    const int N = img->ndim, last = N - 1;
+    for (int d = 0; d < N; ++d)
+        if (img->dims[d] != out->dims[d] || img->origin[d] != out->origin[d]) return 0;
+    if (P.style > B2F_FILL || !sepnd_applicable(P, img->dtype, out->dtype)) return 0;
+    int64_t zlo = 0, zhi = 0;
+    for (int a : P.active) { zlo += P.stages[a].lo[last]; zhi += P.stages[a].hi[last]; }
+    const int64_t h_lo = zlo < 0 ? -zlo : 0, h_hi = zhi > 0 ? zhi : 0, h = h_lo > h_hi ? h_lo : h_hi;
+    if (P.style == B2F_CIRCULAR && h > 0) return 0;            // the wrap-around halo of the first chunk is the last one uploaded
+    int64_t plane = 1;
+    for (int d = 0; d < last; ++d) plane *= img->dims[d];
+    const int64_t Z = img->dims[last];
+    const size_t in_pb = (size_t)plane * dtype_size(img->dtype), out_pb = (size_t)plane * dtype_size(out->dtype);
+    if ((in_pb + out_pb) * (size_t)Z < ((size_t)64 << 20)) return 0;          // small calls: one upload, one launch, one download
+    int64_t nchunk = (int64_t)(((in_pb + out_pb) * (size_t)Z + ((size_t)32 << 20) - 1) / ((size_t)32 << 20));   // ~32 MiB per chunk
+    if (nchunk > 64) nchunk = 64;
+    while (nchunk > 1 && Z / nchunk < 2 * h + 1) --nchunk;
+    if (nchunk < 3) return 0;
+    if (!host_pinned(img->ptr) || !host_pinned(out->ptr)) return 0;      // pageable memory is staged synchronously: no overlap to win
+    int dev = 0;
+    B2F_CUDA(cudaGetDevice(&dev));
+    HostPipe &hp = g_pipe;
+    if (hp.device != dev) {
+        hp = HostPipe();
+        B2F_CUDA(cudaStreamCreateWithFlags(&hp.s_in, cudaStreamNonBlocking));
+        B2F_CUDA(cudaStreamCreateWithFlags(&hp.s_out, cudaStreamNonBlocking));
+        hp.ev.resize(2 * 64 + 2);
+        for (auto &e : hp.ev) B2F_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        hp.device = dev;
+    }
+    cudaEvent_t *ev_in = hp.ev.data(), *ev_k = hp.ev.data() + 64, ev_a = hp.ev[128], ev_done = hp.ev[129];
+    char *d_in = nullptr, *d_out = nullptr;
+    B2F_CUDA(cudaMallocAsync((void **)&d_in, in_pb * (size_t)Z, st));
+    AsyncFrees guard(st);
+    guard.push_back(d_in);
+    B2F_CUDA(cudaMallocAsync((void **)&d_out, out_pb * (size_t)Z, st));
+    guard.push_back(d_out);
+    B2F_CUDA(cudaEventRecord(ev_a, st));
+    B2F_CUDA(cudaStreamWaitEvent(hp.s_in, ev_a, 0));
+    B2F_CUDA(cudaStreamWaitEvent(hp.s_out, ev_a, 0));
+    const int64_t base = Z / nchunk, extra = Z % nchunk;
+    auto first_of = [&](int64_t c) { return c * base + (c < extra ? c : extra); };
+    for (int64_t c = 0; c < nchunk; ++c) {
+        const int64_t z0 = first_of(c), z1 = first_of(c + 1);
+        B2F_CUDA(cudaMemcpyAsync(d_in + (size_t)z0 * in_pb, (const char *)img->ptr + (size_t)z0 * in_pb, (size_t)(z1 - z0) * in_pb,
+                                 cudaMemcpyHostToDevice, hp.s_in));
+        B2F_CUDA(cudaEventRecord(ev_in[c], hp.s_in));
+    }
+    int rc = 0;
+    for (int64_t c = 0; c < nchunk && !rc; ++c) {
+        const int64_t z0 = first_of(c), z1 = first_of(c + 1);
+        B2F_CUDA(cudaStreamWaitEvent(st, ev_in[c + 1 < nchunk ? c + 1 : c], 0));          // the upper halo lives in the next chunk
+        b2f_array a = *img, o = *out;
+        a.mem = o.mem = B2F_DEVICE;
+        a.ptr = d_in + (size_t)z0 * in_pb;
+        o.ptr = d_out + (size_t)z0 * out_pb;
+        a.dims[last] = o.dims[last] = z1 - z0;
+        const int64_t nlo = z0 < h_lo ? z0 : h_lo, nhi = Z - z1 < h_hi ? Z - z1 : h_hi;
+        rc = b2f_imfilter_slab(&a, &o, stages, nstages, border, Z, z0, nlo ? d_in + (size_t)(z0 - nlo) * in_pb : nullptr, nlo,
+                               nhi ? d_in + (size_t)z1 * in_pb : nullptr, nhi, st);
+        if (rc) break;
+        B2F_CUDA(cudaEventRecord(ev_k[c], st));
+        B2F_CUDA(cudaStreamWaitEvent(hp.s_out, ev_k[c], 0));
+        B2F_CUDA(cudaMemcpyAsync((char *)out->ptr + (size_t)z0 * out_pb, d_out + (size_t)z0 * out_pb, (size_t)(z1 - z0) * out_pb,
+                                 cudaMemcpyDeviceToHost, hp.s_out));
+    }
+    // join: nothing may outlive the call (the buffers are freed on st, the caller owns the host arrays again)
+    cudaEventRecord(ev_done, hp.s_out);
+    cudaStreamWaitEvent(st, ev_done, 0);
+    cudaEventRecord(ev_done, hp.s_in);
+    cudaStreamWaitEvent(st, ev_done, 0);
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (rc) return rc < 0 ? rc : -rc;
+    if (e != cudaSuccess) return fail(B2F_ECUDA, "stream sync failed: %s", cudaGetErrorString(e));
+    return 1;
+}
+
 static int imfilter_planes(const b2f_array *img, const b2f_array *outs, int nplanes, const b2f_stage *stages,
                            int nstages_each, const b2f_border *border, const int64_t *roi_lo,
                            const int64_t *roi_hi, void *stream) {
@@ -350,6 +451,11 @@ static int imfilter_planes(const b2f_array *img, const b2f_array *outs, int npla
     if (nothing) { set_path("empty"); return 0; }
     int rc = ensure_ctx();
     if (rc) return rc;
+    if (nplanes == 1 && !roi_lo && !roi_hi) {
+        rc = imfilter_host_pipelined(img, &outs[0], stages, nstages_each, border, plans[0], st);
+        if (rc < 0) return rc;
+        if (rc == 1) return 0;
+    }
 
     bool any_host = img->mem == B2F_HOST;
     for (int p = 0; p < nplanes; ++p) any_host = any_host || outs[p].mem == B2F_HOST;

@@ -156,7 +156,9 @@ int b2f_ipc_close(void *dptr, uint64_t offset);
  * default stream).  Host arrays are copied to stream-ordered device allocations and back (cudaMemcpyAsync straight from /
  * to the caller's memory: at full PCIe speed when that memory is pinned — b2f_host_alloc or b2f_host_register — and through
  * the runtime's bounce buffers when it is pageable) and the call is synchronous; device arrays are used in place and the
- * call is asynchronous on `stream`.
+ * call is asynchronous on `stream`.  A host-to-host call of 64 MiB or more on PINNED arrays whose cascade has a slab form
+ * (b2f_imfilter_slab) runs as a three-stream pipeline over chunks of planes of the last axis — upload of chunk c+1, kernel of
+ * chunk c, download of chunk c-1 — so both directions of the PCIe link work at once (B2F_HOST_PIPELINE=0 turns it off).
  *
  * Arithmetic follows the reference's typing keyed on eltype(out):
  *   out F64           — double accumulate, separate multiply and add in tap order (bit-exact

@@ -792,3 +792,53 @@ def test_dense3d_parity(ifb, oracle, device, border):
     raw = ifb.n0f8(np.asfortranarray(rng.integers(0, 256, size=(35, 18, 11), dtype=np.uint8)))
     pa, pb = _both(ifb, oracle, raw, (k3,), b)
     assert device.last_path() == "dense3d" and np.array_equal(pa, pb)
+
+
+def test_pipelined_host_call_matches_plain_call(ifb, oracle, device):
+    """Large host-to-host calls on PINNED arrays run as an upload / kernel / download pipeline over chunks of planes
+    (csrc/api.cu, imfilter_host_pipelined).  Same result as the plain call on ordinary numpy arrays (bit for bit: the same
+    kernels, chunked through the slab form), and as the oracle on sampled blocks; 3-D cascade with halos between the chunks,
+    and a batch of 2-D images (no halo)."""
+    import ctypes as C
+    rng = np.random.default_rng(123)
+
+    def pinned(shape, dtype):
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = C.c_void_p()
+        device.check(device.dll.b2f_host_alloc(C.byref(p), n))
+        ctype = {4: C.c_float, 8: C.c_double}[np.dtype(dtype).itemsize]
+        a = np.ctypeslib.as_array(C.cast(p, C.POINTER(ctype)), shape=(int(np.prod(shape)),))
+        return p, a.reshape(shape, order="F")
+
+    for shape, kern, border, T in (((256, 192, 330), ifb.KernelFactors.gaussian((4, 4, 4)), "symmetric", np.float32),
+                                   ((200, 160, 520), ifb.KernelFactors.gaussian((2, 3, 1)), ifb.Fill(0.5), np.float64),
+                                   ((512, 384, 140), ifb.KernelFactors.gaussian((3, 3, 0)), "replicate", np.float32)):
+        pi, img = pinned(shape, np.float32)
+        po, out = pinned(shape, T)
+        try:
+            img[...] = rng.random(shape, dtype=np.float32)
+            ifb.imfilter_(out, img, kern, border)
+            path = device.last_path()
+            assert path in ("stream3d_slab", "slab"), path
+            plain = ifb.imfilter(T, np.asfortranarray(np.array(img)), kern, border)
+            assert device.last_path() not in ("stream3d_slab", "slab")
+            if T == np.float64:
+                assert np.array_equal(out, plain), shape
+            else:
+                tol = _tol([k.data.parent for k in kern], img)
+                assert np.max(np.abs(out - plain)) <= tol, shape
+            # the oracle on a block that spans a chunk boundary region and both faces of the last axis
+            for z0, z1 in ((0, 12), (shape[2] // 2 - 6, shape[2] // 2 + 6), (shape[2] - 12, shape[2])):
+                lo, hi = max(0, z0 - 8), min(shape[2], z1 + 8)
+                blk = np.asfortranarray(np.array(img[:64, :48, lo:hi]))
+                ref = ifb.imfilter(np.float64, blk, kern, border, _library=oracle)
+                # compare away from the block's artificial x / y / z faces
+                zz0 = z0 - lo if lo > 0 else 0
+                zz1 = (z1 - lo) if hi < shape[2] else blk.shape[2]
+                got = np.array(out[:40, :28, lo + zz0:lo + zz1], dtype=np.float64)
+                want = ref[:40, :28, zz0:zz1]
+                tol = (_tol([k.data.parent for k in kern], img) if T == np.float32 else 1e-12)
+                assert np.max(np.abs(got - want)) <= tol, (shape, z0)
+        finally:
+            device.dll.b2f_host_free(pi)
+            device.dll.b2f_host_free(po)
