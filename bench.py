@@ -254,12 +254,34 @@ class G:
         if self.world > 1:
             # pin the rank to its share of the host cores BEFORE any pinned host buffer is touched (first touch decides the
             # NUMA node): ranks of the first half of the GPUs take the first half of the cores
+            # — the cores NVML reports as local to this GPU when it can say (shared evenly among the ranks whose GPUs report
+            # the same set), else an even split of the visible cores
             try:
                 cores = sorted(os.sched_getaffinity(0))
-                per = max(1, len(cores) // self.world)
-                os.sched_setaffinity(0, cores[self.local * per:(self.local + 1) * per])
+                mine = None
+                try:
+                    import pynvml
+                    pynvml.nvmlInit()
+                    words = (max(cores) // 64) + 1
+
+                    def local_cores(i):
+                        m = pynvml.nvmlDeviceGetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(i), words)
+                        return tuple(c for c in cores if (int(m[c // 64]) >> (c % 64)) & 1)
+                    sets = [local_cores(i) for i in range(self.world)]
+                    same = [i for i in range(self.world) if sets[i] == sets[self.local]]
+                    if sets[self.local]:
+                        per = max(1, len(sets[self.local]) // len(same))
+                        k = same.index(self.local)
+                        mine = sets[self.local][k * per:(k + 1) * per]
+                except Exception:
+                    mine = None
+                if not mine:
+                    per = max(1, len(cores) // self.world)
+                    mine = cores[self.local * per:(self.local + 1) * per]
+                os.sched_setaffinity(0, mine)
+                self.host_cores = list(mine)
             except Exception:
-                pass
+                self.host_cores = None
             import datetime
             dist.init_process_group("nccl", device_id=self.dev, timeout=datetime.timedelta(seconds=180))
         self.stream = torch.cuda.current_stream()
