@@ -5,7 +5,7 @@ For every case two timings (CUDA events / wall clock around synchronous calls, b
   device_ms   arrays resident in HBM, output preallocated (imfilter! form) — the kernel path alone;
   host_ms     the public call on ordinary (pageable) numpy arrays, result returned as a numpy array: H2D + kernels + D2H,
               what a drop-in user of `imfilter(img, kernel, "replicate", Algorithm.FIR())` sees.
-Cases outside the accelerated path are listed with the reason (FFT, ROF, arbitrary window functions).  Prints one JSON line
+Cases outside the accelerated path are listed with the reason (ROF, arbitrary window functions).  Prints one JSON line
 per case.  python benchmarks/reference_suite.py [substring]"""
 import json
 import os
@@ -74,10 +74,21 @@ def main():
                          device_gpixel_per_s=t_in.numel() / dev_ms / 1e6)
                 except Exception as e:                                  # a report: name the gap, keep going
                     emit(name, error=f"{type(e).__name__}: {e}")
-            for kname in ("FFT",):
-                name = f"{kname}_{aname}_{szs}"
-                if not only or only in name:
-                    emit(name, skipped="Algorithm.FFT() is outside the accelerated path (DESIGN.md, out of scope)")
+            name = f"FFT_{aname}_{szs}"                          # imfilter(img, (Kernel.DoG(twos),), "replicate", Algorithm.FFT())
+            if not only or only in name:
+                try:
+                    fft, kern = ifb.Algorithm.FFT(), (K.DoG(twos),)
+                    host_ms = best_of(lambda: ifb.imfilter(img, kern, "replicate", fft), lambda: None)
+                    raw = img.raw if hasattr(img, "raw") else img
+                    t_in = torch.from_numpy(np.ascontiguousarray(np.asarray(raw).transpose())).cuda()
+                    t_out = torch.empty(t_in.shape, dtype=torch.float64, device="cuda")
+                    d_in = ifb.DeviceArray.from_torch(t_in, n0f8=aname == "N0f8")
+                    d_out = ifb.DeviceArray.from_torch(t_out)
+                    dev_ms = best_of(lambda: ifb.imfilter_(ifb.CUDALibs(fft), d_out, d_in, kern, "replicate"), torch.cuda.synchronize, inner=10)
+                    emit(name, path=lib.last_path(), out_eltype="float64", device_ms=dev_ms, host_ms=host_ms,
+                         device_gpixel_per_s=t_in.numel() / dev_ms / 1e6)
+                except Exception as e:
+                    emit(name, error=f"{type(e).__name__}: {e}")
     # mapwindow group (benchmark/benchmarks.jl:21-35)
     img1d, img2d, img3d = rng.standard_normal(1000), np.asfortranarray(rng.standard_normal((30, 30))), np.asfortranarray(rng.standard_normal((10, 11, 12)))
     for name, f, im, w in (("extrema", ifb.extrema, img2d, (5, 5)), ("maximum", ifb.maximum, img2d, (5, 5)), ("minimum", ifb.minimum, img2d, (5, 5)),

@@ -42,7 +42,7 @@ SYMBOLS = [
     "b2f_memset_async", "b2f_stream_write32", "b2f_stream_wait_geq32",
     "b2f_findlocalextrema", "b2f_scale_into_slice", "b2f_maxabs", "b2f_gather", "b2f_na_prepare", "b2f_divide",
     "b2f_normalize_dims",
-    "b2f_bench_fma_peak", "b2f_set_accum_mode", "b2f_iir", "b2f_launch_count", "b2f_reset_launch_count", "b2f_last_path",
+    "b2f_bench_fma_peak", "b2f_set_accum_mode", "b2f_iir", "b2f_imfilter_fft", "b2f_launch_count", "b2f_reset_launch_count", "b2f_last_path",
 ]
 
 
@@ -185,6 +185,8 @@ class Library:
         d.b2f_memcpy_d2h.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
         d.b2f_set_device.argtypes = [C.c_int]
         d.b2f_set_accum_mode.argtypes = [C.c_int32]
+        d.b2f_imfilter_fft.argtypes = [C.POINTER(b2f_array), C.POINTER(b2f_array), C.POINTER(b2f_stage), C.POINTER(b2f_border),
+                                       C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_void_p]
         d.b2f_iir.argtypes = [C.POINTER(b2f_array), C.POINTER(b2f_array), C.c_int32, C.POINTER(C.c_double), C.POINTER(b2f_border), C.c_void_p]
         d.b2f_device_count.argtypes = [C.POINTER(C.c_int)]
         d.b2f_sm_count.argtypes = [C.POINTER(C.c_int)]
@@ -252,6 +254,14 @@ class Library:
 
     def is_device_library(self) -> bool:
         return bool(self.dll.b2f_is_device_library())
+
+    def imfilter_fft(self, img: b2f_array, out: b2f_array, stages: "StageList", border: b2f_border, roi=None, stream: int = 0):
+        """b2f_imfilter_fft: `stages` holds exactly one dense stage (the convolution of the kernel's factors)."""
+        lo = hi = None
+        if roi is not None:
+            lo = (C.c_int64 * MAXDIM)(*list(roi[0]) + [0] * (MAXDIM - len(roi[0])))
+            hi = (C.c_int64 * MAXDIM)(*list(roi[1]) + [0] * (MAXDIM - len(roi[1])))
+        self.check(self.dll.b2f_imfilter_fft(C.byref(img), C.byref(out), stages.arr, C.byref(border), lo, hi, C.c_void_p(stream)))
 
     def iir(self, img: b2f_array, out: b2f_array, axis: int, coef, border: b2f_border, stream: int = 0):
         """b2f_iir: one Triggs-Sdika recursive pass along `axis` (0-based); coef = TriggsSdika.coefficients() (18 doubles)."""

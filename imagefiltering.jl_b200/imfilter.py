@@ -16,7 +16,7 @@ import warnings
 import numpy as np
 
 from . import _abi
-from ._abi import ArgumentError, DimensionMismatch, NotSupportedError
+from ._abi import ArgumentError, DimensionMismatch, InexactError, NotSupportedError
 from .border import AbstractBorder, Fill, Inner, NA, NoPad, Pad, borderinstance
 from .color import ColorArray, lift_kernel
 from .device import DeviceArray
@@ -24,7 +24,7 @@ from .kernel import Laplacian
 from .kernelfactors import ReshapedOneD, TriggsSdika
 from .n0f8 import N0f8Array, n0f8
 from .offsetarrays import OffsetArray, centered
-from .resources import AbstractResource, Alg, CUDALibs, FIR, FIRTiled, IIR
+from .resources import AbstractResource, Alg, CUDALibs, FFT, FIR, FIRTiled, IIR
 
 STAGE_LAPLACIAN = 2
 
@@ -354,6 +354,57 @@ def _run_iir_na(L, odesc, img_desc, ndim, factors, border):
             L.free(p)
 
 
+# ---- FFT algorithm: src/imfilter.jl:776-888 ---------------------------------------------------------------------------------
+def kernelconv(kernel, ndim):
+    """kernelconv(kernel...) (src/imfilter.jl:1257-1280): the one dense kernel a cascade of factors is equivalent to — the full
+    convolution of the factors, first indices adding up.  Kernel construction on the host, like factorkernel's SVD."""
+    from scipy.signal import convolve
+    acc, first = None, None
+    for k in kernel:
+        if isinstance(k, (Laplacian, TriggsSdika)) or (isinstance(k, ReshapedOneD) and isinstance(k.data, TriggsSdika)):
+            raise NotSupportedError(f"{type(k).__name__} kernels have no array form for the FFT algorithm here")
+        if isinstance(k, ReshapedOneD):
+            if k.N != ndim:
+                raise DimensionMismatch(f"kernel factor is for {k.N}-d arrays, image has {ndim} dims")
+            d = k.dense()
+            p, f = d.parent, tuple(d.first)
+        elif isinstance(k, OffsetArray):
+            p, f = k.parent, tuple(k.first)
+            if p.ndim > ndim:
+                raise DimensionMismatch(f"kernel has {p.ndim} dims, image has {ndim}")
+            p, f = p.reshape(p.shape + (1,) * (ndim - p.ndim)), f + (0,) * (ndim - p.ndim)
+        else:                                   # a plain array inside a tuple keeps its axes 1:n
+            p = np.asarray(k)
+            if p.ndim > ndim:
+                raise DimensionMismatch(f"kernel has {p.ndim} dims, image has {ndim}")
+            f = (1,) * ndim
+            p = p.reshape(p.shape + (1,) * (ndim - p.ndim))
+        if acc is None:
+            acc, first = np.array(p), f
+        else:
+            acc = convolve(acc, p, mode="full", method="direct")
+            first = tuple(a + b for a, b in zip(first, f))
+    return OffsetArray.with_first(np.asfortranarray(acc), first)
+
+
+def _is_fft(r, alg):
+    return isinstance(alg, FFT) or (r is not None and isinstance(getattr(r, "settings", None), FFT))
+
+
+def _run_fft(L, out, desc, ndim, kernel, border, roi):
+    if isinstance(border, NA):
+        raise NotSupportedError("NA() with Algorithm.FFT() is not available")
+    kc = kernelconv(kernel, ndim)
+    p = kc.parent
+    stage = dict(kind=_abi.STAGE_DENSE, ndim=ndim, tap_dtype=_tap_dtype(p.dtype), len=list(p.shape), lo=list(kc.first),
+                 taps=np.asarray(p, dtype=np.float64).reshape(p.shape, order="F"))
+    odesc, keep = _as_output(out)
+    if odesc.ndim != ndim:
+        raise DimensionMismatch(f"out has {odesc.ndim} dims, img has {ndim}")
+    L.imfilter_fft(desc, odesc, _abi.StageList([stage]), border.to_abi(ndim), roi)
+    return stage
+
+
 def imfilter(*args, _library=None):
     """imfilter([r], [T], img, kernel, [border], [alg]) -> filtered array   (src/imfilter.jl:2-49)."""
     args = list(args)
@@ -367,6 +418,19 @@ def imfilter(*args, _library=None):
         raise TypeError("MethodError: a resource and an algorithm cannot both be given")
     r_given = r is not None
     iir = _iir_factors(kernel)
+    if iir is None and _is_fft(r, alg) and not isinstance(img, ColorArray):
+        if r is not None and not isinstance(r, CUDALibs):
+            raise NotSupportedError(f"{r!r}: this package has no CPU execution path")
+        ks = kernel if isinstance(kernel, tuple) else (_kernelshift(kernel) if not isinstance(kernel, (Laplacian, ReshapedOneD)) else kernel,)
+        T = np.dtype(T if T is not None else filter_type(img, ks))
+        if T.kind != "f":
+            raise InexactError(f"Algorithm.FFT() produces floating-point values; eltype {T} cannot hold them (ask for Float64)")
+        desc, ndim, first, shape, keep = _as_input(img)
+        st = [dict(kind=_abi.STAGE_DENSE, ndim=ndim, len=list(kernelconv(ks, ndim).parent.shape), lo=list(kernelconv(ks, ndim).first))]
+        out = allocate_output(T, first, shape, st, border)
+        from ._lib import lib
+        _run_fft(_library if _library is not None else lib(), out, desc, ndim, ks, border, None)
+        return out
     r = _resolve_resource(r, alg, iir is not None)
     if isinstance(img, ColorArray):
         return _imfilter_color(r, T, img, kernel, border, _library)
@@ -455,6 +519,17 @@ def imfilter_(*args, _library=None):
     if r is not None and alg is not None:
         raise TypeError("MethodError: a resource and an algorithm cannot both be given")
     iir = _iir_factors(kernel)
+    if iir is None and _is_fft(r, alg):
+        if r is not None and not isinstance(r, CUDALibs):
+            raise NotSupportedError(f"{r!r}: this package has no CPU execution path")
+        ks = kernel if isinstance(kernel, tuple) else (_kernelshift(kernel) if not isinstance(kernel, (Laplacian, ReshapedOneD)) else kernel,)
+        desc, ndim, first, shape, keep = _as_input(img)
+        roi = None
+        if inds is not None:
+            roi = ([(i.start if isinstance(i, range) else i[0]) for i in inds], [(i.stop - 1 if isinstance(i, range) else i[1]) for i in inds])
+        from ._lib import lib
+        _run_fft(_library if _library is not None else lib(), out, desc, ndim, ks, border, roi)
+        return out
     r = _resolve_resource(r, alg, iir is not None)
     if iir is not None:
         desc, ndim, first, shape, keep = _as_input(img)

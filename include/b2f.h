@@ -382,6 +382,18 @@ int b2f_normalize_dims(const b2f_array *out, const double *const *factors, void 
  * out (_imfilter_inplace_tuple!, :946-960).  A kernel that is a copy (all a, b zero and scale 1, :1254) copies. */
 int b2f_iir(const b2f_array *img, const b2f_array *out, int32_t axis, const double *coef, const b2f_border *border, void *stream);
 
+/* ---- FFT filtering -----------------------------------------------------------------------------------
+ * imfilter!(r::AbstractResource{FFT}, out, img, kernel, border)   replaces src/imfilter.jl:776-888: the image is padded by the
+ * border rule (on the device), the kernel — ONE dense stage, kernelconv(kernel...) of a factored kernel, src/imfilter.jl:1257-1280
+ * — is placed in a zero array of the padded size with periodic indexing, and out = irfft(rfft(A) .* conj(rfft(krn))) restricted
+ * to the requested indices.  The transforms are cuFFT's (loaded on first use; B2F_ENOTSUP when the library is missing), padding,
+ * kernel placement, the spectral product and the crop are this library's kernels.  out is F32 or F64 (= the arithmetic type;
+ * an integer out is B2F_EINEXACT, as the reference's copy into an Int array is); borders as b2f_imfilter (Pad styles, Fill,
+ * Inner); up to 3 transformed axes, later axes the kernel does not touch are a batch.  The result equals b2f_imfilter's up to
+ * the rounding of the transforms (the reference asserts `≈` between its FIR and FFT algorithms, test/2d.jl:69-140). */
+int b2f_imfilter_fft(const b2f_array *img, const b2f_array *out, const b2f_stage *kernel, const b2f_border *border,
+                     const int64_t *roi_lo, const int64_t *roi_hi, void *stream);
+
 /* Measured FP32 multiply-add peak of the current GPU in TFMA/s (a pure fma.rn.f32x2 loop, best of 3, CUDA-event timed): the
  * denominator bench.py reports the dense-kernel path against.  Synchronous.  (The oracle library returns 0.) */
 int b2f_bench_fma_peak(double *tfma_per_s, void *stream);

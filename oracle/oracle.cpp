@@ -1490,3 +1490,17 @@ extern "C" int b2f_iir(const b2f_array *img, const b2f_array *out, int32_t axis,
     return out->dtype == B2F_F32 ? o_iir_typed<float>(img, out, axis, coef, border->style, border->fill)
                                  : o_iir_typed<double>(img, out, axis, coef, border->style, border->fill);
 }
+
+
+// ---- FFT filtering (reference src/imfilter.jl:776-888) -----------------------------------------------------------------------
+// The oracle has no FFT: it returns what the FFT algorithm computes up to rounding, i.e. the exact correlation with the one
+// dense kernel (the reference's own tests assert `≈` between Algorithm.FIR() and Algorithm.FFT(), test/2d.jl:69-140); the GPU
+// tests compare with a tolerance that covers the transforms' rounding.
+extern "C" int b2f_imfilter_fft(const b2f_array *img, const b2f_array *out, const b2f_stage *kernel, const b2f_border *border,
+                                const int64_t *roi_lo, const int64_t *roi_hi, void *stream) {
+    if (!img || !out || !kernel || !border) return fail(B2F_EARG, "NULL argument");
+    if (kernel->kind != B2F_STAGE_DENSE && kernel->kind != B2F_STAGE_1D)
+        return fail(B2F_EARG, "the FFT path takes ONE array kernel (kernelconv of the factors)");
+    if (out->dtype != B2F_F32 && out->dtype != B2F_F64) return fail(B2F_EINEXACT, "FFT filtering produces Float32 / Float64 arrays");
+    return b2f_imfilter(img, out, kernel, 1, border, roi_lo, roi_hi, stream);
+}
