@@ -106,7 +106,7 @@ def test_cpu_resources_are_rejected_not_emulated(ifb):
         with pytest.raises(ifb.NotSupportedError):
             ifb.imfilter(r, img, k)
     with pytest.raises(ifb.NotSupportedError):
-        ifb.imfilter(ifb.CUDALibs(ifb.Algorithm.FFT()), img, k)
+        ifb.imfilter(ifb.CPU1(ifb.Algorithm.FFT()), img, k)       # FFT() runs on the device (b2f_imfilter_fft), never on the CPU
     with pytest.raises(ifb.NotSupportedError):
         ifb.mapwindow(np.std, img, (3, 3))        # arbitrary window functions cannot cross the C ABI (median / mean / sum can: they are kernels)
 
