@@ -142,7 +142,57 @@ stream3d_kernel4(const __grid_constant__ S3Params P, const __grid_constant__ S3V
     const int rt = tma ? min(max(-ya, 0), in_rows) : 0, rb = tma ? min(max(P.H - ya, 0), in_rows) : in_rows;
     if (!tma) cl = cr = in_cols;
     const bool fix = !tma || (P.style != B2F_FILL && (cl > 0 || cr < in_cols || rt > 0 || rb < in_rows));
-    const int ncs = cl + (in_cols - cr), n1 = ncs * in_rows, wc = cr - cl, ncell = fix ? n1 + (rt + (in_rows - rb)) * wc : 0;
+    const int ncs = cl + (in_cols - cr), n1 = ncs * in_rows, wc = cr - cl;
+    // Fast border patch (replicate / reflect / symmetric on 16-byte aligned tile edges): instead of walking a cell list, every
+    // thread owns at most ONE patch item for the whole march, its offsets packed in three registers —
+    //   X item: 4 adjacent out-of-range columns of one tile row <- 4 in-range cells (of the row's source row): 4 LDS.32 + 1 STS.128;
+    //   Y item: 4 adjacent in-range columns of an out-of-range row <- the same columns of its source row:     1 LDS.128 + 1 STS.128.
+    // Both kinds read in-range cells only and write out-of-range cells only, so they need no order among themselves, and ONLY
+    // the threads that own an item wait for the planes' TMA barriers and issue the proxy fence: with the cell list every thread
+    // of a border tile did both in every step, which (not the copies) was what made border tiles slower than interior ones —
+    // and with 3.5 waves of tiles the slowest chain of tiles sets the launch time (1024^3 symmetric: 2.79 -> 2.62 ms; patching
+    // before the arrival or by warp 0 alone were measured worse: 2.68 / 3.11 ms).
+    unsigned fp_a = 0, fp_b = 0, fp_c = 0;       // dst | s0 << 16,  s1 | s2 << 16,  s3 | kind << 16
+    bool fastfix = false;
+    if (fix && tma && P.style != B2F_CIRCULAR) {
+        const int gl = cl >> 2, gr = (in_cols - cr) >> 2, nxg = gl + gr;
+        const int nro = rt + (in_rows - rb), nyg = wc >> 2;
+        const int nx = in_rows * nxg, ny = nro * nyg;
+        int bad = (((cl | cr | in_cols) & 3) != 0 || nx + ny > S3_NT) ? 1 : 0;
+        if (!bad && tid < nx + ny) {
+            int r, c0, kind;
+            if (tid < nx) {
+                r = tid / nxg;
+                const int g = tid - r * nxg;
+                c0 = g < gl ? 4 * g : cr + 4 * (g - gl);
+                kind = 1;
+            } else {
+                const int t2 = tid - nx, rr = t2 / nyg;
+                r = rr < rt ? rr : rb + (rr - rt);
+                c0 = cl + 4 * (t2 - rr * nyg);
+                kind = 2;
+            }
+            const int lr = (int)remap_index(P.style, (int64_t)ya + r, (int64_t)P.H) - ya;
+            if (lr < rt || lr >= rb) bad = 1;
+            int sc[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                int lc = c0 + k;
+                if (kind == 1) {
+                    lc = (int)remap_index(P.style, (int64_t)xa + c0 + k, (int64_t)P.W) - xa;
+                    if (lc < cl || lc >= cr) bad = 1;
+                }
+                sc[k] = lr * S3_RWP + lc;
+            }
+            if (!bad) {
+                fp_a = (unsigned)(r * S3_RWP + c0) | ((unsigned)sc[0] << 16);
+                fp_b = (unsigned)sc[1] | ((unsigned)sc[2] << 16);
+                fp_c = (unsigned)sc[3] | ((unsigned)kind << 16);
+            }
+        }
+        fastfix = __syncthreads_or(bad) == 0;
+    }
+    const int ncell = (fix && !fastfix) ? n1 + (rt + (in_rows - rb)) * wc : 0;
     for (int idx = tid; idx < ncell; idx += S3_NT) {
         int r, c;
         if (idx < n1) {
@@ -229,6 +279,24 @@ stream3d_kernel4(const __grid_constant__ S3Params P, const __grid_constant__ S3V
     // all threads: wait for the TMAs of input planes p .. p+n-1 (n = 1 or 2), then fill in their border cells from the gather
     // list; both planes share one pass over the list (all loads in flight together) and one proxy fence
     auto patch2 = [&](const int p, const int n) {
+        if (fastfix) {                          // only the threads that own a patch item touch the planes (wait, copy, fence)
+            if (fp_c >> 16) {
+                s3_mbar_wait(full + 8 * (p & (N - 1)), (p / N) & 1);
+                if (n > 1) s3_mbar_wait(full + 8 * ((p + 1) & (N - 1)), ((p + 1) / N) & 1);
+                float *d0 = raw + (p & (N - 1)) * RAWSZ, *d1 = raw + ((p + 1) & (N - 1)) * RAWSZ;
+                const int dst = fp_a & 0xffff, s0 = fp_a >> 16;
+                if ((fp_c >> 16) == 1) {
+                    const int s1 = fp_b & 0xffff, s2 = fp_b >> 16, s3 = fp_c & 0xffff;
+                    *reinterpret_cast<float4 *>(d0 + dst) = make_float4(d0[s0], d0[s1], d0[s2], d0[s3]);
+                    if (n > 1) *reinterpret_cast<float4 *>(d1 + dst) = make_float4(d1[s0], d1[s1], d1[s2], d1[s3]);
+                } else {
+                    *reinterpret_cast<float4 *>(d0 + dst) = *reinterpret_cast<const float4 *>(d0 + s0);
+                    if (n > 1) *reinterpret_cast<float4 *>(d1 + dst) = *reinterpret_cast<const float4 *>(d1 + s0);
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            }
+            return;
+        }
         if (tma) {
             s3_mbar_wait(full + 8 * (p & (N - 1)), (p / N) & 1);
             if (n > 1) s3_mbar_wait(full + 8 * ((p + 1) & (N - 1)), ((p + 1) / N) & 1);
