@@ -15,6 +15,7 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <vector>
 
 #include "common.cuh"
 
@@ -194,14 +195,30 @@ static int run_fft_typed(const Plan &P, const b2f_array *img, const void *d_img,
                                                           si.hi[2] - si.lo[2] + 1, si.hi[3] - si.lo[3] + 1, si.lo[0], si.lo[1], si.lo[2], si.lo[3]);
     }
     count_launch(2);
-    int dims[3];
+    int dims[3] = {1, 1, 1};
     for (int d = 0; d < rank; ++d) dims[d] = (int)G.P[rank - 1 - d];                // cuFFT is row-major: slowest axis first
     cufftHandle pf = 0, pk = 0, pi = 0;
+    // plans are cached per thread (creating one costs milliseconds: more than the transforms of a 2048^2 image)
+    struct Cached { int ty, rank, d0, d1, d2, nb, dev; cufftHandle h; };
+    static thread_local std::vector<Cached> cache;
+    int dev = 0;
+    cudaGetDevice(&dev);
     auto plan = [&](cufftHandle *h, cufftType ty, int nb) -> int {
+        for (const Cached &c : cache)
+            if (c.ty == (int)ty && c.rank == rank && c.d0 == dims[0] && c.d1 == dims[1] && c.d2 == dims[2] && c.nb == nb && c.dev == dev) {
+                *h = c.h;
+                return A.SetStream(*h, st) == CUFFT_SUCCESS ? 0 : fail(B2F_ECUDA, "cufftSetStream failed");
+            }
         cufftResult r = A.PlanMany(h, rank, dims, nullptr, 1, 0, nullptr, 1, 0, ty, nb);
         if (r != CUFFT_SUCCESS) return fail(B2F_ECUDA, "cufftPlanMany failed (%d)", (int)r);
         r = A.SetStream(*h, st);
         if (r != CUFFT_SUCCESS) return fail(B2F_ECUDA, "cufftSetStream failed (%d)", (int)r);
+        if (cache.size() >= 12) {                                    // bounded: drop the oldest plan
+            cudaStreamSynchronize(st);
+            A.Destroy(cache.front().h);
+            cache.erase(cache.begin());
+        }
+        cache.push_back({(int)ty, rank, dims[0], dims[1], dims[2], nb, dev, *h});
         return 0;
     };
     int rc = plan(&pf, FftTypes<CT>::fwd, (int)batch);
@@ -233,11 +250,8 @@ static int run_fft_typed(const Plan &P, const b2f_array *img, const void *d_img,
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) rc = fail(B2F_ECUDA, "FFT path launch failed: %s", cudaGetErrorString(e));
     }
-    // the plans own work areas the queued transforms use: wait before destroying them
+    // the cached plans own work areas the queued transforms use: the next call on this thread may run on another stream
     cudaStreamSynchronize(st);
-    if (pf) A.Destroy(pf);
-    if (pk) A.Destroy(pk);
-    if (pi) A.Destroy(pi);
     return rc;
 }
 
