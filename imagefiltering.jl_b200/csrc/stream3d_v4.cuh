@@ -475,22 +475,28 @@ stream3d_kernel4(const __grid_constant__ S3Params P, const __grid_constant__ S3V
         advance();
     };
     // ---- steady state: both planes exist everywhere, both outputs are stored: no predicates ---------------------------------
-    auto fast_step = [&](auto fixc, const int s) {
+    // `emit` = false: the ramp-up steps 0 .. Lz/2 - 1, whose outputs lie before the chunk (everything else as in the steady
+    // state); `all` = false: the drain, where the planes 2s+2 .. 2s+N+1 may not exist any more (bounds checked).  The general
+    // slow_step costs about twice a steady-state step, and ramp-up + drain are 13 of the 72 steps of a 128-plane slab.
+    auto fast_step = [&](auto fixc, const int s, const bool emit, const bool all) {
         constexpr bool FIX = decltype(fixc)::value;
         const int p0 = 2 * s;
         if (!ok) s3_mbar_wait(xfull + 8 * bi, ph);
-        stage_x(p0 + 2, true, true);
-        tma_check(p0, true);
+        stage_x(p0 + 2, all || p0 + 2 < in_planes, all || p0 + 3 < in_planes);
+        tma_check(p0, all);
         arrive_next();
-        tma_work(p0, true);
-        if (FIX) patch2(p0 + 6, 2);
+        tma_work(p0, all);
+        if (FIX) {
+            if (all) patch2(p0 + 6, 2);
+            else if (p0 + 6 < in_planes) patch2(p0 + 6, min(2, in_planes - (p0 + 6)));
+        }
         float2 ma[2], mb[2];
         const unsigned xa0 = xf_sa + (2 * bi * XFSZ + yoff) * 4;
         s3v_y_task4x2<LXT, LYT, LZT>(P, xa0, xa0 + XFSZ * 4, ma, mb, Ly);
         // the next step's barrier is tested here, a z stage ahead of its use: no warp sits out the barrier unit's latency
         ok = s3_mbar_test(xfull + 8 * (bi == 2 ? 0 : bi + 1), bi == 2 ? (ph ^ 1) : ph);
         const float m0[4] = {ma[0].x, ma[0].y, ma[1].x, ma[1].y}, m1[4] = {mb[0].x, mb[0].y, mb[1].x, mb[1].y};
-        s4_z_step<LXT, LYT, LZT, CS, true>(P, TZ, acc, m0, m1, Lz, op, nrow, full4, nrow > 0, nrow > 0);
+        s4_z_step<LXT, LYT, LZT, CS, true>(P, TZ, acc, m0, m1, Lz, op, nrow, full4 && emit, emit && nrow > 0, emit && nrow > 0);
         advance();
     };
 
@@ -509,16 +515,36 @@ stream3d_kernel4(const __grid_constant__ S3Params P, const __grid_constant__ S3V
             if (rb - N - 2 < 0) s_fast1 = s_fast0;
         }
     }
+    // ramp-up on the steady-state code [s_pre0, s_fast0) and drain on it [s_fast1, s_drain): the steps whose two planes and two
+    // outputs exist (xy-filtered boundary planes keep the general step)
+    int s_pre0 = s_fast0, s_drain = s_fast1;
+    if (s_fast1 > s_fast0) {
+        s_pre0 = 0;
+        s_drain = max(s_fast1, min((in_planes - 2) / 2, (nout + Lz - 3) / 2) + 1);
+        if (xy) {
+            const int ra = max(0, P.own_first + (P.xy_lo ? P.xlo_o : 0) - zin0);
+            s_pre0 = min(s_fast0, (ra + 1) >> 1);
+            s_drain = s_fast1;
+        }
+    }
     int s = -1;
-    for (; s < s_fast0; ++s) slow_step(s);
+    for (; s < s_pre0; ++s) slow_step(s);
+    for (; s < s_fast0; ++s) {
+        if (((2 * s + 2) & (S3_PTB - 1)) == 0) locate_block(2 * s + S3_PTA, S3_PTB);
+        if (fix) fast_step(std::true_type{}, s, false, true); else fast_step(std::false_type{}, s, false, true);
+    }
     while (s < s_fast1) {                       // the plane-source table is refilled every 8 steps, outside the inner loop
         if (((2 * s + 2) & (S3_PTB - 1)) == 0) locate_block(2 * s + S3_PTA, S3_PTB);
         const int e = min(s_fast1, (s + 1) | 7);
         if (fix) {
-            for (; s < e; ++s) fast_step(std::true_type{}, s);
+            for (; s < e; ++s) fast_step(std::true_type{}, s, true, true);
         } else {
-            for (; s < e; ++s) fast_step(std::false_type{}, s);
+            for (; s < e; ++s) fast_step(std::false_type{}, s, true, true);
         }
+    }
+    for (; s < s_drain; ++s) {
+        if (((2 * s + 2) & (S3_PTB - 1)) == 0) locate_block(2 * s + S3_PTA, S3_PTB);
+        if (fix) fast_step(std::true_type{}, s, true, false); else fast_step(std::false_type{}, s, true, false);
     }
     for (; s < nsteps; ++s) slow_step(s);
 }
