@@ -394,42 +394,46 @@ static int imfilter_host_pipelined(const b2f_array *img, const b2f_array *out, c
     guard.push_back(d_in);
     B2F_CUDA(cudaMallocAsync((void **)&d_out, out_pb * (size_t)Z, st));
     guard.push_back(d_out);
-    B2F_CUDA(cudaEventRecord(ev_a, st));
-    B2F_CUDA(cudaStreamWaitEvent(hp.s_in, ev_a, 0));
-    B2F_CUDA(cudaStreamWaitEvent(hp.s_out, ev_a, 0));
     const int64_t base = Z / nchunk, extra = Z % nchunk;
     auto first_of = [&](int64_t c) { return c * base + (c < extra ? c : extra); };
-    for (int64_t c = 0; c < nchunk; ++c) {
-        const int64_t z0 = first_of(c), z1 = first_of(c + 1);
-        B2F_CUDA(cudaMemcpyAsync(d_in + (size_t)z0 * in_pb, (const char *)img->ptr + (size_t)z0 * in_pb, (size_t)(z1 - z0) * in_pb,
-                                 cudaMemcpyHostToDevice, hp.s_in));
-        B2F_CUDA(cudaEventRecord(ev_in[c], hp.s_in));
-    }
-    int rc = 0;
-    for (int64_t c = 0; c < nchunk && !rc; ++c) {
-        const int64_t z0 = first_of(c), z1 = first_of(c + 1);
-        B2F_CUDA(cudaStreamWaitEvent(st, ev_in[c + 1 < nchunk ? c + 1 : c], 0));          // the upper halo lives in the next chunk
-        b2f_array a = *img, o = *out;
-        a.mem = o.mem = B2F_DEVICE;
-        a.ptr = d_in + (size_t)z0 * in_pb;
-        o.ptr = d_out + (size_t)z0 * out_pb;
-        a.dims[last] = o.dims[last] = z1 - z0;
-        const int64_t nlo = z0 < h_lo ? z0 : h_lo, nhi = Z - z1 < h_hi ? Z - z1 : h_hi;
-        rc = b2f_imfilter_slab(&a, &o, stages, nstages, border, Z, z0, nlo ? d_in + (size_t)(z0 - nlo) * in_pb : nullptr, nlo,
-                               nhi ? d_in + (size_t)z1 * in_pb : nullptr, nhi, st);
-        if (rc) break;
-        B2F_CUDA(cudaEventRecord(ev_k[c], st));
-        B2F_CUDA(cudaStreamWaitEvent(hp.s_out, ev_k[c], 0));
-        B2F_CUDA(cudaMemcpyAsync((char *)out->ptr + (size_t)z0 * out_pb, d_out + (size_t)z0 * out_pb, (size_t)(z1 - z0) * out_pb,
-                                 cudaMemcpyDeviceToHost, hp.s_out));
-    }
+    // everything that queues work on the side streams runs inside this lambda, so that EVERY exit — error returns included —
+    // passes through the join below before the buffers are released
+    auto run = [&]() -> int {
+        B2F_CUDA(cudaEventRecord(ev_a, st));
+        B2F_CUDA(cudaStreamWaitEvent(hp.s_in, ev_a, 0));
+        B2F_CUDA(cudaStreamWaitEvent(hp.s_out, ev_a, 0));
+        for (int64_t c = 0; c < nchunk; ++c) {
+            const int64_t z0 = first_of(c), z1 = first_of(c + 1);
+            B2F_CUDA(cudaMemcpyAsync(d_in + (size_t)z0 * in_pb, (const char *)img->ptr + (size_t)z0 * in_pb, (size_t)(z1 - z0) * in_pb,
+                                     cudaMemcpyHostToDevice, hp.s_in));
+            B2F_CUDA(cudaEventRecord(ev_in[c], hp.s_in));
+        }
+        for (int64_t c = 0; c < nchunk; ++c) {
+            const int64_t z0 = first_of(c), z1 = first_of(c + 1);
+            B2F_CUDA(cudaStreamWaitEvent(st, ev_in[c + 1 < nchunk ? c + 1 : c], 0));      // the upper halo lives in the next chunk
+            b2f_array a = *img, o = *out;
+            a.mem = o.mem = B2F_DEVICE;
+            a.ptr = d_in + (size_t)z0 * in_pb;
+            o.ptr = d_out + (size_t)z0 * out_pb;
+            a.dims[last] = o.dims[last] = z1 - z0;
+            const int64_t nlo = z0 < h_lo ? z0 : h_lo, nhi = Z - z1 < h_hi ? Z - z1 : h_hi;
+            int rc = b2f_imfilter_slab(&a, &o, stages, nstages, border, Z, z0, nlo ? d_in + (size_t)(z0 - nlo) * in_pb : nullptr, nlo,
+                                       nhi ? d_in + (size_t)z1 * in_pb : nullptr, nhi, st);
+            if (rc) return rc;
+            B2F_CUDA(cudaEventRecord(ev_k[c], st));
+            B2F_CUDA(cudaStreamWaitEvent(hp.s_out, ev_k[c], 0));
+            B2F_CUDA(cudaMemcpyAsync((char *)out->ptr + (size_t)z0 * out_pb, d_out + (size_t)z0 * out_pb, (size_t)(z1 - z0) * out_pb,
+                                     cudaMemcpyDeviceToHost, hp.s_out));
+        }
+        return 0;
+    };
+    const int rc = run();
     // join: nothing may outlive the call (the buffers are freed on st, the caller owns the host arrays again)
-    cudaEventRecord(ev_done, hp.s_out);
-    cudaStreamWaitEvent(st, ev_done, 0);
-    cudaEventRecord(ev_done, hp.s_in);
-    cudaStreamWaitEvent(st, ev_done, 0);
+    cudaStreamSynchronize(hp.s_in);
+    cudaStreamSynchronize(hp.s_out);
     cudaError_t e = cudaStreamSynchronize(st);
-    if (rc) return rc < 0 ? rc : -rc;
+    (void)ev_done;
+    if (rc) return rc;
     if (e != cudaSuccess) return fail(B2F_ECUDA, "stream sync failed: %s", cudaGetErrorString(e));
     return 1;
 }
