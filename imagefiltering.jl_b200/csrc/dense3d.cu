@@ -164,12 +164,8 @@ static int run_dense3d_typed(const Plan &P0, const void *d_img, int img_dt, void
     guard.push_back(d_taps);
     B2F_CUDA(cudaMemcpyAsync(d_taps, h.data(), ntap * sizeof(CT), cudaMemcpyHostToDevice, st));
     P.taps = d_taps;
-    static thread_local bool attr_set[2] = {false, false};
-    bool &as = attr_set[sizeof(CT) == 4 ? 0 : 1];
-    if (!as) {
+    if (smem > 48 * 1024)                        // per launch: the attribute belongs to the current device's copy of the kernel
         B2F_CUDA(cudaFuncSetAttribute(dense3d_kernel<CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D3_SMEM_MAX));
-        as = true;
-    }
     dense3d_kernel<CT><<<(unsigned)blocks, D3_NT, smem, st>>>(P);
     count_launch(1);
     B2F_CUDA(cudaGetLastError());

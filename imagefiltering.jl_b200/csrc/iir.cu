@@ -68,16 +68,29 @@ __global__ void __launch_bounds__(128) iir_strided_kernel(const void *__restrict
     p1 = iir_step<T>(X(2), K.a1, p2, K.a2, p3, K.a3, uminus);
     o[0] = p3; o[W] = p2; o[2 * W] = p1;
     long long i = 3;
-    constexpr int PF = 8;                          // pixel loads run PF elements ahead of the recurrence
-    for (; i + PF <= n - 1; i += PF) {
-        T x[PF];
+    // the pixel loads run one batch of PF elements ahead of the recurrence (double-buffered in registers): with a few thousand
+    // lines there are not enough warps to hide a DRAM round trip per batch behind other warps
+    constexpr int PF = 8;
+    if (i + PF <= n - 1) {
+        T x[PF], xn[PF];
 #pragma unroll
         for (int u = 0; u < PF; ++u) x[u] = X(i + u);
+        for (; i + PF <= n - 1; i += PF) {
+            const bool more = i + 2 * PF <= n - 1;
+            if (more) {
 #pragma unroll
-        for (int u = 0; u < PF; ++u) {
-            const T t = iir_step<T>(x[u], K.a1, p1, K.a2, p2, K.a3, p3);
-            p3 = p2; p2 = p1; p1 = t;
-            o[(i + u) * W] = t;
+                for (int u = 0; u < PF; ++u) xn[u] = X(i + PF + u);
+            }
+#pragma unroll
+            for (int u = 0; u < PF; ++u) {
+                const T t = iir_step<T>(x[u], K.a1, p1, K.a2, p2, K.a3, p3);
+                p3 = p2; p2 = p1; p1 = t;
+                o[(i + u) * W] = t;
+            }
+            if (more) {
+#pragma unroll
+                for (int u = 0; u < PF; ++u) x[u] = xn[u];
+            }
         }
     }
     for (; i <= n - 2; ++i) {
@@ -94,15 +107,26 @@ __global__ void __launch_bounds__(128) iir_strided_kernel(const void *__restrict
     // backward pass (reads this thread's own forward values back), scaling folded in: q1 = v[i+1], q2 = v[i+2], q3 = v[i+3]
     T q1 = v3, q2 = v2, q3 = v1;
     i = n - 4;
-    for (; i - (PF - 1) >= 0; i -= PF) {
-        T u[PF];
+    if (i - (PF - 1) >= 0) {
+        T u[PF], un[PF];
 #pragma unroll
         for (int k = 0; k < PF; ++k) u[k] = o[(i - k) * W];
+        for (; i - (PF - 1) >= 0; i -= PF) {
+            const bool more = i - PF - (PF - 1) >= 0;
+            if (more) {
 #pragma unroll
-        for (int k = 0; k < PF; ++k) {
-            const T t = iir_step<T>(u[k], K.b1, q1, K.b2, q2, K.b3, q3);
-            q3 = q2; q2 = q1; q1 = t;
-            o[(i - k) * W] = mul_rn<T>(t, K.scale);
+                for (int k = 0; k < PF; ++k) un[k] = o[(i - PF - k) * W];
+            }
+#pragma unroll
+            for (int k = 0; k < PF; ++k) {
+                const T t = iir_step<T>(u[k], K.b1, q1, K.b2, q2, K.b3, q3);
+                q3 = q2; q2 = q1; q1 = t;
+                o[(i - k) * W] = mul_rn<T>(t, K.scale);
+            }
+            if (more) {
+#pragma unroll
+                for (int k = 0; k < PF; ++k) u[k] = un[k];
+            }
         }
     }
     for (; i >= 0; --i) {
@@ -134,6 +158,22 @@ __global__ void __launch_bounds__(IIR_WPB * 32) iir_rows_kernel(const void *__re
         }
         __syncwarp();
     };
+    // the next panel travels in registers while the current one is filtered (a warp has nothing else to hide the round trip)
+    T pre[32];
+    auto fetch = [&](long long c0, bool from_out) {
+        const int nc = (int)min(32LL, n - c0);
+#pragma unroll
+        for (int r = 0; r < 32; ++r) {
+            const long long idx = (row0 + r) * n + c0 + lane;
+            pre[r] = (T)0;
+            if (r < nr && lane < nc) pre[r] = from_out ? out[idx] : load_elem<T>(img, img_dt, idx);
+        }
+    };
+    auto commit = [&]() {
+#pragma unroll
+        for (int r = 0; r < 32; ++r) tile[lane][r] = pre[r];
+        __syncwarp();
+    };
     auto store_panel = [&](long long c0) {
         __syncwarp();
         const int nc = (int)min(32LL, n - c0);
@@ -149,8 +189,10 @@ __global__ void __launch_bounds__(IIR_WPB * 32) iir_rows_kernel(const void *__re
     const T x0 = load_elem<T>(img, img_dt, myrow), xlast = load_elem<T>(img, img_dt, myrow + n - 1);
     const T uminus = (K.use_fill ? K.fill : x0) / K.oma;
     T p1 = uminus, p2 = uminus, p3 = uminus;        // u[-1] = u[-2] = u[-3] = uminus reproduces leftborder! term by term
+    fetch(0, false);
     for (long long c0 = 0; c0 < n; c0 += 32) {
-        load_panel(c0, false);
+        commit();
+        if (c0 + 32 < n) fetch(c0 + 32, false);
         const int nc = (int)min(32LL, n - c0);
         if (mine) {
             for (int c = 0; c < nc; ++c) {
@@ -168,8 +210,10 @@ __global__ void __launch_bounds__(IIR_WPB * 32) iir_rows_kernel(const void *__re
     }
     // backward pass over the panels, last first; elements n-1, n-2, n-3 take v1, v2, v3
     T q1 = 0, q2 = 0, q3 = 0;
+    fetch(((n - 1) / 32) * 32, true);
     for (long long c0 = ((n - 1) / 32) * 32; c0 >= 0; c0 -= 32) {
-        load_panel(c0, true);
+        commit();
+        if (c0 >= 32) fetch(c0 - 32, true);
         const int nc = (int)min(32LL, n - c0);
         if (mine) {
             for (int c = nc - 1; c >= 0; --c) {

@@ -297,12 +297,8 @@ int run_longtap(const void *src, int src_dt, CT *dst, const double *taps, int64_
         return fail(B2F_ENOTSUP, "longtap: array too large for one launch");
     const int Lp = ((int)L + 8) & ~7;
     const size_t smem = (size_t)Lp * sizeof(CT) * (sizeof(CT) == 4 ? 3 : 1) + (size_t)(LT_TO + Lp + 8) * LT_PITCH * sizeof(CT);
-    static thread_local bool attr_set[2] = {false, false};
-    bool &as = attr_set[sizeof(CT) == 4 ? 0 : 1];
-    if (!as) {
+    if (smem > 48 * 1024)                        // per launch: the attribute belongs to the current device's copy of the kernel
         B2F_CUDA(cudaFuncSetAttribute(longtap_kernel<CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
-        as = true;
-    }
     longtap_kernel<CT><<<(unsigned)blocks, LT_NT, smem, st>>>(P);
     count_launch(1);
     B2F_CUDA(cudaGetLastError());
