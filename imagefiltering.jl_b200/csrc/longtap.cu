@@ -17,12 +17,15 @@
 //     separate multiply and add in tap order (the reference's arithmetic, src/imfilter.jl:732-737), window of 16 per 8 taps.
 // Roofline: one pass moves sizeof(in) + sizeof(out) bytes per element and issues L multiply-adds; at 41 taps Float32 the FP32
 // pipe (128 FMA / clk / SM) and HBM are within 15 % of each other.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace b2f {
 
 constexpr int LT_MAXL = 256, LT_MINL = 18;
-constexpr int LT_NT = 256, LT_TO = 128, LT_PITCH = 33;
+constexpr int LT_NT = 256, LT_TO = 128, LT_PITCH = 33;     // (LT_TO = 256 gains 4 % on 8192^2 and loses 40 % on 100^3)
+constexpr int LT_NG = LT_TO / 64;            // groups of 8 outputs per warp
 
 template <typename CT>
 struct LtParams {
@@ -141,6 +144,67 @@ __device__ __forceinline__ void lt_load_tile(const LtParams<CT> &P, CT *tile, co
     const IT *src = reinterpret_cast<const IT *>(P.src);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     auto conv = [](IT x) -> CT { return N0 ? N0f8Conv<CT>::f((unsigned)x) : (CT)x; };
+    // source eltype == compute type (Float32 -> Float32, Float64 -> Float64; every pass after the first): the cells go from global
+    // to shared memory with cp.async — all of a thread's ~24 cells in flight at once, no staging registers, one wait
+    if (std::is_same<IT, CT>::value && !N0) {
+        auto cp_cell = [](CT *dst, const IT *g) {
+            const unsigned sa = (unsigned)__cvta_generic_to_shared(dst);
+            if (sizeof(CT) == 4) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(g) : "memory");
+            else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(g) : "memory");
+        };
+        // interior tiles (no border, all 32 lines present): straight pointer walks, no remap, no predicates per cell
+        const long long axis_len = P.along_x ? P.W : P.Ag;
+        const long long first_pos = (P.along_x ? 0 : P.a_first) + out0 + P.klo;
+        const bool interior = first_pos >= 0 && first_pos + npos <= axis_len && line0 + 32 <= nlines &&
+                              (P.along_x || (first_pos - P.a_first >= 0 && first_pos - P.a_first + npos <= P.H));
+        if (interior && P.along_x) {
+            for (int ln = warp; ln < 32; ln += LT_NT / 32) {
+                const IT *g = src + (line0 + ln) * P.W + first_pos + lane;
+                CT *d = tile + lane * LT_PITCH + ln;
+                int q = lane;
+                for (; q < npos; q += 32, g += 32, d += 32 * LT_PITCH) cp_cell(d, g);
+                for (; q < npos_pad; q += 32, d += 32 * LT_PITCH) *d = (CT)0;
+            }
+        } else if (interior) {
+            const IT *g = src + (b * P.H + (first_pos - P.a_first) + warp) * P.W + line0 + lane;
+            CT *d = tile + warp * LT_PITCH + lane;
+            const long long gs = (long long)(LT_NT / 32) * P.W;
+            int q = warp;
+            for (; q < npos; q += LT_NT / 32, g += gs, d += (LT_NT / 32) * LT_PITCH) cp_cell(d, g);
+            for (; q < npos_pad; q += LT_NT / 32, d += (LT_NT / 32) * LT_PITCH) *d = (CT)0;
+        } else if (P.along_x) {
+            const int Wi = (int)P.W, p0 = out0 + P.klo;
+            for (int ln = warp; ln < 32; ln += LT_NT / 32) {
+                const long long row = line0 + ln;
+                const bool rowok = row < nlines;
+                const IT *rp = src + (rowok ? row * P.W : 0);
+                for (int q = lane; q < npos_pad; q += 32) {
+                    int a = -3;
+                    if (q < npos && rowok) a = lt_remap(P.style, p0 + q, Wi);
+                    CT *d = tile + q * LT_PITCH + ln;
+                    if (a >= 0) cp_cell(d, rp + a); else *d = a == -1 ? P.fill : (CT)0;
+                }
+            }
+        } else {
+            const long long xg = line0 + lane;
+            const bool xin = xg < nlines;
+            const int Hi = (int)P.H, Agi = (int)P.Ag, af = (int)P.a_first, p0 = af + out0 + P.klo;
+            const IT *cp = src + b * P.H * P.W + (xin ? xg : 0);
+            for (int q = warp; q < npos_pad; q += LT_NT / 32) {
+                int a = -3;
+                if (q < npos && xin) {
+                    int r = lt_remap(P.style, p0 + q, Agi);
+                    if (r >= 0) r -= af;
+                    a = (r >= 0 && r < Hi) ? r : -1;
+                }
+                CT *d = tile + q * LT_PITCH + lane;
+                if (a >= 0) cp_cell(d, cp + (long long)a * P.W); else *d = a == -1 ? P.fill : (CT)0;
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        return;
+    }
     if (P.along_x) {
         // lines = rows (stride W), positions contiguous: lanes run along the positions (coalesced), smem [pos][line]
         constexpr int UB = 6;
@@ -230,19 +294,16 @@ __global__ void __launch_bounds__(LT_NT) longtap_kernel(const __grid_constant__ 
         default: lt_load_tile<double, false>(P, tile, line0, out0, b, nlines, npos, npos_pad); break;
     }
     __syncthreads();
-    // ---- compute: group g = 8 consecutive outputs; 16 groups per tile, two per warp -----------------------------------------
-    CT res[2][8];
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        const int g = warp + 8 * h;
-        lt_line8(tile + (8 * g) * LT_PITCH + lane, k, kp, L, res[h]);
-    }
+    // ---- compute: group g = 8 consecutive outputs; LT_TO / 8 groups per tile, LT_NG per warp ------------------------------------
     const int oend = (int)(P.o0 + P.on);
-    if (!P.along_x) {
+    if (!P.along_x) {                               // lane = x: one coalesced row per output
         const long long x = line0 + lane;
+        CT res[LT_NG][8];
+#pragma unroll
+        for (int h = 0; h < LT_NG; ++h) lt_line8(tile + (8 * (warp + 8 * h)) * LT_PITCH + lane, k, kp, L, res[h]);
         if (x < nlines) {
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
+            for (int h = 0; h < LT_NG; ++h) {
                 const int o = out0 + 8 * (warp + 8 * h);
                 CT *dp = P.dst + ((b * P.on + (o - (int)P.o0)) * P.W + x);
 #pragma unroll
@@ -250,22 +311,22 @@ __global__ void __launch_bounds__(LT_NT) longtap_kernel(const __grid_constant__ 
                     if (o + i < oend) *dp = res[h][i];
             }
         }
-    } else {
-        __syncthreads();                            // every warp is done reading the tile: reuse its first 128 positions
+    } else {                                        // lane = row: the results go back through the transposed tile
+        CT res[LT_NG][8];
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
+        for (int h = 0; h < LT_NG; ++h) lt_line8(tile + (8 * (warp + 8 * h)) * LT_PITCH + lane, k, kp, L, res[h]);
+        __syncthreads();                            // every warp is done reading the tile: reuse its first LT_TO positions
+#pragma unroll
+        for (int h = 0; h < LT_NG; ++h) {
             const int g = warp + 8 * h;
 #pragma unroll
             for (int i = 0; i < 8; ++i) tile[(8 * g + i) * LT_PITCH + lane] = res[h][i];
         }
         __syncthreads();
-        const int o = out0 + tid % LT_TO;                       // a thread stores one output position of 16 lines
-        if (o < oend) {
-#pragma unroll 4
-            for (int ln = tid / LT_TO; ln < 32; ln += LT_NT / LT_TO) {
-                const long long row = line0 + ln;
-                if (row < nlines) P.dst[row * P.on + (o - (int)P.o0)] = tile[(tid % LT_TO) * LT_PITCH + ln];
-            }
+        for (int idx = tid; idx < 32 * LT_TO; idx += LT_NT) {   // lanes along the positions: coalesced stores
+            const int ln = idx / LT_TO, q = idx - ln * LT_TO;
+            const long long row = line0 + ln;
+            if (row < nlines && out0 + q < oend) P.dst[row * P.on + (out0 + q - (int)P.o0)] = tile[q * LT_PITCH + ln];
         }
     }
 }
@@ -298,7 +359,7 @@ int run_longtap(const void *src, int src_dt, CT *dst, const double *taps, int64_
     const int Lp = ((int)L + 8) & ~7;
     const size_t smem = (size_t)Lp * sizeof(CT) * (sizeof(CT) == 4 ? 3 : 1) + (size_t)(LT_TO + Lp + 8) * LT_PITCH * sizeof(CT);
     if (smem > 48 * 1024)                        // per launch: the attribute belongs to the current device's copy of the kernel
-        B2F_CUDA(cudaFuncSetAttribute(longtap_kernel<CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
+        B2F_CUDA(cudaFuncSetAttribute(longtap_kernel<CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     longtap_kernel<CT><<<(unsigned)blocks, LT_NT, smem, st>>>(P);
     count_launch(1);
     B2F_CUDA(cudaGetLastError());
