@@ -130,6 +130,7 @@ static int run_pass(const int64_t *dims, const StageInfo *sx, const StageInfo *s
     P.out_ox = 0; P.out_oy = (int)ry0;
     P.out_pitch = W; P.out_plane = W * P.rh;
     P.style = style; P.fill = fill;
+    P.fma = accum_mode() == B2F_ACCUM_FMA;      // honoured by the fused x+y pass for the instantiated tap counts (b2f_set_accum_mode)
     P.Lx = 1; P.Ly = 1;
     if (sx) {
         P.Lx = (int)sx->s->len[0]; P.klox = (int)sx->lo[0];
