@@ -341,7 +341,9 @@ int b2f_imfilter_sharded(b2f_shard_ctx *ctx, const b2f_array *img, const b2f_arr
     // 8 GPUs: 0.598 vs 0.499 ms; profiles/r2_sharded_xy_ab.jsonl).  The decision depends on the environment, the kernel and the
     // plane shape only, so every rank of the pass takes the same branch.
     static const bool xy_env = getenv("B2F_SHARD_XY") && atoi(getenv("B2F_SHARD_XY")) == 1;
-    if (xy_env && c.xy_ok && (use_lo || use_hi) && nd == 3 && img->dtype == B2F_F32 && out->dtype == B2F_F32) {
+    // (two-sided cascades only: with a one-sided one the last rank consumes no halo but would still have to publish its
+    // boundary planes — h_lo / h_hi are properties of the kernel, so this test, too, is the same on every rank)
+    if (xy_env && c.xy_ok && (use_lo || use_hi) && h_lo > 0 && h_hi > 0 && nd == 3 && img->dtype == B2F_F32 && out->dtype == B2F_F32) {
         b2f_array gi = *img, go = *out;
         gi.dims[2] = go.dims[2] = global_last_dim;
         gi.ptr = go.ptr = nullptr;

@@ -114,10 +114,11 @@ class ShardedImfilter:
         circ = isinstance(border, Pad) and border.style == "circular"
         self.lower = self.rank - 1 if self.rank > 0 else (self.world - 1 if circ and self.world > 1 else None)
         self.upper = self.rank + 1 if self.rank + 1 < self.world else (0 if circ and self.world > 1 else None)
-        if self.h_lo == 0:
-            self.lower = None
-        if self.h_hi == 0:
-            self.upper = None
+        # The neighbour relation is SYMMETRIC: a rank hand-shakes with both adjacent ranks as soon as the cascade reaches along
+        # the sharded axis in either direction (a one-sided kernel makes rank r need planes of r+1 while r+1 needs none of r's —
+        # r+1 must still tell r that its input is complete).  Transfers of zero planes are skipped on both sides.
+        if self.h_lo == 0 and self.h_hi == 0:
+            self.lower = self.upper = None
         for nb, need in ((self.lower, self.h_lo), (self.upper, self.h_hi)):
             if nb is not None and counts[nb] < need:
                 raise DimensionMismatch(f"rank {nb} owns {counts[nb]} planes but its neighbour needs a halo of {need}")
@@ -226,9 +227,10 @@ class ShardedImfilter:
         n = self.slab.shape[0]
         # gloo moves host memory only: CUDA slabs are staged through host copies there (tests; NCCL sends in place)
         stage = self.slab.is_cuda and not self._nccl
-        send_lo = self.slab[:self.h_hi] if self.lower is not None else None           # -> lower neighbour's hi halo
-        send_hi = self.slab[n - self.h_lo:] if self.upper is not None else None       # -> upper neighbour's lo halo
-        recv_hi, recv_lo = self.recv_hi, self.recv_lo
+        send_lo = self.slab[:self.h_hi] if (self.lower is not None and self.h_hi > 0) else None          # -> lower neighbour's hi halo
+        send_hi = self.slab[n - self.h_lo:] if (self.upper is not None and self.h_lo > 0) else None      # -> upper neighbour's lo halo
+        recv_hi = self.recv_hi if (self.recv_hi is not None and self.h_hi > 0) else None
+        recv_lo = self.recv_lo if (self.recv_lo is not None and self.h_lo > 0) else None
         if stage:
             send_lo = send_lo.cpu() if send_lo is not None else None
             send_hi = send_hi.cpu() if send_hi is not None else None
@@ -338,14 +340,18 @@ class ShardedImfilter:
             early = min(nrows, (-(-self.lib.sm_count() // tiles_x) + 1) * 64)               # tile rows of the first wave (+1 for the halo rows)
             if early >= nrows:
                 early = 0
-        if self.lower is not None:
+        if self.lower is not None and self.h_lo > 0:
             if early:
                 self.lib.memcpy2d_async(self.halo_lo_ptr, plane_bytes, self.peer_lo_ptr, plane_bytes, early * row_bytes, self.h_lo, side)
                 self.lib.memset_async(flags, self._epoch, 1, side)
         if self.upper is not None:
-            self.lib.memcpy_async(self.halo_hi_ptr, self.peer_hi_ptr, self.h_hi * plane_bytes, side)
+            if self.h_hi > 0:
+                self.lib.memcpy_async(self.halo_hi_ptr, self.peer_hi_ptr, self.h_hi * plane_bytes, side)
             self.lib.memset_async(flags + 2, self._epoch, 1, side)
-        if self.lower is not None:
+        if self.lower is not None and self.h_lo == 0:
+            self.lib.memset_async(flags, self._epoch, 1, side)
+            self.lib.memset_async(flags + 1, self._epoch, 1, side)
+        if self.lower is not None and self.h_lo > 0:
             if early:
                 self.lib.memcpy2d_async(self.halo_lo_ptr + early * row_bytes, plane_bytes, self.peer_lo_ptr + early * row_bytes,
                                         plane_bytes, (nrows - early) * row_bytes, self.h_lo, side)
@@ -463,10 +469,8 @@ class ShardedMapwindow:
         # (copy_win!, src/mapwindow.jl:310-333), so a window at a face of the array never sees the opposite face
         self.lower = self.rank - 1 if self.rank > 0 else None
         self.upper = self.rank + 1 if self.rank + 1 < self.world else None
-        if self.h_lo == 0:
-            self.lower = None
-        if self.h_hi == 0:
-            self.upper = None
+        if self.h_lo == 0 and self.h_hi == 0:       # symmetric neighbour relation, as in ShardedImfilter
+            self.lower = self.upper = None
         if self.world > 1 and min(counts) <= max(self.h_lo, self.h_hi):
             raise DimensionMismatch(f"every rank must own more planes than the window reaches ({max(self.h_lo, self.h_hi)}); counts = {counts}")
         self.n_lo = self.h_lo if self.lower is not None else 0

@@ -29,6 +29,13 @@ def cases(ifb):
     out.append(("f32-3d-tma17", np.float32, (128, 96, 48), g((4, 4, 4)), "circular", None))
     out.append(("f32-3d-tma17-sym", np.float32, (64, 96, 40), g((4, 4, 4)), "symmetric", None))   # xy-filtered exchange at the faces
     out.append(("f32-3d-tma5-fill0", np.float32, (64, 88, 30), g((1, 1, 1)), ifb.Fill(0.0), None))
+    # one-sided factors along the sharded axis: rank r needs planes of r+1 only (or of r-1 only); the neighbour relation and the
+    # hand-shake stay symmetric, transfers of zero planes are skipped
+    up = ifb.ReshapedOneD(3, 2, ifb.OffsetArray.with_first(rng.random(3), (0,)))
+    down = ifb.ReshapedOneD(3, 2, ifb.OffsetArray.with_first(rng.random(5), (-4,)))
+    out.append(("f64-3d-onesided-up", np.float64, (20, 12, 21), (g((1, 1, 0))[0], g((1, 1, 0))[1], up), "replicate", None))
+    out.append(("f64-3d-onesided-down", np.float64, (20, 12, 21), (g((1, 1, 0))[0], down), "symmetric", None))
+    out.append(("f32-3d-tma-onesided", np.float32, (64, 80, 30), (g((1, 1, 0))[0], g((1, 1, 0))[1], up), "reflect", None))
     out.append(("f32-2d", np.float32, (33, 29), g((1, 2)), "reflect", None))
     out.append(("f32-3d-uneven", np.float32, (20, 12, 31), g((1, 1, 2)), "circular", [20, 11]))
     out.append(("f64-3d-xy-only", np.float64, (20, 12, 16), (g((1, 1, 0))[0], g((1, 1, 0))[1]), "replicate", None))
@@ -50,6 +57,8 @@ def run(rank, world, port, use_device, modes, errq, env=None):
             torch.cuda.set_device(0)
         failures = []
         for name, T, shape, kern, border, counts in cases(ifb):
+            if "onesided" in name and os.environ.get("B2F_SHARD_XY") == "1":
+                continue                        # the xy-filtered exchange takes two-sided cascades (csrc/sharded.cu); nothing new to test
             rng = np.random.default_rng(sum(map(ord, name)))
             whole = np.asfortranarray(rng.random(shape).astype(T))          # Julia order (X, Y, Z)
             ref = ifb.imfilter(T, whole, kern, border, _library=oracle)
@@ -112,8 +121,12 @@ def run_mapwindow(rank, world, port, use_device, modes, errq, env=None):
                  ("mean-f32-3d", ifb.mean, np.float32, (18, 14, 25), (3, 3, 5), "replicate"),
                  ("sum-u8-3d", sum, np.uint8, (18, 14, 25), (3, 1, 3), "symmetric"),
                  ("median-f64-3d", ifb.median, np.float64, (12, 10, 22), (3, 3, 3), "replicate"),
-                 ("ext-f32-3d-noz", ifb.extrema, np.float32, (30, 20, 12), (7, 7, 1), "replicate")]
+                 ("ext-f32-3d-noz", ifb.extrema, np.float32, (30, 20, 12), (7, 7, 1), "replicate"),
+                 ("max-f64-3d-onesided", ifb.maximum, np.float64, (14, 9, 23), (range(0, 1), range(-1, 2), range(0, 3)), "replicate"),
+                 ("min-i32-3d-onesided", ifb.minimum, np.int32, (14, 9, 23), (range(0, 1), range(0, 1), range(-4, 1)), "symmetric")]
         for name, f, T, shape, window, border in cases:
+            if "onesided" in name and use_device:
+                continue                        # what one-sided windows change is host logic (neighbours, message matching): CPU suite
             rng = np.random.default_rng(sum(map(ord, name)))
             whole = np.asfortranarray((rng.random(shape) * 200).astype(T))
             ref = ifb.mapwindow(f, whole, window, border=border, _library=oracle)
