@@ -432,6 +432,20 @@ def imfilter(*args, _library=None):
         _run_fft(_library if _library is not None else lib(), out, desc, ndim, ks, border, None)
         return out
     r = _resolve_resource(r, alg, iir is not None)
+    if isinstance(img, ColorArray) and iir is not None:
+        # colour image, IIR kernel (test/triggs.jl:45-60, imgc): every channel is filtered along the spatial axes, i.e. the
+        # channel-leading (C, dims...) array along axes 1 .. N; Fill(value) fills every channel with the same value
+        raw = n0f8(img.data) if img.data.dtype == np.uint8 else img.data
+        T = np.dtype(T if T is not None else filter_type(raw, kernel))
+        desc, ndim, first, shape, keep = _as_input(raw)
+        factors = [(ax + 1, k) for ax, k in _iir_factors(kernel, ndim - 1)]
+        out = allocate_output(T, first, shape, [], Pad("replicate"))
+        from ._lib import lib
+        b = _iir_border(border)
+        if isinstance(b, NA):
+            raise NotSupportedError("NA() on colour images with IIR kernels is not available")
+        _run_iir(_library if _library is not None else lib(), _as_output(out)[0], desc, ndim, factors, b)
+        return ColorArray(out)
     if isinstance(img, ColorArray):
         return _imfilter_color(r, T, img, kernel, border, _library)
     if iir is not None:

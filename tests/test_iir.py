@@ -149,3 +149,20 @@ def test_gpu_iir_bit_exact(ifb, oracle, device, dt, border):
         a = ifb.imfilter(im, (k, k), ifb.NA())
         o = ifb.imfilter(im, (k, k), ifb.NA(), _library=oracle)
         assert np.array_equal(a, o, equal_nan=True)
+
+
+def test_triggs_colour_image(ifb, oracle):
+    """test/triggs.jl:45-60, `imgc = fill(RGB{Float64}(0,0,0), 5, 7); imgc[3,4] = RGB(1,0,0)`: the red channel is the filtered
+    impulse, the others stay zero, the input is untouched."""
+    data = np.zeros((3, 5, 7))
+    data[0, 2, 3] = 1.0
+    img = ifb.ColorArray(data)
+    sigma = 5
+    x, y = np.arange(-2, 3)[:, None], np.arange(-3, 4)[None, :]
+    cmp_ = np.exp(-(x ** 2 + y ** 2) / (2 * sigma ** 2)) / (sigma ** 2 * 2 * np.pi)
+    filt = ifb.imfilter(img, ifb.KernelFactors.IIRGaussian((sigma, sigma)), ifb.Fill(0), _library=oracle)
+    assert isinstance(filt, ifb.ColorArray) and filt.data.shape == (3, 5, 7)
+    assert np.sum((cmp_ - filt.data[0]) ** 2) < 0.2 ** 2 * np.sum(cmp_ ** 2)
+    assert not filt.data[1:].any() and data[0, 2, 3] == 1.0
+    gray = ifb.imfilter(np.ascontiguousarray(data[0]), ifb.KernelFactors.IIRGaussian((sigma, sigma)), ifb.Fill(0), _library=oracle)
+    assert np.array_equal(filt.data[0], gray)
